@@ -1,0 +1,656 @@
+// fused_step.cuh -- the fused warp-group transition kernel for N <= 256 (sm_100a).
+//
+// One environment is owned by a group of LPE lanes (LPE in {4,8,16,32}; 32/LPE envs per warp), each
+// lane holding APL consecutive agents in registers (blocked layout -> vectorised int16 / u8 HBM
+// access).  A single pass over HBM performs, per env (reference: swarm_discrete_env.py "SDE"):
+//   move + wrap (SDE:237-244, 60-80) -> collision detect + re-draw rounds (SDE:246-255, 269-292)
+//   -> predator retarget/pursuit on the OLD positions (SDE:258-259, 111-165)
+//   -> termination test on the NEW positions (SDE:307-309, 321-327)
+//   -> pairwise attraction / repulsion counts + alignment (SDE:330-379), N-body style: the env's
+//      positions are staged in shared memory as packed 16x2 "pair words" and every lane sweeps them
+//      with DPX VIADDMNMX.S16x2 ops, two pairs per instruction
+//   -> reward epilogue, episode statistics, in-kernel auto-reset (SDE:197-221, 90-109).
+// All cross-lane traffic is warp shuffles restricted to the env's lane group; no __syncthreads.
+#pragma once
+#include "swarm_common.cuh"
+
+namespace swarm {
+
+template <int LPE>
+struct Seg {
+  unsigned mask;
+  int li, seg;
+  __device__ __forceinline__ Seg() {
+    const int lane = threadIdx.x & 31;
+    seg = lane / LPE;
+    li = lane % LPE;
+    mask = (LPE == 32) ? 0xFFFFFFFFu : (((1u << LPE) - 1u) << (seg * LPE));
+  }
+  __device__ __forceinline__ int sum(int v) const {
+#pragma unroll
+    for (int d = LPE / 2; d > 0; d >>= 1) v += __shfl_xor_sync(mask, v, d, LPE);
+    return v;
+  }
+  __device__ __forceinline__ unsigned umin(unsigned v) const {
+#pragma unroll
+    for (int d = LPE / 2; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(mask, v, d, LPE));
+    return v;
+  }
+  // exclusive prefix sum over the group's lanes; total = group sum
+  __device__ __forceinline__ int excl_scan(int v, int& total) const {
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < LPE; d <<= 1) {
+      const int t = __shfl_up_sync(mask, inc, d, LPE);
+      if (li >= d) inc += t;
+    }
+    total = __shfl_sync(mask, inc, LPE - 1, LPE);
+    return inc - v;
+  }
+  __device__ __forceinline__ bool any(bool pred) const { return (__ballot_sync(mask, pred) & mask) != 0u; }
+  __device__ __forceinline__ unsigned bcast(unsigned v, int src) const { return __shfl_sync(mask, v, src, LPE); }
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+
+// ---- vectorised per-lane loads / stores of APL consecutive elements -------------------------------
+template <int APL>
+__device__ __forceinline__ void load_i16(const int16_t* __restrict__ p, int i0, int N, bool vec, int (&out)[APL]) {
+  if (vec && i0 < N) {     // N % APL == 0 and i0 % APL == 0: the whole vector is inside the env
+    if constexpr (APL == 1) {
+      out[0] = p[i0];
+    } else if constexpr (APL == 2) {
+      const unsigned v = *reinterpret_cast<const unsigned*>(p + i0);
+      out[0] = (int16_t)(v & 0xFFFF); out[1] = (int16_t)(v >> 16);
+    } else if constexpr (APL == 4) {
+      const uint2 v = *reinterpret_cast<const uint2*>(p + i0);
+      out[0] = (int16_t)(v.x & 0xFFFF); out[1] = (int16_t)(v.x >> 16);
+      out[2] = (int16_t)(v.y & 0xFFFF); out[3] = (int16_t)(v.y >> 16);
+    } else {
+      static_assert(APL == 8, "APL");
+      const uint4 v = *reinterpret_cast<const uint4*>(p + i0);
+      out[0] = (int16_t)(v.x & 0xFFFF); out[1] = (int16_t)(v.x >> 16);
+      out[2] = (int16_t)(v.y & 0xFFFF); out[3] = (int16_t)(v.y >> 16);
+      out[4] = (int16_t)(v.z & 0xFFFF); out[5] = (int16_t)(v.z >> 16);
+      out[6] = (int16_t)(v.w & 0xFFFF); out[7] = (int16_t)(v.w >> 16);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < APL; ++k) out[k] = (i0 + k < N) ? (int)p[i0 + k] : 0;
+  }
+}
+
+template <int APL>
+__device__ __forceinline__ void store_i16(int16_t* __restrict__ p, int i0, int N, bool vec, const int (&v)[APL]) {
+  if (vec && i0 < N) {
+    if constexpr (APL == 1) {
+      p[i0] = (int16_t)v[0];
+    } else if constexpr (APL == 2) {
+      *reinterpret_cast<unsigned*>(p + i0) = pack2(v[0], v[1]);
+    } else if constexpr (APL == 4) {
+      *reinterpret_cast<uint2*>(p + i0) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
+    } else {
+      *reinterpret_cast<uint4*>(p + i0) =
+          make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < APL; ++k)
+      if (i0 + k < N) p[i0 + k] = (int16_t)v[k];
+  }
+}
+
+template <int APL>
+__device__ __forceinline__ void load_u8(const uint8_t* __restrict__ p, int i0, int N, bool vec, int (&out)[APL]) {
+  if (vec && i0 < N) {
+    if constexpr (APL == 1) {
+      out[0] = p[i0];
+    } else if constexpr (APL == 2) {
+      const unsigned v = *reinterpret_cast<const uint16_t*>(p + i0);
+      out[0] = v & 0xFF; out[1] = v >> 8;
+    } else if constexpr (APL == 4) {
+      const unsigned v = *reinterpret_cast<const unsigned*>(p + i0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) out[k] = (v >> (8 * k)) & 0xFF;
+    } else {
+      const uint2 v = *reinterpret_cast<const uint2*>(p + i0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { out[k] = (v.x >> (8 * k)) & 0xFF; out[4 + k] = (v.y >> (8 * k)) & 0xFF; }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < APL; ++k) out[k] = (i0 + k < N) ? (int)p[i0 + k] : 8;
+  }
+}
+
+template <int APL>
+__device__ __forceinline__ void store_u8(uint8_t* __restrict__ p, int i0, int N, bool vec, const int (&v)[APL]) {
+  if (vec && i0 < N) {
+    if constexpr (APL == 1) {
+      p[i0] = (uint8_t)v[0];
+    } else if constexpr (APL == 2) {
+      *reinterpret_cast<uint16_t*>(p + i0) = (uint16_t)(v[0] | (v[1] << 8));
+    } else if constexpr (APL == 4) {
+      *reinterpret_cast<unsigned*>(p + i0) = (unsigned)(v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24));
+    } else {
+      *reinterpret_cast<uint2*>(p + i0) = make_uint2((unsigned)(v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24)),
+                                                     (unsigned)(v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24)));
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < APL; ++k)
+      if (i0 + k < N) p[i0 + k] = (uint8_t)v[k];
+  }
+}
+
+// ---- exact occupancy counts c_i (SDE:269-292) by an all-pairs sweep over smem keys ---------------
+// skey: this env's NMAX-word key region.  c[k] = number of agents on agent k's cell (1 = alone).
+template <int LPE, int APL>
+__device__ __forceinline__ void occupancy_counts(const Seg<LPE>& g, unsigned* skey, int N, int i0,
+                                                 const int (&cx)[APL], const int (&cy)[APL], int (&c)[APL]) {
+  unsigned key[APL];
+#pragma unroll
+  for (int k = 0; k < APL; ++k) {
+    key[k] = (i0 + k < N) ? pack2(cx[k], cy[k]) : (0xFFFF0000u | (unsigned)(i0 + k));
+    skey[i0 + k] = key[k];
+    c[k] = 0;
+  }
+  g.sync();
+  for (int j = 0; j < N; ++j) {
+    const unsigned kj = skey[j];
+#pragma unroll
+    for (int k = 0; k < APL; ++k) c[k] += (kj == key[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < APL; ++k)
+    if (i0 + k >= N) c[k] = 1;
+  g.sync();
+}
+
+// ---- "is any cell shared?" via a per-env occupancy bitmap in smem (S*S bits) ---------------------
+template <int LPE, int APL>
+__device__ __forceinline__ bool bitmap_any_collision(const Seg<LPE>& g, unsigned* sbit, int N, int S, int i0,
+                                                     const int (&cx)[APL], const int (&cy)[APL]) {
+  bool hit = false;
+  int word[APL];
+#pragma unroll
+  for (int k = 0; k < APL; ++k) {
+    word[k] = -1;
+    if (i0 + k < N) {
+      const int cell = cy[k] * S + cx[k];
+      word[k] = cell >> 5;
+      const unsigned bit = 1u << (cell & 31);
+      const unsigned old = atomicOr(&sbit[word[k]], bit);
+      hit |= (old & bit) != 0u;
+    }
+  }
+  const bool any = g.any(hit);   // ballot also orders the atomics before the clears below
+  g.sync();
+#pragma unroll
+  for (int k = 0; k < APL; ++k)
+    if (word[k] >= 0) sbit[word[k]] = 0u;
+  g.sync();
+  return any;
+}
+
+// ---- nearest agent to (qx,qy) with the canonical tie rule (SDE:111-131) --------------------------
+template <int LPE, int APL>
+__device__ __forceinline__ int closest_target(const Seg<LPE>& g, int N, int S, int i0, int qx, int qy,
+                                              const int (&ax)[APL], const int (&ay)[APL]) {
+  unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;
+#pragma unroll
+  for (int k = 0; k < APL; ++k) {
+    if (i0 + k < N) {
+      const int d = max(iabs(qx - ax[k]), iabs(qy - ay[k]));
+      klo = min(klo, nn_key_lo(d, i0 + k));
+      khi = min(khi, nn_key_hi(d, i0 + k));
+    }
+  }
+  klo = g.umin(klo);
+  khi = g.umin(khi);
+  return nn_pick(klo, khi, S);
+}
+
+// ---- reference reset (SDE:197-221 + Predator.__init__ SDE:90-109) for one env group ---------------
+template <int LPE, int APL>
+__device__ __noinline__ void reset_group(const StepParams& p, const Seg<LPE>& g, int env, unsigned* skey, int i0,
+                                         int (&x)[APL], int (&y)[APL], int& px, int& py, int& target,
+                                         unsigned& err) {
+  const int N = p.N, S = p.S;
+  unsigned rc = p.reset_count[env];
+  g.sync();   // every lane has read reset_count before lane 0 bumps it
+  if (g.li == 0) p.reset_count[env] = rc + 1u;
+  const size_t slot = (size_t)(rc % (unsigned)p.R) * (size_t)p.E + (size_t)env;
+  const int16_t* __restrict__ tape = p.place + slot * (size_t)p.PL;
+#pragma unroll
+  for (int k = 0; k < APL; ++k) {
+    const bool v = i0 + k < N;
+    x[k] = v ? (int)tape[i0 + k] : 0;          // SDE:202-203: all x's then all y's
+    y[k] = v ? (int)tape[N + i0 + k] : 0;
+  }
+  int cur = 2 * N;
+  for (;;) {
+    int c[APL];
+    occupancy_counts<LPE, APL>(g, skey, N, i0, x, y, c);
+    int extra = 0;
+#pragma unroll
+    for (int k = 0; k < APL; ++k) extra += c[k] - 1;
+    int L;
+    int off = g.excl_scan(extra, L);
+    if (L == 0) break;
+    if (cur + 2 * L > p.PL) { err |= SWARM_ERR_PLACE_OVERFLOW; break; }
+#pragma unroll
+    for (int k = 0; k < APL; ++k) {
+      const int e = c[k] - 1;
+      if (e > 0) {                                // SDE:208-209: (2,L) block, last duplicate wins
+        const int s = off + e - 1;
+        x[k] = tape[cur + s];
+        y[k] = tape[cur + L + s];
+      }
+      off += e;
+    }
+    cur += 2 * L;
+  }
+  const int16_t* __restrict__ pt = p.ptape + slot * (size_t)p.KP * 2;
+  int a = 0;
+  px = 0; py = 0;
+  for (;;) {                                      // SDE:92-105
+    if (a >= p.KP) { err |= SWARM_ERR_PRED_OVERFLOW; break; }
+    px = pt[2 * a]; py = pt[2 * a + 1];
+    ++a;
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < APL; ++k) hit |= (i0 + k < N) && x[k] == px && y[k] == py;
+    if (!g.any(hit)) break;
+  }
+  target = closest_target<LPE, APL>(g, N, S, i0, px, py, x, y);   // SDE:109
+}
+
+// ---- the fused step kernel ------------------------------------------------------------------------
+template <int LPE, int APL>
+struct FusedCfg {
+  static constexpr int EPW = 32 / LPE;       // envs per warp
+  static constexpr int NMAX = LPE * APL;     // agents per env capacity
+  static constexpr int PW = NMAX / 2;        // pair words per env
+  static constexpr int WARPS = 8;            // warps per CTA
+  // bytes of smem per warp: pair words (aliased by the collision keys) + VF words + bitmap
+  __host__ __device__ static constexpr int pair_bytes() { return EPW * PW * 16; }
+  __host__ __device__ static constexpr int vf_bytes() { return EPW * NMAX * 8; }
+};
+
+template <int LPE, int APL, bool HAS_VF>
+__global__ void __launch_bounds__(FusedCfg<LPE, APL>::WARPS * 32)
+fused_step_kernel(const __grid_constant__ StepParams p) {
+  using C = FusedCfg<LPE, APL>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const Seg<LPE> g;
+  const int env = (blockIdx.x * C::WARPS + warp) * C::EPW + g.seg;
+  const int N = p.N, S = p.S;
+
+  // smem carve-up (per warp, then per env group)
+  const int warp_bytes = C::pair_bytes() + (HAS_VF ? C::vf_bytes() : 0) + C::EPW * p.bitmap_words * 4;
+  unsigned char* wbase = smem_raw + (size_t)warp * warp_bytes;
+  uint4* spw = reinterpret_cast<uint4*>(wbase) + g.seg * C::PW;
+  unsigned* skey = reinterpret_cast<unsigned*>(spw);   // aliases the pair words (NMAX words <= PW*4 words)
+  uint2* svf = reinterpret_cast<uint2*>(wbase + C::pair_bytes()) + g.seg * C::NMAX;
+  unsigned* sbit = reinterpret_cast<unsigned*>(wbase + C::pair_bytes() + (HAS_VF ? C::vf_bytes() : 0)) +
+                   g.seg * p.bitmap_words;
+  if (p.bitmap_words) {
+    for (int w = g.li; w < p.bitmap_words; w += LPE) sbit[w] = 0u;
+  }
+  if (env >= p.E) return;
+  g.sync();
+
+  const int i0 = g.li * APL;
+  const size_t base = (size_t)env * (size_t)N;
+  const bool vec = (N % APL) == 0;
+
+  if (p.frozen[env]) {                      // SDE:233-234: finished episode, auto-reset off
+    if (g.li == 0) {
+      p.err[env] |= SWARM_ERR_STEP_WHEN_DONE;
+      p.done[env] = 1;
+      p.eaten[env] = -1;
+      p.counts[2 * env] = 0; p.counts[2 * env + 1] = 0;
+      p.consumed[env] = 0;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) p.reward[5 * env + q] = 0.f;
+    }
+    return;
+  }
+
+  int x[APL], y[APL], act[APL];
+  load_i16<APL>(p.x + base, i0, N, vec, x);
+  load_i16<APL>(p.y + base, i0, N, vec, y);
+  load_u8<APL>(p.actions + base, i0, N, vec, act);
+  int px = p.px[env], py = p.py[env];
+  int target = p.target[env];
+  const int retarget = p.retarget[env];
+  unsigned err = 0;
+
+  // ---- move + collision re-draw rounds (SDE:237-255) --------------------------------------------
+  int eff[APL], nx[APL], ny[APL];
+  {
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < APL; ++k) { bad |= act[k] > 8; eff[k] = min(act[k], 8); }
+    if (g.any(bad)) err |= SWARM_ERR_BAD_ACTION;
+  }
+  int cur = 0;
+  const uint8_t* __restrict__ slab = p.slab + (size_t)env * (size_t)p.K;
+  for (;;) {
+#pragma unroll
+    for (int k = 0; k < APL; ++k) {
+      nx[k] = wrap1(x[k] + move_dx(eff[k]), S);          // SDE:60-80
+      ny[k] = wrap1(y[k] + move_dy(eff[k]), S);
+    }
+    if (p.bitmap_words) {
+      if (!bitmap_any_collision<LPE, APL>(g, sbit, N, S, i0, nx, ny)) break;
+    }
+    int c[APL];
+    occupancy_counts<LPE, APL>(g, skey, N, i0, nx, ny, c);
+    int extra = 0;
+#pragma unroll
+    for (int k = 0; k < APL; ++k) extra += c[k] - 1;
+    int L;
+    int off = g.excl_scan(extra, L);
+    if (L == 0) break;                                   // change_position_id returned None
+    if (cur + L > p.K) { err |= SWARM_ERR_SLAB_OVERFLOW; break; }
+#pragma unroll
+    for (int k = 0; k < APL; ++k) {
+      const int e = c[k] - 1;
+      if (e > 0) eff[k] = slab[cur + off + e - 1] & 7;   // SDE:250-252: last of its c-1 draws wins
+      off += e;
+    }
+    cur += L;
+  }
+
+  // ---- predator (SDE:258-259, 133-165) on the OLD agent positions ------------------------------
+  const int prev_px = px, prev_py = py;
+  if (retarget) target = closest_target<LPE, APL>(g, N, S, i0, px, py, x, y);
+  target = min(max(target, 0), N - 1);
+  int orient;
+  {
+    const int lt = target / APL, kt = target % APL;
+    unsigned mine = 0;
+#pragma unroll
+    for (int k = 0; k < APL; ++k)
+      if (k == kt) mine = pack2(x[k], y[k]);
+    const unsigned tp = g.bcast(mine, lt);
+    pursue(px, py, (int)(int16_t)(tp & 0xFFFFu), (int)(int16_t)(tp >> 16), S, px, py, orient);
+  }
+  const int step_target = target;
+
+  // ---- termination (SDE:307-309, 321-327) on the NEW positions ---------------------------------
+  unsigned hit = 0xFFFFu;
+#pragma unroll
+  for (int k = 0; k < APL; ++k)
+    if (i0 + k < N && nx[k] == px && ny[k] == py) hit = min(hit, (unsigned)(i0 + k));
+  hit = g.umin(hit);
+  const bool done = hit != 0xFFFFu;
+  const int eaten = done ? (int)hit : -1;
+
+  // ---- reward (SDE:330-379) ---------------------------------------------------------------------
+  double r_surv = 0.0, r_att = 0.0, r_rep = 0.0, r_ali = 0.0, r_sum = 0.0;
+  int g_rep = 0, g_att = 0;
+  if (!done) {
+    // stage the env's positions as packed pair words {x2, y2, -x2, -y2}; padding agents sit at x=-S
+    int sx[APL], sy[APL];
+#pragma unroll
+    for (int k = 0; k < APL; ++k) {
+      const bool v = i0 + k < N;
+      sx[k] = v ? nx[k] : -S;
+      sy[k] = v ? ny[k] : 0;
+    }
+    if constexpr (APL == 1) {
+      const unsigned mine = pack2(sx[0], sy[0]);
+      const unsigned oth = __shfl_xor_sync(g.mask, mine, 1, LPE);
+      if ((g.li & 1) == 0) {
+        const int ox = (int)(int16_t)(oth & 0xFFFFu), oy = (int)(int16_t)(oth >> 16);
+        spw[g.li >> 1] = make_uint4(pack2(sx[0], ox), pack2(sy[0], oy), pack2(-sx[0], -ox), pack2(-sy[0], -oy));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < APL; k += 2)
+        spw[(i0 + k) >> 1] = make_uint4(pack2(sx[k], sx[k + 1]), pack2(sy[k], sy[k + 1]),
+                                        pack2(-sx[k], -sx[k + 1]), pack2(-sy[k], -sy[k + 1]));
+    }
+    if constexpr (HAS_VF) {
+#pragma unroll
+      for (int k = 0; k < APL; ++k) {
+        const int a = eff[k];
+        const bool mover = (i0 + k < N) && a < 8;
+        const int mx = mover ? move_dx(a) : 0, my = mover ? move_dy(a) : 0;
+        const bool diag = (a & 1) != 0;
+        svf[i0 + k] = make_uint2(pack2((diag ? 0 : mx) + 1, (diag ? 0 : my) + 1),
+                                 pack2((diag ? mx : 0) + 1, (diag ? my : 0) + 1));
+      }
+    }
+    g.sync();
+
+    unsigned XI[APL], YI[APL], NXI[APL], NYI[APL];
+    unsigned aR[APL], aA[APL], aRf[APL], aAf[APL];
+    unsigned aV[APL], accA[APL], accD[APL];
+#pragma unroll
+    for (int k = 0; k < APL; ++k) {
+      XI[k] = rep2(sx[k]); YI[k] = rep2(sy[k]); NXI[k] = rep2(-sx[k]); NYI[k] = rep2(-sy[k]);
+      aR[k] = aA[k] = aRf[k] = aAf[k] = 0u;
+      aV[k] = accA[k] = accD[k] = 0u;
+    }
+    const unsigned TR = rep2(p.t_rep), TA = rep2(p.t_att), TRf = rep2(p.t_repf), TAf = rep2(p.t_attf);
+    const unsigned TV = rep2(HAS_VF ? p.t_vf : 0);
+    const int NW = (N + 1) >> 1;
+#pragma unroll 2
+    for (int q = 0; q < NW; ++q) {
+      const uint4 w = spw[q];
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if constexpr (HAS_VF) u = *reinterpret_cast<const uint4*>(&svf[2 * q]);
+#pragma unroll
+      for (int k = 0; k < APL; ++k) {
+        const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], w);
+        aR[k] += lt2(TR, m);
+        aA[k] += lt2(TA, m);
+        aRf[k] += lt2(TRf, m);
+        aAf[k] += lt2(TAf, m);
+        if constexpr (HAS_VF) {
+          const unsigned gate = lt2(TV, m);
+          const unsigned g0 = gate & 0xFFFFu, g1 = gate >> 16;
+          aV[k] += gate;
+          accA[k] += g0 * u.x + g1 * u.z;
+          accD[k] += g0 * u.y + g1 * u.w;
+        }
+      }
+    }
+
+    // alignment sums (SDE:346-359)
+    int Ax = 0, Ay = 0, Dx = 0, Dy = 0;
+    if constexpr (!HAS_VF) {
+      int ax = 0, ay = 0, dx = 0, dy = 0;
+#pragma unroll
+      for (int k = 0; k < APL; ++k) {
+        const int a = eff[k];
+        if (i0 + k < N && a < 8) {
+          const int mx = move_dx(a), my = move_dy(a);
+          if (a & 1) { dx += mx; dy += my; } else { ax += mx; ay += my; }
+        }
+      }
+      // two biased 16-bit fields per word keep the group reduction at 2 words
+      const unsigned s1 = (unsigned)g.sum((int)pack2(ax + APL, ay + APL));
+      const unsigned s2 = (unsigned)g.sum((int)pack2(dx + APL, dy + APL));
+      Ax = (int)(s1 & 0xFFFFu) - C::NMAX; Ay = (int)(s1 >> 16) - C::NMAX;
+      Dx = (int)(s2 & 0xFFFFu) - C::NMAX; Dy = (int)(s2 >> 16) - C::NMAX;
+    }
+
+    const int selfR = p.t_rep >= 1, selfA = p.t_att >= 1, selfRf = p.t_repf >= 1, selfAf = p.t_attf >= 1;
+    const int selfV = HAS_VF ? (p.t_vf >= 1) : 1;
+    int s_rep = 0, s_att = 0, s_P = 0, s_Q = 0, s_vis = 0;
+    int rep_i[APL], att_i[APL];
+    double una_i[APL];
+#pragma unroll
+    for (int k = 0; k < APL; ++k) {
+      const bool v = i0 + k < N;
+      int vis, P, Q;
+      if constexpr (HAS_VF) {
+        const int vin = hsum2(aV[k]);                       // gated count incl. self
+        const int gAx = (int)(accA[k] & 0xFFFFu) - vin, gAy = (int)(accA[k] >> 16) - vin;
+        const int gDx = (int)(accD[k] & 0xFFFFu) - vin, gDy = (int)(accD[k] >> 16) - vin;
+        vis = vin - selfV;
+        align_PQ(eff[k], gAx, gAy, gDx, gDy, selfV, P, Q);
+      } else {
+        vis = N - 1;
+        align_PQ(eff[k], Ax, Ay, Dx, Dy, 1, P, Q);
+      }
+      const AgentTerms t = agent_terms(p, hsum2(aR[k]) - selfR, hsum2(aA[k]) - selfA, hsum2(aRf[k]) - selfRf,
+                                       hsum2(aAf[k]) - selfAf, vis, P, Q);
+      rep_i[k] = v ? t.rep_i : 0;
+      att_i[k] = v ? t.att_i : 0;
+      una_i[k] = v ? t.una : 0.0;
+      if (v) { s_rep += t.rep_i; s_att += t.att_i; s_P += P; s_Q += Q; s_vis += vis; }
+    }
+    g_rep = g.sum(s_rep);
+    g_att = g.sum(s_att);
+    const int g_P = g.sum(s_P), g_Q = g.sum(s_Q);
+    const int g_vis = HAS_VF ? g.sum(s_vis) : N * (N - 1);
+    const double g_una = 0.5 * (double)g_vis - 0.25 * (double)g_P - 0.35355339059327376220 * (double)g_Q;
+    r_rep = p.w_rep * (double)g_rep * p.inv_nn;             // SDE:363-366
+    r_att = p.w_att * (double)g_att * p.inv_nn;
+    r_ali = p.w_ali * (-g_una) * p.inv_nn;
+    r_sum = r_rep + r_att + r_ali;
+
+    if (p.agent_reward) {                                   // SDE:371-379
+      float4* __restrict__ ar = reinterpret_cast<float4*>(p.agent_reward) + base;
+#pragma unroll
+      for (int k = 0; k < APL; ++k) {
+        if (i0 + k < N) {
+          const double a_rep = p.w_rep * (double)rep_i[k] * p.inv_nn;
+          const double a_att = p.w_att * (double)att_i[k] * p.inv_nn;
+          const double a_ali = p.w_ali * (-una_i[k]) * p.inv_nn;
+          ar[i0 + k] = make_float4((float)a_att, (float)a_rep, (float)a_ali, (float)(a_rep + a_att + a_ali));
+        }
+      }
+    }
+    if (p.agent_counts) {
+      int2* __restrict__ ac = reinterpret_cast<int2*>(p.agent_counts) + base;
+#pragma unroll
+      for (int k = 0; k < APL; ++k)
+        if (i0 + k < N) ac[i0 + k] = make_int2(rep_i[k], att_i[k]);
+    }
+    g.sync();   // pair words are dead; the reset path reuses the region as keys
+  } else {
+    r_surv = (double)p.eat;
+    r_sum = (double)p.eat;
+    if (p.agent_reward) {
+      float4* __restrict__ ar = reinterpret_cast<float4*>(p.agent_reward) + base;
+#pragma unroll
+      for (int k = 0; k < APL; ++k)
+        if (i0 + k < N) ar[i0 + k] = make_float4(0.f, 0.f, 0.f, (i0 + k == eaten) ? p.eat : 0.f);
+    }
+    if (p.agent_counts) {
+      int2* __restrict__ ac = reinterpret_cast<int2*>(p.agent_counts) + base;
+#pragma unroll
+      for (int k = 0; k < APL; ++k)
+        if (i0 + k < N) ac[i0 + k] = make_int2(0, 0);
+    }
+  }
+  if (p.eff_action) store_u8<APL>(p.eff_action + base, i0, N, vec, eff);
+
+  // ---- per-env outputs ---------------------------------------------------------------------------
+  if (g.li == 0) {
+    p.done[env] = done ? 1 : 0;
+    p.eaten[env] = eaten;
+    float* rw = p.reward + 5 * (size_t)env;
+    rw[0] = (float)r_surv; rw[1] = (float)r_att; rw[2] = (float)r_rep; rw[3] = (float)r_ali; rw[4] = (float)r_sum;
+    p.counts[2 * env] = g_rep;
+    p.counts[2 * env + 1] = g_att;
+    p.pred_prev[2 * env] = (int16_t)prev_px; p.pred_prev[2 * env + 1] = (int16_t)prev_py;
+    p.pred_next[2 * env] = (int16_t)px; p.pred_next[2 * env + 1] = (int16_t)py;
+    p.step_orient[env] = (uint8_t)orient;
+    p.step_target[env] = step_target;
+    p.consumed[env] = cur;
+    if (p.track_stats) {
+      const unsigned len = p.ep_len[env] + 1u;
+      float4 ret = reinterpret_cast<float4*>(p.ep_ret)[env];
+      ret.x += (float)r_surv; ret.y += (float)r_att; ret.z += (float)r_rep; ret.w += (float)r_ali;
+      if (done) {
+        p.fin_count[env] += 1u;
+        p.fin_len[env] += len;
+        float4 f = reinterpret_cast<float4*>(p.fin_ret)[env];
+        f.x += ret.x; f.y += ret.y; f.z += ret.z; f.w += ret.w;
+        reinterpret_cast<float4*>(p.fin_ret)[env] = f;
+        p.ep_len[env] = 0u;
+        reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        p.ep_len[env] = len;
+        reinterpret_cast<float4*>(p.ep_ret)[env] = ret;
+      }
+    }
+  }
+
+  // ---- commit / auto-reset (SDE:260; reset semantics SDE:197-221) -----------------------------
+  if (done) {
+    if (p.term_x) {
+      store_i16<APL>(p.term_x + base, i0, N, vec, nx);
+      store_i16<APL>(p.term_y + base, i0, N, vec, ny);
+    }
+    if (p.auto_reset) {
+      reset_group<LPE, APL>(p, g, env, skey, i0, nx, ny, px, py, target, err);
+      orient = 0;                                           // SDE:107
+    } else if (g.li == 0) {
+      p.frozen[env] = 1;
+    }
+  }
+  store_i16<APL>(p.x + base, i0, N, vec, nx);
+  store_i16<APL>(p.y + base, i0, N, vec, ny);
+  if (g.li == 0) {
+    p.px[env] = (int16_t)px;
+    p.py[env] = (int16_t)py;
+    p.target[env] = target;
+    p.orient[env] = (uint8_t)orient;
+    if (err) p.err[env] |= err;
+  }
+}
+
+// ---- reset kernel: every env (mask == nullptr) or the masked envs ----------------------------------
+template <int LPE, int APL>
+__global__ void __launch_bounds__(FusedCfg<LPE, APL>::WARPS * 32)
+fused_reset_kernel(const __grid_constant__ StepParams p, const uint8_t* __restrict__ mask, int zero_counts) {
+  using C = FusedCfg<LPE, APL>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const Seg<LPE> g;
+  const int env = (blockIdx.x * C::WARPS + warp) * C::EPW + g.seg;
+  if (env >= p.E) return;
+  if (mask && !mask[env]) return;
+  unsigned* skey = reinterpret_cast<unsigned*>(smem_raw) + (warp * C::EPW + g.seg) * C::NMAX;
+  const int N = p.N;
+  const int i0 = g.li * APL;
+  const size_t base = (size_t)env * (size_t)N;
+  const bool vec = (N % APL) == 0;
+  if (zero_counts) {
+    if (g.li == 0) p.reset_count[env] = 0u;
+    g.sync();
+  }
+  int x[APL], y[APL], px, py, target;
+  unsigned err = 0;
+  reset_group<LPE, APL>(p, g, env, skey, i0, x, y, px, py, target, err);
+  store_i16<APL>(p.x + base, i0, N, vec, x);
+  store_i16<APL>(p.y + base, i0, N, vec, y);
+  if (g.li == 0) {
+    p.px[env] = (int16_t)px;
+    p.py[env] = (int16_t)py;
+    p.target[env] = target;
+    p.orient[env] = 0;
+    p.frozen[env] = 0;
+    p.err[env] = err;
+    if (p.track_stats) {
+      p.ep_len[env] = 0u;
+      reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (zero_counts) {
+        p.fin_count[env] = 0u;
+        p.fin_len[env] = 0u;
+        reinterpret_cast<float4*>(p.fin_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+}
+
+}  // namespace swarm

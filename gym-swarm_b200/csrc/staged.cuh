@@ -1,0 +1,812 @@
+// staged.cuh -- the staged transition for large N (N > 256, up to 16384 agents per env) and the
+// standalone roofline kernels named by the C ABI (swarm_move / swarm_predator / swarm_pairwise).
+//
+//   K1 move_kernel        flat, 128-bit vectorised; HBM bound         SDE:60-80, 467-475
+//   K2 collide_kernel     CTA per env, exact occupancy counts via a global (L2-resident) hash
+//                         table + block scan for the re-draw slots     SDE:246-255, 269-292
+//   K3 predator_kernel    warp per env, shuffle argmin, pursuit, termination test
+//                                                                       SDE:111-165, 307-309
+//   K4 pairprep_kernel    packs positions into 16x2 "pair words"
+//   K5 pairwise_kernel    persistent, statically partitioned (env, i-tile, j-chunk) units; the j-chunk
+//                         is staged in shared memory by a TMA bulk copy (cp.async.bulk + mbarrier,
+//                         double buffered) and swept with DPX VIADDMNMX.S16x2 ops   SDE:330-343
+//   K6 finalize_kernel    CTA per env: reward epilogue, statistics, commit   SDE:363-379, 260
+//   K7 reset_kernel       CTA per env (masked): reference reset            SDE:197-221, 90-109
+//
+// (SDE = /root/reference/gym_swarm/envs/swarm_discrete_env.py)
+#pragma once
+#include "swarm_common.cuh"
+
+namespace swarm {
+
+constexpr unsigned HASH_EMPTY = 0xFFFFFFFFu;
+
+// Scratch owned by the library for the staged path.
+struct StagedScratch {
+  int16_t *nx, *ny;        // [E,N] candidate / new positions
+  uint8_t* eff;            // [E,N] effective action
+  unsigned* hash;          // [grid][2*HS] {keys[HS], counts[HS]}
+  unsigned* aslot;         // [grid][N] hash slot of each agent
+  int log2hs;
+  int env_grid;            // CTAs of the per-env kernels
+  uint4* pairw;            // [E,NW] packed pair words
+  uint2* vfw;              // [E,2*NW] (VF) packed unit-vector words
+  unsigned* pcounts;       // [E,N,8] per-agent accumulators {cR,cA,cRf,cAf,cV,accA,accD,-}
+  int NW;
+};
+
+// ------------------------------------------------------------------------------------------------
+// block-level helpers (blockDim.x multiple of 32, <= 1024)
+// ------------------------------------------------------------------------------------------------
+struct BlockScratch {
+  int warp_vals[32];
+  int bcast[4];
+  unsigned ubcast[4];
+};
+
+__device__ __forceinline__ int block_excl_scan(int v, int& total, BlockScratch& bs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) bs.warp_vals[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = lane < nw ? bs.warp_vals[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+      if (lane >= d) winc += t;
+    }
+    bs.warp_vals[lane] = winc - w;
+    if (lane == 31) bs.bcast[0] = winc;
+  }
+  __syncthreads();
+  total = bs.bcast[0];
+  return bs.warp_vals[warp] + inc - v;
+}
+
+__device__ __forceinline__ int block_sum(int v, BlockScratch& bs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+  __syncthreads();
+  if (lane == 0) bs.warp_vals[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < nw ? bs.warp_vals[lane] : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(0xFFFFFFFFu, w, d);
+    if (lane == 0) bs.bcast[0] = w;
+  }
+  __syncthreads();
+  return bs.bcast[0];
+}
+
+__device__ __forceinline__ unsigned block_umin(unsigned v, BlockScratch& bs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
+  __syncthreads();
+  if (lane == 0) bs.warp_vals[warp] = (int)v;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = lane < nw ? (unsigned)bs.warp_vals[lane] : 0xFFFFFFFFu;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) w = min(w, __shfl_xor_sync(0xFFFFFFFFu, w, d));
+    if (lane == 0) bs.ubcast[0] = w;
+  }
+  __syncthreads();
+  return bs.ubcast[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: flat move kernel.  8 agents per thread: 2 x LDG.128 (x, y) + 1 x LDG.64 (actions) in,
+// 2 x STG.128 (+ optional STG.64 effective action) out.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void move8(const uint4& xv, const uint4& yv, const uint2& av, int S, uint4& ox, uint4& oy,
+                                      uint2& oa, bool& bad) {
+  const unsigned xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+  unsigned rx[4], ry[4];
+  unsigned ra[2] = {0u, 0u};
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    int nxv[2], nyv[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int e = 2 * h + s;
+      int a = (int)(((e < 4 ? av.x : av.y) >> (8 * (e & 3))) & 0xFFu);
+      bad |= a > 8;
+      a = min(a, 8);
+      ra[e >> 2] |= (unsigned)a << (8 * (e & 3));
+      const int xo = (int)(int16_t)((xs[h] >> (16 * s)) & 0xFFFFu);
+      const int yo = (int)(int16_t)((ys[h] >> (16 * s)) & 0xFFFFu);
+      nxv[s] = wrap1(xo + move_dx(a), S);
+      nyv[s] = wrap1(yo + move_dy(a), S);
+    }
+    rx[h] = pack2(nxv[0], nxv[1]);
+    ry[h] = pack2(nyv[0], nyv[1]);
+  }
+  ox = make_uint4(rx[0], rx[1], rx[2], rx[3]);
+  oy = make_uint4(ry[0], ry[1], ry[2], ry[3]);
+  oa = make_uint2(ra[0], ra[1]);
+}
+
+__global__ void __launch_bounds__(256) move_kernel(long long total, int N, int S, const int16_t* __restrict__ x,
+                                                   const int16_t* __restrict__ y, const uint8_t* __restrict__ act,
+                                                   int16_t* __restrict__ ox, int16_t* __restrict__ oy,
+                                                   uint8_t* __restrict__ oeff, uint32_t* __restrict__ err) {
+  const long long nvec = total >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x) + v);
+    const uint4 yv = __ldg(reinterpret_cast<const uint4*>(y) + v);
+    const uint2 av = __ldg(reinterpret_cast<const uint2*>(act) + v);
+    uint4 rx, ry;
+    uint2 ra;
+    bool bad = false;
+    move8(xv, yv, av, S, rx, ry, ra, bad);
+    reinterpret_cast<uint4*>(ox)[v] = rx;
+    reinterpret_cast<uint4*>(oy)[v] = ry;
+    if (oeff) reinterpret_cast<uint2*>(oeff)[v] = ra;
+    if (bad && err) {
+      for (int e = 0; e < 8; ++e)
+        if (act[v * 8 + e] > 8) atomicOr(&err[(v * 8 + e) / N], SWARM_ERR_BAD_ACTION);
+    }
+  }
+  // scalar tail (total not a multiple of 8)
+  for (long long i = (nvec << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int a = act[i];
+    if (a > 8) { if (err) atomicOr(&err[i / N], SWARM_ERR_BAD_ACTION); a = 8; }
+    ox[i] = (int16_t)wrap1((int)x[i] + move_dx(a), S);
+    oy[i] = (int16_t)wrap1((int)y[i] + move_dy(a), S);
+    if (oeff) oeff[i] = (uint8_t)a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact occupancy counts (SDE:269-292) for one env inside a CTA: open-addressing hash table in
+// global memory (L2 resident; HS = power of two >= 2N slots of {key, count}).  Thread t owns the
+// contiguous agents [lo,hi) (keeps agent order for the re-draw prefix sum).  Each agent's slot is
+// remembered in aslot[], so nothing probes the table after the insert phase.
+// Returns the thread's sum of (c_i - 1); c_i is re-read from the table by the caller.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned hash_slot(unsigned key, int log2hs) { return (key * 2654435761u) >> (32 - log2hs); }
+
+__device__ __forceinline__ unsigned hash_insert(unsigned* hkeys, unsigned* hcnt, unsigned hmask, int log2hs,
+                                                unsigned key) {
+  unsigned s = hash_slot(key, log2hs);
+  for (;;) {
+    const unsigned old = atomicCAS(&hkeys[s], HASH_EMPTY, key);
+    if (old == HASH_EMPTY || old == key) { atomicAdd(&hcnt[s], 1u); return s; }
+    s = (s + 1u) & hmask;
+  }
+}
+
+struct EnvHash {
+  unsigned *keys, *cnt, *aslot;
+  unsigned mask;
+  int log2hs;
+};
+
+// phase 1+2: insert all, sync, return this thread's extra = sum(c_i - 1)
+template <typename PosFn>
+__device__ __forceinline__ int hash_count_extra(const EnvHash& h, int lo, int hi, PosFn pos) {
+  for (int i = lo; i < hi; ++i) h.aslot[i] = hash_insert(h.keys, h.cnt, h.mask, h.log2hs, pos(i));
+  __syncthreads();
+  int extra = 0;
+  for (int i = lo; i < hi; ++i) extra += (int)__ldcg(&h.cnt[h.aslot[i]]) - 1;
+  return extra;
+}
+__device__ __forceinline__ int hash_c(const EnvHash& h, int i) { return (int)__ldcg(&h.cnt[h.aslot[i]]); }
+// phase 3: wipe the used slots (call after every thread finished reading counts)
+__device__ __forceinline__ void hash_clear(const EnvHash& h, int lo, int hi) {
+  __syncthreads();
+  for (int i = lo; i < hi; ++i) {
+    const unsigned s = h.aslot[i];
+    h.keys[s] = HASH_EMPTY;
+    h.cnt[s] = 0u;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ EnvHash env_hash(const StagedScratch& sc, int N) {
+  EnvHash h;
+  const unsigned hs = 1u << sc.log2hs;
+  h.keys = sc.hash + (size_t)blockIdx.x * 2u * hs;
+  h.cnt = h.keys + hs;
+  h.aslot = sc.aslot + (size_t)blockIdx.x * (size_t)N;
+  h.mask = hs - 1u;
+  h.log2hs = sc.log2hs;
+  return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: collision re-draw rounds for large N.  grid-stride over envs, one CTA per env at a time.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) collide_kernel(const StepParams p, const StagedScratch sc) {
+  __shared__ BlockScratch bs;
+  const int N = p.N, S = p.S;
+  const EnvHash h = env_hash(sc, N);
+  const int per = (N + blockDim.x - 1) / blockDim.x;
+  const int lo = min(N, (int)threadIdx.x * per), hi = min(N, lo + per);
+  for (int env = blockIdx.x; env < p.E; env += gridDim.x) {
+    if (p.frozen[env]) continue;              // uniform per CTA
+    const size_t base = (size_t)env * (size_t)N;
+    int16_t* __restrict__ nx = sc.nx + base;
+    int16_t* __restrict__ ny = sc.ny + base;
+    uint8_t* __restrict__ eff = sc.eff + base;
+    const uint8_t* __restrict__ slab = p.slab + (size_t)env * (size_t)p.K;
+    int cur = 0;
+    unsigned err = 0;
+    for (;;) {
+      const int extra = hash_count_extra(h, lo, hi, [&](int i) { return pack2(nx[i], ny[i]); });
+      int L;
+      int off = block_excl_scan(extra, L, bs);
+      const bool overflow = cur + L > p.K;
+      if (L > 0 && !overflow) {
+        for (int i = lo; i < hi; ++i) {
+          const int e = hash_c(h, i) - 1;
+          if (e > 0) {                                       // SDE:250-255
+            const int a = slab[cur + off + e - 1] & 7;
+            eff[i] = (uint8_t)a;
+            nx[i] = (int16_t)wrap1((int)p.x[base + i] + move_dx(a), S);
+            ny[i] = (int16_t)wrap1((int)p.y[base + i] + move_dy(a), S);
+          }
+          off += e;
+        }
+      }
+      hash_clear(h, lo, hi);
+      if (L == 0) break;
+      if (overflow) { err |= SWARM_ERR_SLAB_OVERFLOW; break; }
+      cur += L;
+    }
+    if (threadIdx.x == 0) {
+      p.consumed[env] = cur;
+      if (err) p.err[env] |= err;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: predator, one warp per env (any N).  Reads the OLD positions only when the env retargets.
+// Also the standalone swarm_predator kernel (then frozen == nullptr, outputs subset).
+// ------------------------------------------------------------------------------------------------
+struct PredIO {
+  int E, N, S;
+  const int16_t *xo, *yo, *xn, *yn;
+  const uint8_t *retarget, *frozen;
+  int16_t *px, *py;
+  int32_t* target;
+  uint8_t* orient;
+  int16_t *pred_prev, *pred_next;
+  uint8_t* step_orient;
+  int32_t* step_target;
+  uint8_t* done;
+  int32_t* eaten;
+  uint32_t* err;
+};
+
+__device__ __forceinline__ unsigned warp_umin(unsigned v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
+  return v;
+}
+
+__global__ void __launch_bounds__(256) predator_kernel(const PredIO io) {
+  const int lane = threadIdx.x & 31;
+  const int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (env >= io.E) return;
+  const int N = io.N, S = io.S;
+  if (io.frozen && io.frozen[env]) {
+    if (lane == 0) {
+      io.err[env] |= SWARM_ERR_STEP_WHEN_DONE;
+      io.done[env] = 1;
+      io.eaten[env] = -1;
+    }
+    return;
+  }
+  const size_t base = (size_t)env * (size_t)N;
+  int px = io.px[env], py = io.py[env];
+  int target = io.target[env];
+  const int ppx = px, ppy = py;
+  const bool vec = ((N & 7) == 0);
+  if (io.retarget[env]) {                                      // SDE:138-140
+    unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;
+    if (vec) {
+      for (int v = lane; v < (N >> 3); v += 32) {
+        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(io.xo + base) + v);
+        const uint4 yv = __ldg(reinterpret_cast<const uint4*>(io.yo + base) + v);
+        const unsigned xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int ax = (int)(int16_t)((xs[e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+          const int ay = (int)(int16_t)((ys[e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+          const int d = max(iabs(px - ax), iabs(py - ay));
+          klo = min(klo, nn_key_lo(d, v * 8 + e));
+          khi = min(khi, nn_key_hi(d, v * 8 + e));
+        }
+      }
+    } else {
+      for (int i = lane; i < N; i += 32) {
+        const int d = max(iabs(px - (int)io.xo[base + i]), iabs(py - (int)io.yo[base + i]));
+        klo = min(klo, nn_key_lo(d, i));
+        khi = min(khi, nn_key_hi(d, i));
+      }
+    }
+    target = nn_pick(warp_umin(klo), warp_umin(khi), S);
+  }
+  target = min(max(target, 0), N - 1);
+  int orient;
+  pursue(px, py, (int)io.xo[base + target], (int)io.yo[base + target], S, px, py, orient);
+
+  unsigned hit = 0xFFFFFFFFu;                                  // SDE:307-309 on the NEW positions
+  if (vec) {
+    const unsigned kx = rep2(px), ky = rep2(py);
+    for (int v = lane; v < (N >> 3); v += 32) {
+      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(io.xn + base) + v);
+      const uint4 yv = __ldg(reinterpret_cast<const uint4*>(io.yn + base) + v);
+      const unsigned xs[4] = {xv.x ^ kx, xv.y ^ kx, xv.z ^ kx, xv.w ^ kx};
+      const unsigned ys[4] = {yv.x ^ ky, yv.y ^ ky, yv.z ^ ky, yv.w ^ ky};
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        const unsigned z = xs[hh] | ys[hh];
+        if ((z & 0xFFFFu) == 0u) hit = min(hit, (unsigned)(v * 8 + 2 * hh));
+        if ((z >> 16) == 0u) hit = min(hit, (unsigned)(v * 8 + 2 * hh + 1));
+      }
+    }
+  } else {
+    for (int i = lane; i < N; i += 32)
+      if ((int)io.xn[base + i] == px && (int)io.yn[base + i] == py) hit = min(hit, (unsigned)i);
+  }
+  hit = warp_umin(hit);
+  if (lane == 0) {
+    const bool done = hit != 0xFFFFFFFFu;
+    io.px[env] = (int16_t)px;
+    io.py[env] = (int16_t)py;
+    io.target[env] = target;
+    io.orient[env] = (uint8_t)orient;
+    io.done[env] = done ? 1 : 0;
+    io.eaten[env] = done ? (int)hit : -1;
+    if (io.pred_prev) { io.pred_prev[2 * env] = (int16_t)ppx; io.pred_prev[2 * env + 1] = (int16_t)ppy; }
+    if (io.pred_next) { io.pred_next[2 * env] = (int16_t)px; io.pred_next[2 * env + 1] = (int16_t)py; }
+    if (io.step_orient) io.step_orient[env] = (uint8_t)orient;
+    if (io.step_target) io.step_target[env] = target;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: pack positions into pair words {x2, y2, -x2, -y2} (+ VF unit-vector words) and zero the
+// per-agent accumulators.  One thread per pair word.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pairprep_kernel(int E, int N, int S, int NW, const int16_t* __restrict__ x,
+                                                       const int16_t* __restrict__ y, const uint8_t* __restrict__ eff,
+                                                       uint4* __restrict__ pairw, uint2* __restrict__ vfw,
+                                                       unsigned* __restrict__ pcounts) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)E * NW) return;
+  const int env = (int)(t / NW), q = (int)(t % NW);
+  const size_t base = (size_t)env * (size_t)N;
+  const int j0 = 2 * q, j1 = 2 * q + 1;
+  const int x0 = x[base + j0], y0 = y[base + j0];
+  const int x1 = j1 < N ? (int)x[base + j1] : -S, y1 = j1 < N ? (int)y[base + j1] : 0;
+  pairw[t] = make_uint4(pack2(x0, x1), pack2(y0, y1), pack2(-x0, -x1), pack2(-y0, -y1));
+  if (vfw) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int j = j0 + s;
+      const int a = j < N ? (int)eff[base + j] : 8;
+      const bool mover = a < 8;
+      const int mx = mover ? move_dx(a) : 0, my = mover ? move_dy(a) : 0;
+      const bool diag = (a & 1) != 0;
+      vfw[2 * t + s] = make_uint2(pack2((diag ? 0 : mx) + 1, (diag ? 0 : my) + 1),
+                                  pack2((diag ? mx : 0) + 1, (diag ? my : 0) + 1));
+    }
+  }
+  uint4* pc = reinterpret_cast<uint4*>(pcounts + (base + j0) * 8);
+  pc[0] = make_uint4(0, 0, 0, 0);
+  pc[1] = make_uint4(0, 0, 0, 0);
+  if (j1 < N) { pc[2] = make_uint4(0, 0, 0, 0); pc[3] = make_uint4(0, 0, 0, 0); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: tiled pairwise kernel (the INT32/DPX-bound contract kernel).
+//   unit = (env, i-tile of PW_THREADS*PW_APL agents, j-chunk of PW_JC pair words)
+//   CTA b sweeps units [b*U/G, (b+1)*U/G): consecutive units share the i-tile, so the accumulators
+//   live in registers across j-chunks and are flushed with one atomicAdd per counter when the
+//   i-tile changes.  j-chunks are staged by TMA bulk copies (cp.async.bulk, mbarrier completion),
+//   double buffered; all threads read the same smem word (broadcast, no bank conflicts).
+// ------------------------------------------------------------------------------------------------
+constexpr int PW_THREADS = 128;
+constexpr int PW_APL = 4;
+constexpr int PW_TILE = PW_THREADS * PW_APL;   // 512 agents per i-tile
+constexpr int PW_JC = 256;                     // pair words per j-chunk (512 agents, 4 KB)
+
+__device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                             unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct PairIO {
+  int E, N, S, NW;
+  int t_rep, t_att, t_repf, t_attf, t_vf;
+  const uint4* pairw;
+  const uint2* vfw;
+  const int16_t *x, *y;
+  const uint8_t* skip;      // [E] (nullable)
+  unsigned* pcounts;        // [E,N,8]
+  int tiles_per_env, chunks_per_env;
+  long long units;
+};
+
+template <bool HAS_VF>
+__global__ void __launch_bounds__(PW_THREADS) pairwise_kernel(const PairIO io) {
+  __shared__ __align__(128) uint4 sj[2][PW_JC];
+  __shared__ __align__(128) uint4 sv[HAS_VF ? 2 : 1][HAS_VF ? PW_JC : 1];
+  __shared__ __align__(8) unsigned long long full_bar[2];
+  const int tid = threadIdx.x;
+  const long long u_begin = (io.units * blockIdx.x) / gridDim.x;
+  const long long u_end = (io.units * (blockIdx.x + 1)) / gridDim.x;
+  if (u_begin >= u_end) return;
+  if (tid == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int upe = io.tiles_per_env * io.chunks_per_env;
+  auto decode = [&](long long u, int& env, int& tile, int& chunk) {
+    env = (int)(u / upe);
+    const int r = (int)(u % upe);
+    tile = r / io.chunks_per_env;
+    chunk = r % io.chunks_per_env;
+  };
+  auto chunk_words = [&](int chunk) { return min(PW_JC, io.NW - chunk * PW_JC); };
+  auto issue = [&](long long u, int stage) {       // thread 0 only
+    int env, tile, chunk;
+    decode(u, env, tile, chunk);
+    const int words = chunk_words(chunk);
+    const unsigned bytes = (unsigned)words * 16u * (HAS_VF ? 2u : 1u);
+    mbar_expect_tx(&full_bar[stage], bytes);
+    tma_bulk_g2s(&sj[stage][0], io.pairw + (size_t)env * io.NW + (size_t)chunk * PW_JC, (unsigned)words * 16u,
+                 &full_bar[stage]);
+    if (HAS_VF)
+      tma_bulk_g2s(&sv[HAS_VF ? stage : 0][0],
+                   reinterpret_cast<const uint4*>(io.vfw) + (size_t)env * io.NW + (size_t)chunk * PW_JC,
+                   (unsigned)words * 16u, &full_bar[stage]);
+  };
+
+  const unsigned TR = rep2(io.t_rep), TA = rep2(io.t_att), TRf = rep2(io.t_repf), TAf = rep2(io.t_attf);
+  const unsigned TV = rep2(HAS_VF ? io.t_vf : 0);
+
+  unsigned XI[PW_APL], YI[PW_APL], NXI[PW_APL], NYI[PW_APL];
+  unsigned aR[PW_APL], aA[PW_APL], aRf[PW_APL], aAf[PW_APL], aV[PW_APL], accA[PW_APL], accD[PW_APL];
+  int cur_env = -1, cur_tile = -1;
+  bool cur_skip = true;
+
+  auto flush = [&]() {
+    if (cur_env < 0 || cur_skip) return;
+#pragma unroll
+    for (int k = 0; k < PW_APL; ++k) {
+      const int i = cur_tile * PW_TILE + tid * PW_APL + k;
+      if (i < io.N) {
+        unsigned* pc = io.pcounts + ((size_t)cur_env * io.N + i) * 8;
+        atomicAdd(pc + 0, (unsigned)hsum2(aR[k]));
+        atomicAdd(pc + 1, (unsigned)hsum2(aA[k]));
+        atomicAdd(pc + 2, (unsigned)hsum2(aRf[k]));
+        atomicAdd(pc + 3, (unsigned)hsum2(aAf[k]));
+        if (HAS_VF) {
+          atomicAdd(pc + 4, (unsigned)hsum2(aV[k]));
+          atomicAdd(pc + 5, accA[k]);
+          atomicAdd(pc + 6, accD[k]);
+        }
+      }
+    }
+  };
+
+  if (tid == 0) issue(u_begin, 0);
+  unsigned phase[2] = {0u, 0u};
+  for (long long u = u_begin; u < u_end; ++u) {
+    const int stage = (int)((u - u_begin) & 1);
+    if (tid == 0 && u + 1 < u_end) issue(u + 1, stage ^ 1);   // stage^1 was released by the barrier below
+    int env, tile, chunk;
+    decode(u, env, tile, chunk);
+    if (env != cur_env || tile != cur_tile) {
+      flush();
+      cur_env = env; cur_tile = tile;
+      cur_skip = io.skip && io.skip[env];
+      const size_t base = (size_t)env * io.N;
+#pragma unroll
+      for (int k = 0; k < PW_APL; ++k) {
+        const int i = tile * PW_TILE + tid * PW_APL + k;
+        const int xi = i < io.N ? (int)io.x[base + i] : -io.S, yi = i < io.N ? (int)io.y[base + i] : 0;
+        XI[k] = rep2(xi); YI[k] = rep2(yi); NXI[k] = rep2(-xi); NYI[k] = rep2(-yi);
+        aR[k] = aA[k] = aRf[k] = aAf[k] = aV[k] = accA[k] = accD[k] = 0u;
+      }
+    }
+    mbar_wait(&full_bar[stage], phase[stage]);
+    phase[stage] ^= 1u;
+    if (!cur_skip) {
+      const int words = chunk_words(chunk);
+#pragma unroll 2
+      for (int q = 0; q < words; ++q) {
+        const uint4 w = sj[stage][q];
+        uint4 uv = make_uint4(0, 0, 0, 0);
+        if (HAS_VF) uv = sv[HAS_VF ? stage : 0][q];
+#pragma unroll
+        for (int k = 0; k < PW_APL; ++k) {
+          const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], w);
+          aR[k] += lt2(TR, m);
+          aA[k] += lt2(TA, m);
+          aRf[k] += lt2(TRf, m);
+          aAf[k] += lt2(TAf, m);
+          if (HAS_VF) {
+            const unsigned gate = lt2(TV, m);
+            aV[k] += gate;
+            accA[k] += (gate & 0xFFFFu) * uv.x + (gate >> 16) * uv.z;
+            accD[k] += (gate & 0xFFFFu) * uv.y + (gate >> 16) * uv.w;
+          }
+        }
+      }
+    }
+    __syncthreads();   // everyone is done with sj[stage] before it is refilled two units later
+  }
+  flush();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: finalize, CTA per env (grid-stride).  Reads the per-agent accumulators, the effective
+// actions and the new positions; writes rewards, outputs, statistics and commits the positions.
+// ------------------------------------------------------------------------------------------------
+template <bool HAS_VF>
+__global__ void __launch_bounds__(256) finalize_kernel(const StepParams p, const StagedScratch sc) {
+  __shared__ BlockScratch bs;
+  const int N = p.N;
+  for (int env = blockIdx.x; env < p.E; env += gridDim.x) {
+    const size_t base = (size_t)env * (size_t)N;
+    const bool frozen = p.frozen[env] != 0;
+    const bool done = p.done[env] != 0;
+    __syncthreads();                                // flags are read by everyone before thread 0 updates them
+    if (frozen) {                                   // SDE:233-234 (flagged by K3)
+      if (threadIdx.x == 0) {
+        p.counts[2 * env] = 0; p.counts[2 * env + 1] = 0;
+        p.consumed[env] = 0;
+        for (int q = 0; q < 5; ++q) p.reward[5 * env + q] = 0.f;
+      }
+      continue;
+    }
+    const int eaten = p.eaten[env];
+    double r_surv = 0.0, r_att = 0.0, r_rep = 0.0, r_ali = 0.0, r_sum = 0.0;
+    int g_rep = 0, g_att = 0;
+    if (!done) {
+      int Ax = 0, Ay = 0, Dx = 0, Dy = 0;
+      if (!HAS_VF) {
+        int ax = 0, ay = 0, dx = 0, dy = 0;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+          const int a = sc.eff[base + i];
+          if (a < 8) {
+            const int mx = move_dx(a), my = move_dy(a);
+            if (a & 1) { dx += mx; dy += my; } else { ax += mx; ay += my; }
+          }
+        }
+        Ax = block_sum(ax, bs); Ay = block_sum(ay, bs); Dx = block_sum(dx, bs); Dy = block_sum(dy, bs);
+      }
+      const int selfR = p.t_rep >= 1, selfA = p.t_att >= 1, selfRf = p.t_repf >= 1, selfAf = p.t_attf >= 1;
+      const int selfV = HAS_VF ? (p.t_vf >= 1) : 1;
+      int s_rep = 0, s_att = 0, s_vis = 0;
+      long long s_P = 0, s_Q = 0;
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const uint4 c0 = reinterpret_cast<const uint4*>(sc.pcounts + (base + i) * 8)[0];
+        const int a = sc.eff[base + i];
+        int vis, P, Q;
+        if (HAS_VF) {
+          const uint4 c1 = reinterpret_cast<const uint4*>(sc.pcounts + (base + i) * 8)[1];
+          const int vin = (int)c1.x;
+          vis = vin - selfV;
+          align_PQ(a, (int)(c1.y & 0xFFFFu) - vin, (int)(c1.y >> 16) - vin, (int)(c1.z & 0xFFFFu) - vin,
+                   (int)(c1.z >> 16) - vin, selfV, P, Q);
+        } else {
+          vis = N - 1;
+          align_PQ(a, Ax, Ay, Dx, Dy, 1, P, Q);
+        }
+        const AgentTerms t = agent_terms(p, (int)c0.x - selfR, (int)c0.y - selfA, (int)c0.z - selfRf,
+                                         (int)c0.w - selfAf, vis, P, Q);
+        s_rep += t.rep_i; s_att += t.att_i; s_vis += vis; s_P += P; s_Q += Q;
+        if (p.agent_reward) {
+          const double a_rep = p.w_rep * (double)t.rep_i * p.inv_nn;
+          const double a_att = p.w_att * (double)t.att_i * p.inv_nn;
+          const double a_ali = p.w_ali * (-t.una) * p.inv_nn;
+          reinterpret_cast<float4*>(p.agent_reward)[base + i] =
+              make_float4((float)a_att, (float)a_rep, (float)a_ali, (float)(a_rep + a_att + a_ali));
+        }
+        if (p.agent_counts) reinterpret_cast<int2*>(p.agent_counts)[base + i] = make_int2(t.rep_i, t.att_i);
+      }
+      // N <= 16384: |sum P|, |sum Q| <= 2 N^2 = 5.4e8 fits int32; vis sum N(N-1) = 2.7e8 fits too
+      g_rep = block_sum(s_rep, bs);
+      g_att = block_sum(s_att, bs);
+      const int g_P = block_sum((int)s_P, bs), g_Q = block_sum((int)s_Q, bs);
+      const int g_vis = HAS_VF ? block_sum(s_vis, bs) : N * (N - 1);
+      const double g_una = 0.5 * (double)g_vis - 0.25 * (double)g_P - 0.35355339059327376220 * (double)g_Q;
+      r_rep = p.w_rep * (double)g_rep * p.inv_nn;
+      r_att = p.w_att * (double)g_att * p.inv_nn;
+      r_ali = p.w_ali * (-g_una) * p.inv_nn;
+      r_sum = r_rep + r_att + r_ali;
+    } else {
+      r_surv = (double)p.eat;
+      r_sum = (double)p.eat;
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        if (p.agent_reward)
+          reinterpret_cast<float4*>(p.agent_reward)[base + i] = make_float4(0.f, 0.f, 0.f, i == eaten ? p.eat : 0.f);
+        if (p.agent_counts) reinterpret_cast<int2*>(p.agent_counts)[base + i] = make_int2(0, 0);
+      }
+    }
+    // commit (SDE:260) + terminal copy
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const int16_t vx = sc.nx[base + i], vy = sc.ny[base + i];
+      p.x[base + i] = vx;
+      p.y[base + i] = vy;
+      if (done && p.term_x) { p.term_x[base + i] = vx; p.term_y[base + i] = vy; }
+      if (p.eff_action) p.eff_action[base + i] = sc.eff[base + i];
+    }
+    if (threadIdx.x == 0) {
+      float* rw = p.reward + 5 * (size_t)env;
+      rw[0] = (float)r_surv; rw[1] = (float)r_att; rw[2] = (float)r_rep; rw[3] = (float)r_ali; rw[4] = (float)r_sum;
+      p.counts[2 * env] = g_rep;
+      p.counts[2 * env + 1] = g_att;
+      if (done && !p.auto_reset) p.frozen[env] = 1;
+      if (p.track_stats) {
+        const unsigned len = p.ep_len[env] + 1u;
+        float4 ret = reinterpret_cast<float4*>(p.ep_ret)[env];
+        ret.x += (float)r_surv; ret.y += (float)r_att; ret.z += (float)r_rep; ret.w += (float)r_ali;
+        if (done) {
+          p.fin_count[env] += 1u;
+          p.fin_len[env] += len;
+          float4 f = reinterpret_cast<float4*>(p.fin_ret)[env];
+          f.x += ret.x; f.y += ret.y; f.z += ret.z; f.w += ret.w;
+          reinterpret_cast<float4*>(p.fin_ret)[env] = f;
+          p.ep_len[env] = 0u;
+          reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          p.ep_len[env] = len;
+          reinterpret_cast<float4*>(p.ep_ret)[env] = ret;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: reference reset for large N, CTA per env (grid-stride), optionally masked.
+//   mode 0: reset every env, zero reset_count / statistics     (swarm_reset)
+//   mode 1: reset envs with mask[env] != 0                     (auto-reset after a step, swarm_autoreset)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) reset_kernel(const StepParams p, const StagedScratch sc,
+                                                     const uint8_t* __restrict__ mask, int mode) {
+  __shared__ BlockScratch bs;
+  const int N = p.N, S = p.S;
+  const EnvHash h = env_hash(sc, N);
+  const int per = (N + blockDim.x - 1) / blockDim.x;
+  const int lo = min(N, (int)threadIdx.x * per), hi = min(N, lo + per);
+  for (int env = blockIdx.x; env < p.E; env += gridDim.x) {
+    if (mode == 1 && mask && !mask[env]) continue;
+    if (mode == 1 && p.frozen[env]) continue;      // frozen envs report done=1 but are never reset
+    const size_t base = (size_t)env * (size_t)N;
+    int16_t* __restrict__ x = p.x + base;
+    int16_t* __restrict__ y = p.y + base;
+    unsigned rc = mode == 0 ? 0u : p.reset_count[env];
+    __syncthreads();
+    if (threadIdx.x == 0) p.reset_count[env] = rc + 1u;
+    const size_t slot = (size_t)(rc % (unsigned)p.R) * (size_t)p.E + (size_t)env;
+    const int16_t* __restrict__ tape = p.place + slot * (size_t)p.PL;
+    unsigned err = 0;
+    for (int i = lo; i < hi; ++i) { x[i] = tape[i]; y[i] = tape[N + i]; }   // SDE:202-203
+    int cur = 2 * N;
+    for (;;) {
+      const int extra = hash_count_extra(h, lo, hi, [&](int i) { return pack2(x[i], y[i]); });
+      int L;
+      int off = block_excl_scan(extra, L, bs);
+      const bool overflow = cur + 2 * L > p.PL;
+      if (L > 0 && !overflow) {
+        for (int i = lo; i < hi; ++i) {
+          const int e = hash_c(h, i) - 1;
+          if (e > 0) {                                // SDE:208-209
+            const int s = off + e - 1;
+            x[i] = tape[cur + s];
+            y[i] = tape[cur + L + s];
+          }
+          off += e;
+        }
+      }
+      hash_clear(h, lo, hi);
+      if (L == 0) break;
+      if (overflow) { err |= SWARM_ERR_PLACE_OVERFLOW; break; }
+      cur += 2 * L;
+    }
+    const int16_t* __restrict__ pt = p.ptape + slot * (size_t)p.KP * 2;
+    int a = 0, px = 0, py = 0;
+    for (;;) {                                        // SDE:92-105
+      if (a >= p.KP) { err |= SWARM_ERR_PRED_OVERFLOW; break; }
+      px = pt[2 * a]; py = pt[2 * a + 1];
+      ++a;
+      int hit = 0;
+      for (int i = lo; i < hi; ++i) hit |= ((int)x[i] == px && (int)y[i] == py);
+      if (!__syncthreads_or(hit)) break;
+    }
+    unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;    // SDE:109
+    for (int i = lo; i < hi; ++i) {
+      const int d = max(iabs(px - (int)x[i]), iabs(py - (int)y[i]));
+      klo = min(klo, nn_key_lo(d, i));
+      khi = min(khi, nn_key_hi(d, i));
+    }
+    klo = block_umin(klo, bs);
+    khi = block_umin(khi, bs);
+    if (threadIdx.x == 0) {
+      p.px[env] = (int16_t)px;
+      p.py[env] = (int16_t)py;
+      p.target[env] = nn_pick(klo, khi, S);
+      p.orient[env] = 0;
+      if (mode == 0) {
+        p.frozen[env] = 0;
+        p.err[env] = err;
+      } else if (err) {
+        p.err[env] |= err;
+      }
+      if (p.track_stats && mode == 0) {
+        p.ep_len[env] = 0u;
+        reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
+        p.fin_count[env] = 0u;
+        p.fin_len[env] = 0u;
+        reinterpret_cast<float4*>(p.fin_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// standalone swarm_pairwise epilogue: accumulators -> (rew_rep_i, rew_attr_i)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pair_counts_kernel(const StepParams p, const unsigned* __restrict__ pcounts,
+                                                          const uint8_t* __restrict__ skip, int32_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)p.E * p.N) return;
+  if (skip && skip[i / p.N]) { reinterpret_cast<int2*>(out)[i] = make_int2(0, 0); return; }
+  const uint4 c0 = reinterpret_cast<const uint4*>(pcounts + i * 8)[0];
+  const AgentTerms t = agent_terms(p, (int)c0.x - (p.t_rep >= 1), (int)c0.y - (p.t_att >= 1),
+                                   (int)c0.z - (p.t_repf >= 1), (int)c0.w - (p.t_attf >= 1), 0, 0, 0);
+  reinterpret_cast<int2*>(out)[i] = make_int2(t.rep_i, t.att_i);
+}
+
+}  // namespace swarm

@@ -1,0 +1,642 @@
+// swarm_abi.cu -- host side of the C ABI declared in include/swarm_abi.h (libswarm_b200.so).
+// Plain pointers in, kernel launches on the caller's stream out; no torch, no CPU fallback.
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+#include "fused_step.cuh"
+#include "staged.cuh"
+
+namespace swarm {
+
+static thread_local std::string g_last_error;
+
+struct Ctx {
+  swarm_config cfg;
+  swarm_state st;
+  bool has_state = false;
+  const int16_t* place = nullptr;
+  const int16_t* ptape = nullptr;
+  std::string err;
+  std::string path_name;
+  bool fused = false;
+  int lpe = 0, apl = 0;
+  int bitmap_words = 0;
+  int launches = 0;
+  int num_sms = 148;
+  // staged scratch
+  StagedScratch sc{};
+  void* scratch_block = nullptr;
+  int per_env_threads = 256;
+  // stats
+  double* d_stats = nullptr;
+  // nccl
+  void* nccl_lib = nullptr;
+  void* nccl_comm = nullptr;
+};
+
+static int fail(Ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  g_last_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(c, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail((c), SWARM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+  } while (0)
+
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+static void fill_thresholds(StepParams& p, int N, int S, int att, int rep) {
+  p.N = N;
+  p.S = S;
+  p.t_rep = clampi(rep, 0, S);
+  p.t_att = clampi(att, 0, S);
+  p.t_repf = clampi((long long)S - rep + 1 > S ? S : (S - rep + 1), 0, S);
+  p.t_attf = clampi((long long)S - att + 1 > S ? S : (S - att + 1), 0, S);
+  // literal diagonal terms of the N x N sums (D = 0, S - D = S): SDE:336-342
+  p.diag_rep = (0 < rep ? 1 : 0) + (S < rep ? 1 : 0);
+  p.diag_att = (((0 < att) == (0 >= rep)) ? 1 : 0) + (((S < att) == (S >= rep)) ? 1 : 0);
+  p.inv_nn = 1.0 / ((double)N * (double)(N - 1));
+}
+
+static StepParams base_params(const Ctx* c) {
+  StepParams p;
+  memset(&p, 0, sizeof(p));
+  const swarm_config& g = c->cfg;
+  p.E = g.num_envs;
+  fill_thresholds(p, g.num_agents, g.grid_size, g.attraction_thresh, g.repulsion_thresh);
+  p.t_vf = -1;
+  p.w_att = p.w_rep = p.w_ali = 1.0;
+  p.eat = g.predator_eat_rew;
+  p.K = g.slab_len; p.PL = g.place_len; p.KP = g.pred_attempts; p.R = g.reset_slots;
+  p.auto_reset = g.auto_reset; p.track_stats = g.track_stats;
+  p.bitmap_words = c->bitmap_words;
+  const swarm_state& s = c->st;
+  p.x = s.x; p.y = s.y; p.px = s.px; p.py = s.py; p.target = s.target; p.orient = s.pred_orient;
+  p.frozen = s.frozen; p.err = s.err; p.reset_count = s.reset_count;
+  p.ep_len = s.ep_len; p.ep_ret = s.ep_ret; p.fin_count = s.fin_count; p.fin_len = s.fin_len; p.fin_ret = s.fin_ret;
+  p.place = c->place; p.ptape = c->ptape;
+  return p;
+}
+
+// ---- fused dispatch -------------------------------------------------------------------------------
+template <int LPE, int APL>
+static int fused_smem_bytes(int bitmap_words, bool vf) {
+  using C = FusedCfg<LPE, APL>;
+  return C::WARPS * (C::pair_bytes() + (vf ? C::vf_bytes() : 0) + C::EPW * bitmap_words * 4);
+}
+
+template <int LPE, int APL>
+static cudaError_t launch_fused_step(const StepParams& p, bool vf, cudaStream_t s) {
+  using C = FusedCfg<LPE, APL>;
+  const int envs_per_cta = C::WARPS * C::EPW;
+  const int grid = (p.E + envs_per_cta - 1) / envs_per_cta;
+  const int smem = fused_smem_bytes<LPE, APL>(p.bitmap_words, vf);
+  cudaError_t e;
+  if (vf) {
+    e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    fused_step_kernel<LPE, APL, true><<<grid, C::WARPS * 32, smem, s>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    fused_step_kernel<LPE, APL, false><<<grid, C::WARPS * 32, smem, s>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+template <int LPE, int APL>
+static cudaError_t launch_fused_reset(const StepParams& p, const uint8_t* mask, int zero_counts, cudaStream_t s) {
+  using C = FusedCfg<LPE, APL>;
+  const int envs_per_cta = C::WARPS * C::EPW;
+  const int grid = (p.E + envs_per_cta - 1) / envs_per_cta;
+  const int smem = C::WARPS * C::EPW * C::NMAX * 4;
+  fused_reset_kernel<LPE, APL><<<grid, C::WARPS * 32, smem, s>>>(p, mask, zero_counts);
+  return cudaGetLastError();
+}
+
+#define FUSED_DISPATCH(c, CALL)                                  \
+  do {                                                           \
+    const int _l = (c)->lpe, _a = (c)->apl;                      \
+    if (_l == 4 && _a == 1) { CALL(4, 1); }                      \
+    else if (_l == 8 && _a == 1) { CALL(8, 1); }                 \
+    else if (_l == 8 && _a == 2) { CALL(8, 2); }                 \
+    else if (_l == 8 && _a == 4) { CALL(8, 4); }                 \
+    else if (_l == 16 && _a == 4) { CALL(16, 4); }               \
+    else if (_l == 32 && _a == 4) { CALL(32, 4); }               \
+    else { CALL(32, 8); }                                        \
+  } while (0)
+
+static void choose_fused_shape(int N, int& lpe, int& apl) {
+  if (N <= 4) { lpe = 4; apl = 1; }
+  else if (N <= 8) { lpe = 8; apl = 1; }
+  else if (N <= 16) { lpe = 8; apl = 2; }
+  else if (N <= 32) { lpe = 8; apl = 4; }
+  else if (N <= 64) { lpe = 16; apl = 4; }
+  else if (N <= 128) { lpe = 32; apl = 4; }
+  else { lpe = 32; apl = 8; }
+}
+
+// ---- staged scratch ---------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int staged_alloc(Ctx* c) {
+  const int E = c->cfg.num_envs, N = c->cfg.num_agents;
+  StagedScratch& sc = c->sc;
+  sc.NW = (N + 1) / 2;
+  int log2hs = 4;
+  while ((1 << log2hs) < 2 * N) ++log2hs;
+  sc.log2hs = log2hs;
+  sc.env_grid = std::min(E, 2 * c->num_sms);
+  int threads = 128;
+  while (threads < 1024 && threads * 4 < N) threads <<= 1;
+  c->per_env_threads = threads;
+  const size_t hs = (size_t)1 << log2hs;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_nx = take((size_t)E * N * 2), o_ny = take((size_t)E * N * 2), o_eff = take((size_t)E * N);
+  const size_t o_hash = take((size_t)sc.env_grid * 2 * hs * 4), o_aslot = take((size_t)sc.env_grid * N * 4);
+  const size_t o_pairw = take((size_t)E * sc.NW * 16), o_vfw = take((size_t)E * sc.NW * 16);
+  const size_t o_pc = take((size_t)E * N * 32 + 64);
+  CUDA_TRY(c, cudaMalloc(&c->scratch_block, off));
+  char* b = (char*)c->scratch_block;
+  sc.nx = (int16_t*)(b + o_nx); sc.ny = (int16_t*)(b + o_ny); sc.eff = (uint8_t*)(b + o_eff);
+  sc.hash = (unsigned*)(b + o_hash); sc.aslot = (unsigned*)(b + o_aslot);
+  sc.pairw = (uint4*)(b + o_pairw); sc.vfw = (uint2*)(b + o_vfw); sc.pcounts = (unsigned*)(b + o_pc);
+  CUDA_TRY(c, cudaMemset(b + o_hash, 0xFF, (size_t)sc.env_grid * hs * 4 * 2));   // keys = EMPTY ...
+  // ... and counts = 0: keys and counts are interleaved per CTA ({keys[HS], cnt[HS]}), fix the counts
+  for (int g = 0; g < sc.env_grid; ++g)
+    CUDA_TRY(c, cudaMemset(b + o_hash + ((size_t)g * 2 * hs + hs) * 4, 0, hs * 4));
+  return SWARM_OK;
+}
+
+static int pairwise_launch(const StepParams& p, const StagedScratch& sc, const int16_t* x, const int16_t* y,
+                           const uint8_t* skip, bool vf, int num_sms, cudaStream_t s) {
+  PairIO io;
+  io.E = p.E; io.N = p.N; io.S = p.S; io.NW = sc.NW;
+  io.t_rep = p.t_rep; io.t_att = p.t_att; io.t_repf = p.t_repf; io.t_attf = p.t_attf; io.t_vf = p.t_vf;
+  io.pairw = sc.pairw; io.vfw = sc.vfw; io.x = x; io.y = y; io.skip = skip; io.pcounts = sc.pcounts;
+  io.tiles_per_env = (p.N + PW_TILE - 1) / PW_TILE;
+  io.chunks_per_env = (sc.NW + PW_JC - 1) / PW_JC;
+  io.units = (long long)p.E * io.tiles_per_env * io.chunks_per_env;
+  // 4 resident CTAs per SM (128 threads, ~8-16 KB smem each); never more CTAs than units
+  long long grid = std::min<long long>(io.units, (long long)num_sms * 4);
+  if (grid < 1) grid = 1;
+  if (vf) pairwise_kernel<true><<<(int)grid, PW_THREADS, 0, s>>>(io);
+  else pairwise_kernel<false><<<(int)grid, PW_THREADS, 0, s>>>(io);
+  return 0;
+}
+
+// ---- statistics reduction ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) stats_reduce_kernel(int E, const uint32_t* __restrict__ fin_count,
+                                                            const uint32_t* __restrict__ fin_len,
+                                                            const float* __restrict__ fin_ret,
+                                                            const uint32_t* __restrict__ ep_len,
+                                                            double* __restrict__ out) {
+  __shared__ double sh[8][32];
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const float4 r = reinterpret_cast<const float4*>(fin_ret)[e];
+    acc[0] += (double)fin_count[e];
+    acc[1] += (double)fin_len[e];
+    acc[3] += (double)r.x; acc[4] += (double)r.y; acc[5] += (double)r.z; acc[6] += (double)r.w;
+    acc[7] += (double)ep_len[e];
+  }
+  acc[2] = acc[3] + acc[4] + acc[5] + acc[6];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    double v = acc[q];
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    if (lane == 0) sh[q][warp] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      double v = lane < (int)(blockDim.x >> 5) ? sh[q][lane] : 0.0;
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+      if (lane == 0) out[q] = v;
+    }
+  }
+}
+
+// ---- INT32 pipe micro-benchmarks ----------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) int32_peak_kernel(int iters, unsigned seed, unsigned* __restrict__ out) {
+  constexpr int CH = 8;
+  unsigned a[CH], b[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) { a[c] = seed + threadIdx.x * 7u + c; b[c] = seed * 3u + c * 11u + blockIdx.x; }
+  const unsigned k1 = seed | 1u, k2 = (seed >> 3) | 0x00010001u;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      if (KIND == 0) {            // IADD3 dependent chains
+        a[c] = a[c] + b[c] + k1;
+        b[c] = b[c] + a[c] + k2;
+      } else if (KIND == 1) {     // IMNMX / VIMNMX
+        a[c] = (unsigned)max((int)a[c], (int)(b[c] ^ k1));
+        b[c] = (unsigned)min((int)b[c], (int)(a[c] ^ k2));
+      } else if (KIND == 2) {     // IADD3 (alu pipe) + IMAD (fma pipe)
+        a[c] = a[c] + b[c] + k1;
+        b[c] = b[c] * k1 + a[c];
+      } else if (KIND == 3) {     // DPX 16x2
+        a[c] = __viaddmin_s16x2(a[c], k1, b[c]);
+        b[c] = __viaddmin_s16x2_relu(b[c], k2, a[c]);
+      } else {                    // DPX 16x2 + IMAD
+        a[c] = __viaddmin_s16x2(a[c], k1, b[c]);
+        b[c] = b[c] * k1 + a[c];
+      }
+    }
+  }
+  unsigned r = 0;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) r ^= a[c] ^ b[c];
+  if (r == 0x12345678u) out[0] = r;   // keep the chains alive
+}
+
+}  // namespace swarm
+
+using namespace swarm;
+
+extern "C" {
+
+int swarm_abi_version(void) { return SWARM_ABI_VERSION; }
+
+const char* swarm_last_error(swarm_handle h) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  return c ? c->err.c_str() : g_last_error.c_str();
+}
+
+int swarm_create(const swarm_config* cfg, swarm_handle* out) {
+  if (!cfg || !out) return fail(nullptr, SWARM_E_INVALID, "swarm_create: null argument");
+  if (cfg->abi_version != SWARM_ABI_VERSION) return fail(nullptr, SWARM_E_INVALID, "swarm_create: ABI version mismatch");
+  if (cfg->num_envs < 1) return fail(nullptr, SWARM_E_INVALID, "swarm_create: num_envs < 1");
+  if (cfg->num_agents < 2 || cfg->num_agents > SWARM_MAX_AGENTS)
+    return fail(nullptr, SWARM_E_INVALID, "swarm_create: num_agents must be in [2, 16384] (reward divides by N(N-1))");
+  if (cfg->grid_size < 2 || cfg->grid_size > SWARM_MAX_GRID)
+    return fail(nullptr, SWARM_E_INVALID, "swarm_create: grid_size must be in [2, 16384]");
+  if ((long long)cfg->grid_size * cfg->grid_size <= cfg->num_agents)
+    return fail(nullptr, SWARM_E_INVALID, "swarm_create: need more cells than agents + predator");
+  if (cfg->slab_len < 0 || cfg->place_len < 2 * cfg->num_agents || cfg->pred_attempts < 1 || cfg->reset_slots < 1)
+    return fail(nullptr, SWARM_E_INVALID, "swarm_create: bad tape geometry");
+  if (cfg->path == SWARM_PATH_FUSED && cfg->num_agents > SWARM_FUSED_MAX_AGENTS)
+    return fail(nullptr, SWARM_E_INVALID, "swarm_create: fused path needs num_agents <= 256");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(nullptr, SWARM_E_CUDA, "swarm_create: no CUDA device (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SWARM_E_INVALID, "swarm_create: bad device ordinal");
+  Ctx* c = new Ctx();
+  c->cfg = *cfg;
+  CUDA_TRY(c, cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(c, cudaGetDeviceProperties(&prop, cfg->device));
+  c->num_sms = prop.multiProcessorCount;
+  c->fused = cfg->path == SWARM_PATH_FUSED || (cfg->path == SWARM_PATH_AUTO && cfg->num_agents <= SWARM_FUSED_MAX_AGENTS);
+  if (c->fused) {
+    choose_fused_shape(cfg->num_agents, c->lpe, c->apl);
+    const long long cells = (long long)cfg->grid_size * cfg->grid_size;
+    const long long words = ((cells + 31) / 32 + 3) / 4 * 4;
+    c->bitmap_words = (words <= 2048 && cfg->num_agents >= 16) ? (int)words : 0;
+    char buf[64];
+    snprintf(buf, sizeof(buf), "fused<%d,%d>%s", c->lpe, c->apl, c->bitmap_words ? "+bitmap" : "");
+    c->path_name = buf;
+  } else {
+    c->path_name = "staged";
+  }
+  // the staged scratch also backs swarm_autoreset / masks on the fused path only when needed
+  if (!c->fused) {
+    int rc = staged_alloc(c);
+    if (rc != SWARM_OK) { std::string m = c->err; delete c; return fail(nullptr, rc, m); }
+  }
+  cudaError_t e = cudaMalloc(&c->d_stats, 8 * sizeof(double));
+  if (e != cudaSuccess) { delete c; return fail(nullptr, SWARM_E_CUDA, "cudaMalloc stats"); }
+  *out = reinterpret_cast<swarm_handle>(c);
+  return SWARM_OK;
+}
+
+int swarm_destroy(swarm_handle h) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return SWARM_OK;
+  cudaSetDevice(c->cfg.device);
+  if (c->nccl_comm && c->nccl_lib) {
+    typedef int (*destroy_t)(void*);
+    destroy_t f = (destroy_t)dlsym(c->nccl_lib, "ncclCommDestroy");
+    if (f) f(c->nccl_comm);
+  }
+  if (c->scratch_block) cudaFree(c->scratch_block);
+  if (c->d_stats) cudaFree(c->d_stats);
+  delete c;
+  return SWARM_OK;
+}
+
+int swarm_bind_state(swarm_handle h, const swarm_state* st) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || !st) return fail(c, SWARM_E_INVALID, "swarm_bind_state: null argument");
+  if (!st->x || !st->y || !st->px || !st->py || !st->target || !st->pred_orient || !st->frozen || !st->err ||
+      !st->reset_count)
+    return fail(c, SWARM_E_INVALID, "swarm_bind_state: a required state pointer is null");
+  if (c->cfg.track_stats && (!st->ep_len || !st->ep_ret || !st->fin_count || !st->fin_len || !st->fin_ret))
+    return fail(c, SWARM_E_INVALID, "swarm_bind_state: track_stats needs the statistics pointers");
+  if (((uintptr_t)st->x | (uintptr_t)st->y) & 15)
+    return fail(c, SWARM_E_INVALID, "swarm_bind_state: x / y must be 16-byte aligned");
+  c->st = *st;
+  c->has_state = true;
+  return SWARM_OK;
+}
+
+int swarm_bind_reset_tapes(swarm_handle h, const int16_t* place, const int16_t* ptape) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || !place || !ptape) return fail(c, SWARM_E_INVALID, "swarm_bind_reset_tapes: null argument");
+  c->place = place;
+  c->ptape = ptape;
+  return SWARM_OK;
+}
+
+const char* swarm_path_name(swarm_handle h) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  return c ? c->path_name.c_str() : "";
+}
+
+int swarm_last_launch_count(swarm_handle h) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  return c ? c->launches : 0;
+}
+
+static int do_reset(Ctx* c, const uint8_t* mask, int mode, cudaStream_t s) {
+  if (!c->has_state || !c->place || !c->ptape) return fail(c, SWARM_E_STATE, "reset: bind state and reset tapes first");
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  StepParams p = base_params(c);
+  c->launches = 0;
+  if (c->fused) {
+#define CALL(L, A) CUDA_TRY(c, (launch_fused_reset<L, A>(p, mask, mode == 0 ? 1 : 0, s)))
+    FUSED_DISPATCH(c, CALL);
+#undef CALL
+  } else {
+    reset_kernel<<<c->sc.env_grid, c->per_env_threads, 0, s>>>(p, c->sc, mask, mode);
+    CUDA_TRY(c, cudaGetLastError());
+  }
+  c->launches = 1;
+  return SWARM_OK;
+}
+
+int swarm_reset(swarm_handle h, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return fail(nullptr, SWARM_E_INVALID, "swarm_reset: null handle");
+  return do_reset(c, nullptr, 0, (cudaStream_t)stream);
+}
+
+int swarm_autoreset(swarm_handle h, const uint8_t* mask, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return fail(nullptr, SWARM_E_INVALID, "swarm_autoreset: null handle");
+  return do_reset(c, mask, 1, (cudaStream_t)stream);
+}
+
+int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* out, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || !in || !out) return fail(c, SWARM_E_INVALID, "swarm_step: null argument");
+  if (!c->has_state) return fail(c, SWARM_E_STATE, "swarm_step: bind state first");
+  if (c->cfg.auto_reset && (!c->place || !c->ptape))
+    return fail(c, SWARM_E_STATE, "swarm_step: auto_reset needs bound reset tapes");
+  if (!in->actions || !in->retarget || (!in->slab && c->cfg.slab_len > 0))
+    return fail(c, SWARM_E_INVALID, "swarm_step: null input tape");
+  if (!out->done || !out->eaten || !out->reward || !out->counts || !out->pred_prev || !out->pred_next ||
+      !out->step_orient || !out->step_target || !out->consumed)
+    return fail(c, SWARM_E_INVALID, "swarm_step: a required output pointer is null");
+  if ((out->term_x == nullptr) != (out->term_y == nullptr))
+    return fail(c, SWARM_E_INVALID, "swarm_step: term_x and term_y go together");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  StepParams p = base_params(c);
+  p.actions = in->actions; p.retarget = in->retarget; p.slab = in->slab;
+  p.w_att = in->w_attraction; p.w_rep = in->w_repulsion; p.w_ali = in->w_alignment;
+  p.t_vf = in->vf_size < 0 ? -1 : clampi(in->vf_size >= p.S ? p.S : in->vf_size + 1, 0, p.S);
+  p.done = out->done; p.eaten = out->eaten; p.reward = out->reward; p.counts = out->counts;
+  p.pred_prev = out->pred_prev; p.pred_next = out->pred_next; p.step_orient = out->step_orient;
+  p.step_target = out->step_target; p.consumed = out->consumed; p.term_x = out->term_x; p.term_y = out->term_y;
+  p.agent_reward = out->agent_reward; p.agent_counts = out->agent_counts; p.eff_action = out->eff_action;
+  const bool vf = p.t_vf >= 0;
+  c->launches = 0;
+  if (c->fused) {
+#define CALL(L, A) CUDA_TRY(c, (launch_fused_step<L, A>(p, vf, s)))
+    FUSED_DISPATCH(c, CALL);
+#undef CALL
+    c->launches = 1;
+    return SWARM_OK;
+  }
+  // ---- staged path -------------------------------------------------------------------------------
+  const StagedScratch& sc = c->sc;
+  const long long total = (long long)p.E * p.N;
+  {
+    const long long nvec = std::max<long long>(1, total >> 3);
+    const int grid = (int)std::min<long long>((nvec + 255) / 256, (long long)c->num_sms * 16);
+    move_kernel<<<grid, 256, 0, s>>>(total, p.N, p.S, p.x, p.y, p.actions, sc.nx, sc.ny, sc.eff, p.err);
+  }
+  collide_kernel<<<sc.env_grid, c->per_env_threads, 0, s>>>(p, sc);
+  {
+    PredIO io;
+    io.E = p.E; io.N = p.N; io.S = p.S; io.xo = p.x; io.yo = p.y; io.xn = sc.nx; io.yn = sc.ny;
+    io.retarget = p.retarget; io.frozen = p.frozen; io.px = p.px; io.py = p.py; io.target = p.target;
+    io.orient = p.orient; io.pred_prev = p.pred_prev; io.pred_next = p.pred_next; io.step_orient = p.step_orient;
+    io.step_target = p.step_target; io.done = p.done; io.eaten = p.eaten; io.err = p.err;
+    predator_kernel<<<(p.E * 32 + 255) / 256, 256, 0, s>>>(io);
+  }
+  {
+    const long long words = (long long)p.E * sc.NW;
+    pairprep_kernel<<<(int)((words + 255) / 256), 256, 0, s>>>(p.E, p.N, p.S, sc.NW, sc.nx, sc.ny, sc.eff, sc.pairw,
+                                                              vf ? sc.vfw : nullptr, sc.pcounts);
+  }
+  pairwise_launch(p, sc, sc.nx, sc.ny, p.done, vf, c->num_sms, s);
+  if (vf) finalize_kernel<true><<<sc.env_grid, 256, 0, s>>>(p, sc);
+  else finalize_kernel<false><<<sc.env_grid, 256, 0, s>>>(p, sc);
+  c->launches = 6;
+  if (p.auto_reset) {
+    reset_kernel<<<sc.env_grid, c->per_env_threads, 0, s>>>(p, sc, p.done, 1);
+    c->launches = 7;
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return SWARM_OK;
+}
+
+// ---- standalone kernels ------------------------------------------------------------------------------
+
+int swarm_move(int32_t E, int32_t N, int32_t S, const int16_t* x, const int16_t* y, const uint8_t* actions,
+               int16_t* out_x, int16_t* out_y, void* stream) {
+  if (E < 1 || N < 1 || S < 2 || !x || !y || !actions || !out_x || !out_y)
+    return fail(nullptr, SWARM_E_INVALID, "swarm_move: bad argument");
+  if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)out_x | (uintptr_t)out_y) & 15 || ((uintptr_t)actions & 7))
+    return fail(nullptr, SWARM_E_INVALID, "swarm_move: pointers must be 16-byte (positions) / 8-byte (actions) aligned");
+  const long long total = (long long)E * N;
+  const long long nvec = std::max<long long>(1, total >> 3);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)std::min<long long>((nvec + 255) / 256, (long long)sms * 16);
+  move_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(total, N, S, x, y, actions, out_x, out_y, nullptr, nullptr);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  return SWARM_OK;
+}
+
+int swarm_predator(int32_t E, int32_t N, int32_t S, const int16_t* x_old, const int16_t* y_old,
+                   const int16_t* x_new, const int16_t* y_new, const uint8_t* retarget, int16_t* px, int16_t* py,
+                   int32_t* target, uint8_t* pred_orient, int16_t* pred_prev, uint8_t* done, int32_t* eaten,
+                   void* stream) {
+  if (E < 1 || N < 1 || S < 2 || !x_old || !y_old || !x_new || !y_new || !retarget || !px || !py || !target ||
+      !pred_orient || !done || !eaten)
+    return fail(nullptr, SWARM_E_INVALID, "swarm_predator: bad argument");
+  PredIO io;
+  memset(&io, 0, sizeof(io));
+  io.E = E; io.N = N; io.S = S; io.xo = x_old; io.yo = y_old; io.xn = x_new; io.yn = y_new;
+  io.retarget = retarget; io.px = px; io.py = py; io.target = target; io.orient = pred_orient;
+  io.pred_prev = pred_prev; io.done = done; io.eaten = eaten;
+  predator_kernel<<<(int)(((long long)E * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(io);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  return SWARM_OK;
+}
+
+int swarm_pairwise(int32_t E, int32_t N, int32_t S, int32_t attraction_thresh, int32_t repulsion_thresh,
+                   const int16_t* x, const int16_t* y, const uint8_t* skip, int32_t* out_counts, void* stream) {
+  if (E < 1 || N < 2 || N > SWARM_MAX_AGENTS || S < 2 || S > SWARM_MAX_GRID || !x || !y || !out_counts)
+    return fail(nullptr, SWARM_E_INVALID, "swarm_pairwise: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  StepParams p;
+  memset(&p, 0, sizeof(p));
+  p.E = E;
+  fill_thresholds(p, N, S, attraction_thresh, repulsion_thresh);
+  p.t_vf = -1;
+  StagedScratch sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.NW = (N + 1) / 2;
+  void* block = nullptr;
+  const size_t b_pairw = align_up((size_t)E * sc.NW * 16, 256), b_pc = (size_t)E * N * 32 + 64;
+  CUDA_TRY(nullptr, cudaMallocAsync(&block, b_pairw + b_pc, s));
+  sc.pairw = (uint4*)block;
+  sc.pcounts = (unsigned*)((char*)block + b_pairw);
+  const long long words = (long long)E * sc.NW;
+  pairprep_kernel<<<(int)((words + 255) / 256), 256, 0, s>>>(E, N, S, sc.NW, x, y, nullptr, sc.pairw, nullptr,
+                                                            sc.pcounts);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  pairwise_launch(p, sc, x, y, skip, false, sms, s);
+  const long long agents = (long long)E * N;
+  pair_counts_kernel<<<(int)((agents + 255) / 256), 256, 0, s>>>(p, sc.pcounts, skip, out_counts);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  CUDA_TRY(nullptr, cudaFreeAsync(block, s));
+  return SWARM_OK;
+}
+
+// ---- statistics -----------------------------------------------------------------------------------------
+
+int swarm_stats_read(swarm_handle h, double out[8], void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || !out) return fail(c, SWARM_E_INVALID, "swarm_stats_read: null argument");
+  if (!c->cfg.track_stats || !c->has_state) return fail(c, SWARM_E_STATE, "swarm_stats_read: track_stats is off");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  stats_reduce_kernel<<<1, 1024, 0, s>>>(c->cfg.num_envs, c->st.fin_count, c->st.fin_len, c->st.fin_ret, c->st.ep_len,
+                                         c->d_stats);
+  CUDA_TRY(c, cudaGetLastError());
+  CUDA_TRY(c, cudaMemcpyAsync(out, c->d_stats, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(c, cudaStreamSynchronize(s));
+  return SWARM_OK;
+}
+
+static void* nccl_open() {
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  return lib;
+}
+
+int swarm_nccl_unique_id(uint8_t out_id[128]) {
+  void* lib = nccl_open();
+  if (!lib) return fail(nullptr, SWARM_E_NCCL, "libnccl.so.2 not found");
+  typedef int (*getid_t)(void*);
+  getid_t f = (getid_t)dlsym(lib, "ncclGetUniqueId");
+  if (!f) return fail(nullptr, SWARM_E_NCCL, "ncclGetUniqueId missing");
+  if (f(out_id) != 0) return fail(nullptr, SWARM_E_NCCL, "ncclGetUniqueId failed");
+  return SWARM_OK;
+}
+
+int swarm_nccl_init(swarm_handle h, const uint8_t id[128], int32_t nranks, int32_t rank) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || !id) return fail(c, SWARM_E_INVALID, "swarm_nccl_init: null argument");
+  c->nccl_lib = nccl_open();
+  if (!c->nccl_lib) return fail(c, SWARM_E_NCCL, "libnccl.so.2 not found");
+  struct uid { char b[128]; } u;
+  memcpy(u.b, id, 128);
+  typedef int (*init_t)(void**, int, uid, int);
+  init_t f = (init_t)dlsym(c->nccl_lib, "ncclCommInitRank");
+  if (!f) return fail(c, SWARM_E_NCCL, "ncclCommInitRank missing");
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  const int rc = f(&c->nccl_comm, nranks, u, rank);
+  if (rc != 0) return fail(c, SWARM_E_NCCL, "ncclCommInitRank failed, code " + std::to_string(rc));
+  return SWARM_OK;
+}
+
+int swarm_stats_allreduce(swarm_handle h, double inout[8], void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || !inout) return fail(c, SWARM_E_INVALID, "swarm_stats_allreduce: null argument");
+  if (!c->nccl_comm) return fail(c, SWARM_E_STATE, "swarm_stats_allreduce: call swarm_nccl_init first");
+  typedef int (*ar_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  ar_t f = (ar_t)dlsym(c->nccl_lib, "ncclAllReduce");
+  if (!f) return fail(c, SWARM_E_NCCL, "ncclAllReduce missing");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  CUDA_TRY(c, cudaMemcpyAsync(c->d_stats, inout, 8 * sizeof(double), cudaMemcpyHostToDevice, s));
+  const int rc = f(c->d_stats, c->d_stats, 8, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl_comm, s);
+  if (rc != 0) return fail(c, SWARM_E_NCCL, "ncclAllReduce failed, code " + std::to_string(rc));
+  CUDA_TRY(c, cudaMemcpyAsync(inout, c->d_stats, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(c, cudaStreamSynchronize(s));
+  return SWARM_OK;
+}
+
+// ---- INT32 peak ------------------------------------------------------------------------------------------
+
+int swarm_int32_peak(int32_t device, int32_t kind, double* out_lane_ops_per_s, void* stream) {
+  if (!out_lane_ops_per_s || kind < 0 || kind > 4) return fail(nullptr, SWARM_E_INVALID, "swarm_int32_peak: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  unsigned* d = nullptr;
+  CUDA_TRY(nullptr, cudaMalloc(&d, 64));
+  const int iters = 4096, grid = sms * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, s);
+    switch (kind) {
+      case 0: int32_peak_kernel<0><<<grid, threads, 0, s>>>(iters, 12345u + rep, d); break;
+      case 1: int32_peak_kernel<1><<<grid, threads, 0, s>>>(iters, 12345u + rep, d); break;
+      case 2: int32_peak_kernel<2><<<grid, threads, 0, s>>>(iters, 12345u + rep, d); break;
+      case 3: int32_peak_kernel<3><<<grid, threads, 0, s>>>(iters, 12345u + rep, d); break;
+      default: int32_peak_kernel<4><<<grid, threads, 0, s>>>(iters, 12345u + rep, d); break;
+    }
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaError_t e = cudaGetLastError();
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(nullptr, SWARM_E_CUDA, cudaGetErrorString(e));
+  const double ops = (double)grid * threads * (double)iters * 8.0 * 2.0;   // CH chains x 2 ops per iteration
+  *out_lane_ops_per_s = ops / ((double)best * 1e-3);
+  return SWARM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+// swarm_common.cuh -- device helpers shared by the fused and the staged kernels (sm_100a).
+//
+// Reference semantics restated here (citations into /root/reference/gym_swarm/envs/swarm_discrete_env.py,
+// "SDE"): action table SDE:467-475, wrap rule SDE:45-57 / 60-80, predator pursuit SDE:142-165,
+// nearest-neighbour tie rule SDE:121-129 (stable argsort), reward formulas SDE:330-379.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/swarm_abi.h"
+
+namespace swarm {
+
+// ----------------------------------------------------------------------------------------------
+// Kernel parameter block (by-value kernel argument).
+// ----------------------------------------------------------------------------------------------
+struct StepParams {
+  int E, N, S;
+  // Integer thresholds, all clamped to [0,S].  With c(t) = #{j != i : D_ij < t} (D = plain Chebyshev):
+  //   #{D < rep}              = c(t_rep)            #{S-D < rep}  = (N-1) - c(t_repf),  t_repf = S-rep+1
+  //   #{(D<att)==(D>=rep)}    = |c(t_att)-c(t_rep)| #{XNOR on S-D} = |c(t_repf)-c(t_attf)|, t_attf = S-att+1
+  int t_rep, t_att, t_repf, t_attf;
+  int diag_rep, diag_att;  // contribution of the diagonal (D=0, S-D=S) to the literal N x N sums
+  int t_vf;                // D <= vf  <=>  D < t_vf ; -1: no visual-field gate
+  double w_att, w_rep, w_ali, inv_nn;  // reward_type weights, 1/(N(N-1))
+  float eat;
+  int K, PL, KP, R;
+  int auto_reset, track_stats;
+  int bitmap_words;  // per-env smem occupancy bitmap words (0: not used)
+  // state
+  int16_t *x, *y, *px, *py;
+  int32_t* target;
+  uint8_t *orient, *frozen;
+  uint32_t *err, *reset_count;
+  uint32_t *ep_len, *fin_count, *fin_len;
+  float *ep_ret, *fin_ret;
+  // tapes
+  const int16_t *place, *ptape;
+  const uint8_t *actions, *retarget, *slab;
+  // outputs
+  uint8_t* done;
+  int32_t* eaten;
+  float* reward;
+  int32_t* counts;
+  int16_t *pred_prev, *pred_next;
+  uint8_t* step_orient;
+  int32_t *step_target, *consumed;
+  int16_t *term_x, *term_y;
+  float* agent_reward;
+  int32_t* agent_counts;
+  uint8_t* eff_action;
+};
+
+// ----------------------------------------------------------------------------------------------
+// Action table SDE:467-475 as 2-bit LUTs: (d+1) for action a sits at bits [2a, 2a+2).
+//   dx: -1 -1  0  1  1  1  0 -1  0      dy:  0 -1 -1 -1  0  1  1  1  0
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ int move_dx(int a) { return (int)((0x11A90u >> (2 * a)) & 3u) - 1; }
+__device__ __forceinline__ int move_dy(int a) { return (int)((0x1A901u >> (2 * a)) & 3u) - 1; }
+
+// One-step torus wrap, valid because |move| <= 1 (SDE:52-56, 70-79).
+__device__ __forceinline__ int wrap1(int p, int S) { return p > S - 1 ? 0 : (p < 0 ? S - 1 : p); }
+
+// Inverse action table (SDE:161-163): nibble index (mx+1)*3 + (my+1) -> action id.
+__device__ __forceinline__ int move_to_action(int mx, int my) {
+  return (int)((0x543682701ULL >> (4 * ((mx + 1) * 3 + (my + 1)))) & 0xFULL);
+}
+
+__device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
+
+// Predator pursuit SDE:142-165 given the (old) target position.  Returns new position + orientation.
+__device__ __forceinline__ void pursue(int px, int py, int tx, int ty, int S, int& npx, int& npy, int& orient) {
+  const int cx = px - tx, cy = py - ty;                    // SDE:142 signed coordinate distance
+  int mx = cx >= 1 ? -1 : (cx <= -1 ? 1 : 0);              // SDE:145-149
+  int my = cy >= 1 ? -1 : (cy <= -1 ? 1 : 0);
+  if (max(cx, cy) > (S >> 1)) { mx = -mx; my = -my; }      // SDE:152-159 SIGNED max, floor(S/2)
+  orient = move_to_action(mx, my);                         // SDE:161-163
+  npx = wrap1(px + mx, S);                                 // SDE:164
+  npy = wrap1(py + my, S);
+}
+
+// Nearest-neighbour keys (SDE:111-131, canonical stable-sort tie rule):
+//   lo = lowest index at minimum distance, hi = highest; target = lo if lo==hi or 2*dmin < S else hi.
+__device__ __forceinline__ unsigned nn_key_lo(int d, int i) { return ((unsigned)d << 16) | (unsigned)i; }
+__device__ __forceinline__ unsigned nn_key_hi(int d, int i) { return ((unsigned)d << 16) | (unsigned)(0xFFFF - i); }
+__device__ __forceinline__ int nn_pick(unsigned klo, unsigned khi, int S) {
+  const int dmin = (int)(klo >> 16);
+  const int lo = (int)(klo & 0xFFFFu);
+  const int hi = 0xFFFF - (int)(khi & 0xFFFFu);
+  return (lo == hi || 2 * dmin < S) ? lo : hi;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Packed 16x2 Chebyshev / threshold machinery (Blackwell DPX: VIADDMNMX.S16x2[.RELU]).
+// A "pair word" carries two agents j0 (low half) and j1 (high half):
+//   {xj2, yj2, nxj2, nyj2} = packed x, y, -x, -y.     Own agent i: XI = x_i in both halves, etc.
+//   m = min(xj-xi, xi-xj, yj-yi, yi-yj) = -D per half          (1 VIADD.16x2 + 3 VIADDMNMX.S16x2)
+//   [D < t] = clamp(t + m, 0, 1) per half                       (1 VIADDMNMX.S16x2.RELU)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned rep2(int v) { return ((unsigned)v & 0xFFFFu) * 0x10001u; }
+__device__ __forceinline__ unsigned pack2(int lo, int hi) { return ((unsigned)lo & 0xFFFFu) | ((unsigned)hi << 16); }
+
+__device__ __forceinline__ unsigned neg_cheb2(unsigned XI, unsigned YI, unsigned NXI, unsigned NYI, const uint4& w) {
+  unsigned m = __vadd2(w.x, NXI);
+  m = __viaddmin_s16x2(XI, w.z, m);
+  m = __viaddmin_s16x2(w.y, NYI, m);
+  m = __viaddmin_s16x2(YI, w.w, m);
+  return m;
+}
+__device__ __forceinline__ unsigned lt2(unsigned T2, unsigned m) { return __viaddmin_s16x2_relu(T2, m, 0x00010001u); }
+__device__ __forceinline__ int hsum2(unsigned v) { return (int)(v & 0xFFFFu) + (int)(v >> 16); }
+
+// Unit-vector decomposition of an action for the alignment term (SDE:346-347: cosine_distances/2).
+//   even ids are axis moves, odd ids diagonal moves, 8 = no move (zero vector: cos = 0 with everyone).
+//   cos(a_i,a_j) = u_i . u_j  with u = m/|m|;   the sqrt(2)/2 factors are kept symbolic:
+//   cosSum_i = sum_j cos = P_i/2 + (sqrt2/2) Q_i  with integers
+//     axis i:  P_i = 2 (mx Ax + my Ay),  Q_i = mx Dx + my Dy
+//     diag i:  P_i =    mx Dx + my Dy,   Q_i = mx Ax + my Ay
+//   (Ax,Ay) / (Dx,Dy) = summed moves of the axis / diagonal movers that are counted for agent i.
+__device__ __forceinline__ void align_PQ(int a, int Ax, int Ay, int Dx, int Dy, int self_gate, int& P, int& Q) {
+  if (a >= 8) { P = 0; Q = 0; return; }
+  const int mx = move_dx(a), my = move_dy(a);
+  const int sa = mx * Ax + my * Ay, sd = mx * Dx + my * Dy;
+  if (a & 1) { P = sd - 2 * self_gate; Q = sa; }      // minus own contribution (u_i.u_i = 1 -> P += -2)
+  else       { P = 2 * sa - 2 * self_gate; Q = sd; }
+}
+
+// Per-agent reward epilogue (SDE:371-379) from integer pieces.
+//   cR=c(t_rep) cA=c(t_att) cRf=c(t_repf) cAf=c(t_attf) (off-diagonal counts),
+//   vis = number of j != i counted for alignment, P,Q as above.
+struct AgentTerms {
+  int rep_i;    // rew_rep_i  = -(sum R1[i,:] + sum R2[i,:] - 1)      SDE:372
+  int att_i;    // rew_attr_i =   sum A1[i,:] + sum A2[i,:]          SDE:373
+  double una;   // sum_j unalign[i,j]                                SDE:374
+};
+__device__ __forceinline__ AgentTerms agent_terms(const StepParams& p, int cR, int cA, int cRf, int cAf, int vis,
+                                                  int P, int Q) {
+  AgentTerms t;
+  const int offR = cR + (p.N - 1) - cRf;
+  const int offA = iabs(cA - cR) + iabs(cRf - cAf);
+  t.rep_i = -(offR + p.diag_rep - 1);
+  t.att_i = offA + p.diag_att;
+  t.una = 0.5 * (double)vis - 0.25 * (double)P - 0.35355339059327376220 * (double)Q;
+  return t;
+}
+
+}  // namespace swarm

@@ -1,0 +1,423 @@
+"""Host-side mirror of the reference Gym surface for the swarm transition.
+
+``BatchedSwarmEnv``  -- E independent environments stepped together on one B200; tensor I/O.
+``SwarmEnv``         -- drop-in for the reference ``DiscreteSwarmEnv`` (one env, dict I/O):
+                        same constructor defaults, ``reset()``, ``step(action[, reward_type])``,
+                        ``set_env_parameters``, ``set_reward_parameters`` and public attributes as
+                        ``/root/reference/gym_swarm/envs/swarm_discrete_env.py:168-406`` ("SDE").
+``ContinuousSwarmEnv`` -- alias: the reference's swarm_continuous_env.py is byte-identical to the
+                        discrete file except for the class name.
+
+All compute happens in ``libswarm_b200.so`` (sm_100a CUDA) through ctypes; PyTorch only provides
+device memory and the current stream.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import tapes as _tapes
+
+REWARD_KEYS = ("survival", "attraction", "repulsion", "alignment", "sum")
+DEFAULT_REWARD_TYPE = {"attraction": True, "repulsion": True, "alignment": True,
+                       "indiv_rewards": False, "vf_size": None}           # SDE:223-227
+
+# SDE:467-475 / 477-485
+action_to_move = {0: np.array([-1, 0]), 1: np.array([-1, -1]), 2: np.array([0, -1]), 3: np.array([1, -1]),
+                  4: np.array([1, 0]), 5: np.array([1, 1]), 6: np.array([0, 1]), 7: np.array([-1, 1]),
+                  8: np.array([0, 0])}
+ACTION_LOOKUP = {0: "left", 1: "left-down", 2: "down", 3: "right-down", 4: "right", 5: "right-up", 6: "up",
+                 7: "left-up", 8: "no-move"}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _as_dev(a, dtype, device):
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=device, dtype=dtype)
+    else:
+        t = torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device)
+    return t.contiguous()
+
+
+class BatchedSwarmEnv:
+    """E environments, N agents + 1 predator each, on an S x S grid, on one GPU.
+
+    Randomness is explicit (tapes.py): reset tapes are bound once, the per-step ``retarget`` flags
+    and re-draw ``slab`` either come from the caller (parity runs) or from an internal host
+    generator that pre-draws chunks.
+    """
+
+    def __init__(self, num_envs, num_agents=4, obs_space_size=20, attraction_thresh=5, repulsion_thresh=2,
+                 predator_eat_rew=-10, device="cuda:0", auto_reset=True, track_stats=False, slab_len=None,
+                 place_extra=None, pred_attempts=8, reset_slots=4, per_agent=True, debug_outputs=False,
+                 path="auto", seed=0, tape_chunk=16):
+        self.lib = _lib.load()                      # raises when the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise _lib.SwarmLibraryError("no CUDA device: the swarm transition has no CPU fallback")
+        self.device = torch.device(device)
+        self.E, self.N, self.S = int(num_envs), int(num_agents), int(obs_space_size)
+        self.attraction_thresh, self.repulsion_thresh = attraction_thresh, repulsion_thresh
+        self.predator_eat_rew = predator_eat_rew
+        self.auto_reset, self.track_stats = bool(auto_reset), bool(track_stats)
+        self.K = _tapes.default_slab_len(self.N) if slab_len is None else int(slab_len)
+        self.KR = _tapes.default_place_extra(self.N) if place_extra is None else int(place_extra)
+        self.PL = 2 * self.N + 2 * self.KR
+        self.KP, self.R = int(pred_attempts), int(reset_slots)
+        self.per_agent, self.debug_outputs = bool(per_agent), bool(debug_outputs)
+        self._rng = np.random.default_rng(seed)
+        self._tape_chunk = int(tape_chunk)
+        self._chunk = None
+        self._chunk_pos = 0
+
+        cfg = _lib.Config(
+            abi_version=_lib.ABI_VERSION, device=self.device.index or 0, num_envs=self.E, num_agents=self.N,
+            grid_size=self.S, attraction_thresh=int(math.ceil(attraction_thresh)),
+            repulsion_thresh=int(math.ceil(repulsion_thresh)), predator_eat_rew=float(predator_eat_rew),
+            slab_len=self.K, place_len=self.PL, pred_attempts=self.KP, reset_slots=self.R,
+            auto_reset=int(self.auto_reset), track_stats=int(self.track_stats),
+            path={"auto": _lib.PATH_AUTO, "staged": _lib.PATH_STAGED, "fused": _lib.PATH_FUSED}[path])
+        self._h = C.c_void_p()
+        _lib.check(self.lib.swarm_create(C.byref(cfg), C.byref(self._h)))
+        self.path_name = self.lib.swarm_path_name(self._h).decode()
+
+        E, N, dev = self.E, self.N, self.device
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        # persistent state (SoA, int16 positions)
+        self.x, self.y = z((E, N), torch.int16), z((E, N), torch.int16)
+        self.px, self.py = z((E,), torch.int16), z((E,), torch.int16)
+        self.target = z((E,), torch.int32)
+        self.pred_orient, self.frozen = z((E,), torch.uint8), z((E,), torch.uint8)
+        self.err, self.reset_count = z((E,), torch.int32), z((E,), torch.int32)
+        if self.track_stats:
+            self.ep_len, self.ep_ret = z((E,), torch.int32), z((E, 4), torch.float32)
+            self.fin_count, self.fin_len = z((E,), torch.int32), z((E,), torch.int32)
+            self.fin_ret = z((E, 4), torch.float32)
+        else:
+            self.ep_len = self.ep_ret = self.fin_count = self.fin_len = self.fin_ret = None
+        st = _lib.State(x=_ptr(self.x), y=_ptr(self.y), px=_ptr(self.px), py=_ptr(self.py), target=_ptr(self.target),
+                        pred_orient=_ptr(self.pred_orient), frozen=_ptr(self.frozen), err=_ptr(self.err),
+                        reset_count=_ptr(self.reset_count), ep_len=_ptr(self.ep_len), ep_ret=_ptr(self.ep_ret),
+                        fin_count=_ptr(self.fin_count), fin_len=_ptr(self.fin_len), fin_ret=_ptr(self.fin_ret))
+        _lib.check(self.lib.swarm_bind_state(self._h, C.byref(st)), self._h)
+        # step outputs (owned by the env, overwritten by the next step)
+        self.done, self.eaten = z((E,), torch.uint8), z((E,), torch.int32)
+        self.reward, self.counts = z((E, 5), torch.float32), z((E, 2), torch.int32)
+        self.pred_prev, self.pred_next = z((E, 2), torch.int16), z((E, 2), torch.int16)
+        self.step_orient, self.step_target = z((E,), torch.uint8), z((E,), torch.int32)
+        self.consumed = z((E,), torch.int32)
+        self.term_x, self.term_y = z((E, N), torch.int16), z((E, N), torch.int16)
+        self.agent_reward = z((E, N, 4), torch.float32) if self.per_agent else None
+        self.agent_counts = z((E, N, 2), torch.int32) if self.debug_outputs else None
+        self.eff_action = z((E, N), torch.uint8) if self.debug_outputs else None
+        self._out = _lib.StepOut(
+            done=_ptr(self.done), eaten=_ptr(self.eaten), reward=_ptr(self.reward), counts=_ptr(self.counts),
+            pred_prev=_ptr(self.pred_prev), pred_next=_ptr(self.pred_next), step_orient=_ptr(self.step_orient),
+            step_target=_ptr(self.step_target), consumed=_ptr(self.consumed), term_x=_ptr(self.term_x),
+            term_y=_ptr(self.term_y), agent_reward=_ptr(self.agent_reward), agent_counts=_ptr(self.agent_counts),
+            eff_action=_ptr(self.eff_action))
+        self._place = self._ptape = None
+        self._nccl_ready = False
+
+    # ---- lifecycle -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.swarm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- tapes -------------------------------------------------------------------------------------
+    def set_reset_tapes(self, place, ptape):
+        """place int16[R,E,2N+2KR], ptape int16[R,E,KP,2] (tapes.make_reset_tapes)."""
+        place = _as_dev(place, torch.int16, self.device)
+        ptape = _as_dev(ptape, torch.int16, self.device)
+        assert tuple(place.shape) == (self.R, self.E, self.PL), (tuple(place.shape), (self.R, self.E, self.PL))
+        assert tuple(ptape.shape) == (self.R, self.E, self.KP, 2), tuple(ptape.shape)
+        self._place, self._ptape = place, ptape
+        _lib.check(self.lib.swarm_bind_reset_tapes(self._h, _ptr(place), _ptr(ptape)), self._h)
+
+    def _ensure_reset_tapes(self):
+        if self._place is None:
+            rt = _tapes.make_reset_tapes(self._rng, self.R, self.E, self.N, self.S, KR=self.KR, KP=self.KP)
+            self.set_reset_tapes(rt.place, rt.ptape)
+
+    def _next_step_tapes(self):
+        if self._chunk is None or self._chunk_pos >= self._tape_chunk:
+            T = self._tape_chunk
+            roll = self._rng.random(size=(T, self.E))
+            retarget = torch.from_numpy((roll < 0.1).astype(np.uint8)).to(self.device)
+            slab = torch.from_numpy(self._rng.integers(0, 8, size=(T, self.E, self.K), dtype=np.uint8)).to(self.device)
+            self._chunk, self._chunk_pos = (retarget, slab), 0
+        r, s = self._chunk[0][self._chunk_pos], self._chunk[1][self._chunk_pos]
+        self._chunk_pos += 1
+        return r, s
+
+    # ---- Gym-style surface (tensor I/O) ----------------------------------------------------------
+    def reset(self):
+        """SDE:197-221 for every env. Returns the observation (x, y): int16[E,N] views of the state."""
+        self._ensure_reset_tapes()
+        _lib.check(self.lib.swarm_reset(self._h, self._stream()), self._h)
+        return self.x, self.y
+
+    def step(self, actions, reward_type=None, retarget=None, slab=None):
+        """SDE:223-267 for every env.
+
+        actions: uint8[E,N] (ids 0..8).  Returns (obs, reward, done, info):
+          obs    = (x, y) int16[E,N] (post auto-reset where done)
+          reward = {"global": f32[E,5] (survival, attraction, repulsion, alignment, sum),
+                    "agents": f32[E,N,4] (attraction, repulsion, alignment, sum) or None,
+                    "counts": i32[E,2] integer rew_rep / rew_attr}
+          done   = uint8[E]
+          info   = predator_state / predator_next_state int16[E,2], predator_orientation, eaten, ...
+        """
+        rt = DEFAULT_REWARD_TYPE if reward_type is None else reward_type
+        vf = rt.get("vf_size", None)
+        actions = _as_dev(actions, torch.uint8, self.device)
+        assert tuple(actions.shape) == (self.E, self.N), tuple(actions.shape)
+        if retarget is None or slab is None:
+            r2, s2 = self._next_step_tapes()
+            retarget = r2 if retarget is None else retarget
+            slab = s2 if slab is None else slab
+        retarget = _as_dev(retarget, torch.uint8, self.device)
+        slab = _as_dev(slab, torch.uint8, self.device)
+        assert tuple(retarget.shape) == (self.E,) and tuple(slab.shape) == (self.E, self.K), (retarget.shape, slab.shape)
+        sin = _lib.StepIn(actions=_ptr(actions), retarget=_ptr(retarget), slab=_ptr(slab),
+                          w_attraction=float(rt["attraction"]), w_repulsion=float(rt["repulsion"]),
+                          w_alignment=float(rt["alignment"]), vf_size=-1 if vf is None else int(math.floor(vf)))
+        self._keep = (actions, retarget, slab)      # keep inputs alive until the kernels ran
+        _lib.check(self.lib.swarm_step(self._h, C.byref(sin), C.byref(self._out), self._stream()), self._h)
+        reward = {"global": self.reward, "agents": self.agent_reward, "counts": self.counts}
+        info = {"predator_state": self.pred_prev, "predator_next_state": self.pred_next,
+                "predator_orientation": self.step_orient, "predator_target": self.step_target, "eaten": self.eaten,
+                "terminal_state": (self.term_x, self.term_y), "redraws": self.consumed, "errors": self.err}
+        return (self.x, self.y), reward, self.done, info
+
+    def last_launch_count(self):
+        return int(self.lib.swarm_last_launch_count(self._h))
+
+    def check_errors(self):
+        """Raise if any env has a sticky error bit other than STEP_WHEN_DONE."""
+        bad = (self.err & ~_lib.ERR_STEP_WHEN_DONE).nonzero()
+        if bad.numel():
+            e = int(bad[0])
+            raise _lib.SwarmLibraryError(f"env {e} error bits {int(self.err[e])} (tape exhausted or bad action)")
+
+    # ---- statistics -------------------------------------------------------------------------------
+    STAT_KEYS = ("episodes", "sum_length", "sum_return", "sum_survival", "sum_attraction", "sum_repulsion",
+                 "sum_alignment", "running_steps")
+
+    def stats(self):
+        out = (C.c_double * 8)()
+        _lib.check(self.lib.swarm_stats_read(self._h, out, self._stream()), self._h)
+        return dict(zip(self.STAT_KEYS, [float(v) for v in out]))
+
+    def init_nccl(self, rank, world_size, broadcast_bytes):
+        """Bootstrap the library's own NCCL communicator; ``broadcast_bytes(b, src=0)`` must return
+        rank 0's 128-byte unique id on every rank (e.g. via torch.distributed.broadcast_object_list)."""
+        uid = (C.c_uint8 * 128)()
+        if rank == 0:
+            _lib.check(self.lib.swarm_nccl_unique_id(uid))
+        raw = broadcast_bytes(bytes(uid))
+        uid = (C.c_uint8 * 128).from_buffer_copy(raw)
+        _lib.check(self.lib.swarm_nccl_init(self._h, uid, world_size, rank), self._h)
+        self._nccl_ready = True
+
+    def stats_allreduce(self):
+        """Sum the episode statistics over all ranks (NCCL over NVLink, 8 doubles)."""
+        st = self.stats()
+        buf = (C.c_double * 8)(*[st[k] for k in self.STAT_KEYS])
+        _lib.check(self.lib.swarm_stats_allreduce(self._h, buf, self._stream()), self._h)
+        return dict(zip(self.STAT_KEYS, [float(v) for v in buf]))
+
+    # ---- numpy views for tests / the compatibility class ------------------------------------------
+    def state_numpy(self):
+        torch.cuda.synchronize(self.device)
+        return dict(x=self.x.cpu().numpy(), y=self.y.cpu().numpy(), px=self.px.cpu().numpy(), py=self.py.cpu().numpy(),
+                    target=self.target.cpu().numpy(), err=self.err.cpu().numpy().astype(np.uint32),
+                    frozen=self.frozen.cpu().numpy())
+
+    def step_numpy(self, actions, slab, retarget, weights=(1.0, 1.0, 1.0), vf=None):
+        rt = {"attraction": weights[0], "repulsion": weights[1], "alignment": weights[2], "vf_size": vf}
+        self.step(actions, rt, retarget=retarget, slab=slab)
+        o = self.state_numpy()
+        o.update(done=self.done.cpu().numpy(), eaten=self.eaten.cpu().numpy(),
+                 glob=self.reward.cpu().numpy().astype(np.float64), cnt=self.counts.cpu().numpy().astype(np.int64),
+                 pred_prev=self.pred_prev.cpu().numpy(), pred_next=self.pred_next.cpu().numpy(),
+                 pred_orient=self.step_orient.cpu().numpy(), step_target=self.step_target.cpu().numpy(),
+                 consumed=self.consumed.cpu().numpy(), term_x=self.term_x.cpu().numpy(), term_y=self.term_y.cpu().numpy())
+        if self.agent_reward is not None:
+            ar = self.agent_reward.cpu().numpy().astype(np.float64)       # attraction, repulsion, alignment, sum
+            ag = np.zeros((self.E, self.N, 5))
+            ag[:, :, 1:] = ar
+            dn = o["done"].astype(bool) & (o["eaten"] >= 0)
+            idx = np.nonzero(dn)[0]
+            ag[idx, o["eaten"][idx], 0] = float(self.predator_eat_rew)
+            o["agent"] = ag
+        if self.agent_counts is not None:
+            o["agent_cnt"] = self.agent_counts.cpu().numpy().astype(np.int64)
+            o["eff"] = self.eff_action.cpu().numpy()
+        return o
+
+
+class SwarmEnv:
+    """Drop-in for the reference ``DiscreteSwarmEnv`` (SDE:168-406) backed by one GPU environment.
+
+    Differences (documented in INTEGRATION.md): randomness comes from explicit tapes drawn from a
+    seeded ``np.random.Generator`` (``seed()``), not the process-global ``np.random``; ``render`` is
+    out of scope; returned arrays are copies.
+    """
+    metadata = {"render.modes": ["human"]}
+
+    def __init__(self, device="cuda:0", seed=0):
+        self.num_agents = 4                          # SDE:184-195
+        self.obs_space_size = 20
+        self.action_space = SimpleNamespace(n=8)
+        self.observation_space = np.zeros((self.obs_space_size, self.obs_space_size))
+        self.random_placement = True
+        self.done = None
+        self.attraction_thresh = 5
+        self.repulsion_thresh = 2
+        self.predator_eat_rew = -10
+        self._device, self._seed = device, seed
+        self._rng = np.random.default_rng(seed)
+        self._env = None
+        self._key = None
+        self.predator = None
+
+    def seed(self, seed=None):
+        self._seed = seed
+        self._rng = np.random.default_rng(seed)
+        return [seed]
+
+    def set_env_parameters(self, num_agents=4, obs_space_size=20, verbose=True):   # SDE:382-392
+        self.num_agents = num_agents
+        self.obs_space_size = obs_space_size
+        if verbose:
+            print("Swarm Environment Parameters have been set to:")
+            print("\t Number of Agents: {}".format(self.num_agents))
+            print("\t State Space: {}x{} Grid".format(self.obs_space_size, self.obs_space_size))
+
+    def set_reward_parameters(self, attraction_thresh=5, repulsion_thresh=2, predator_eat_rew=-10,
+                              verbose=False):                                        # SDE:394-406
+        self.attraction_thresh = attraction_thresh
+        self.repulsion_thresh = repulsion_thresh
+        self.predator_eat_rew = predator_eat_rew
+        if verbose:
+            print("Swarm Reward Parameters have been set to:")
+            print("\t Attraction Threshold: {}".format(self.attraction_thresh))
+            print("\t Repulsion Threshold: {}".format(self.repulsion_thresh))
+            print("\t Predator Punishment: {}".format(self.predator_eat_rew))
+
+    def _build(self):
+        key = (self.num_agents, self.obs_space_size, self.attraction_thresh, self.repulsion_thresh,
+               self.predator_eat_rew)
+        if self._env is None or key != self._key:
+            if self._env is not None:
+                self._env.close()
+            self._env = BatchedSwarmEnv(1, self.num_agents, self.obs_space_size, self.attraction_thresh,
+                                        self.repulsion_thresh, self.predator_eat_rew, device=self._device,
+                                        auto_reset=False, reset_slots=1, per_agent=True, debug_outputs=True)
+            self._key = key
+
+    def _state_dict(self):
+        x = self._env.x[0].cpu().numpy().astype(np.int64)
+        y = self._env.y[0].cpu().numpy().astype(np.int64)
+        return {i: np.array([x[i], y[i]]) for i in range(self.num_agents)}
+
+    def reset(self):                                                                 # SDE:197-221
+        if not self.random_placement:
+            raise NameError("name 'states_temp' is not defined")   # the reference has no fixed-placement mode
+        self._build()
+        env = self._env
+        rt = _tapes.make_reset_tapes(self._rng, 1, 1, env.N, env.S, KR=env.KR, KP=env.KP)
+        env.set_reset_tapes(rt.place, rt.ptape)
+        env.reset()
+        env.check_errors()
+        self.current_state = self._state_dict()
+        self.orientation = dict(enumerate(rt.orient[0, 0].astype(np.int64)))         # SDE:216
+        self.predator = SimpleNamespace(
+            obs_space_size=self.obs_space_size,
+            current_state=np.array([int(env.px[0]), int(env.py[0])]), orientation=0,
+            current_target=int(env.target[0]))
+        self.done = False
+        return self.current_state
+
+    def step(self, action, reward_type=DEFAULT_REWARD_TYPE):                          # SDE:223-267
+        if self.done:
+            raise RuntimeError("Episode has finished. Call env.reset() to start a new episode.")
+        env = self._env
+        move = {}
+        for key in action.keys():
+            move[key] = action_to_move[action[key]]          # KeyError for unknown ids, as SDE:239
+        act = np.array([[int(action[i]) for i in range(self.num_agents)]], dtype=np.uint8)
+        roll = self._rng.random()
+        slab = self._rng.integers(0, 8, size=(1, env.K), dtype=np.uint8)
+        self.orientation = action                                                    # SDE:242
+        env.step(act, reward_type, retarget=np.array([roll < 0.1], dtype=np.uint8), slab=slab)
+        env.check_errors()
+        eff = env.eff_action[0].cpu().numpy()
+        self.move = {i: action_to_move[int(eff[i])] for i in range(self.num_agents)}  # SDE:252 mutates move
+        self.current_state = self._state_dict()
+        self.done = bool(env.done[0])
+        g = env.reward[0].cpu().numpy().astype(np.float64)
+        ar = env.agent_reward[0].cpu().numpy().astype(np.float64)
+        eaten = int(env.eaten[0])
+        reward = {}
+        for i in range(self.num_agents):
+            surv = float(self.predator_eat_rew) if (self.done and i == eaten) else 0
+            reward[i] = {"survival": surv, "attraction": ar[i, 0], "repulsion": ar[i, 1], "alignment": ar[i, 2],
+                         "sum": ar[i, 3]}
+        reward["global"] = dict(zip(REWARD_KEYS, g))
+        prev = env.pred_prev[0].cpu().numpy().astype(np.int64)
+        nxt = env.pred_next[0].cpu().numpy().astype(np.int64)
+        self.predator.current_state = nxt.copy()
+        self.predator.orientation = int(env.step_orient[0])
+        self.predator.current_target = int(env.step_target[0])
+        info = {"predator_state": prev, "predator_orientation": self.predator.orientation,
+                "predator_next_state": nxt.copy()}
+        return self.current_state, reward, self.done, info
+
+    def render(self, mode="rgb_array", close=False):
+        raise NotImplementedError("rendering (SDE:408-464) is out of scope of the B200 transition path")
+
+    def close(self):
+        if self._env is not None:
+            self._env.close()
+            self._env = None
+
+
+DiscreteSwarmEnv = SwarmEnv
+
+
+class ContinuousSwarmEnv(SwarmEnv):
+    """gym_swarm/envs/swarm_continuous_env.py is identical to the discrete file except for the class name."""
+
+
+def register_gym():
+    """Register ``Discrete-Swarm-v0`` / ``Continuous-Swarm-v0`` (gym_swarm/__init__.py:6-14) when a gym
+    package is importable; returns the list of ids registered."""
+    try:
+        from gym.envs.registration import register
+    except Exception:
+        try:
+            from gymnasium.envs.registration import register
+        except Exception:
+            return []
+    register(id="Discrete-Swarm-v0", entry_point="gym_swarm_b200.envs:DiscreteSwarmEnv")
+    register(id="Continuous-Swarm-v0", entry_point="gym_swarm_b200.envs:ContinuousSwarmEnv")
+    return ["Discrete-Swarm-v0", "Continuous-Swarm-v0"]

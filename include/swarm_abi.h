@@ -1,0 +1,183 @@
+/*
+ * swarm_abi.h -- C ABI of libswarm_b200.so: the B200 (sm_100a) batched implementation of the
+ * gym-swarm DiscreteSwarmEnv transition.
+ *
+ * Reference path being replaced (all citations into /root/reference):
+ *   gym_swarm/envs/swarm_discrete_env.py   ("SDE")
+ *     SDE:223-267  DiscreteSwarmEnv.step           -> swarm_step
+ *     SDE:197-221  DiscreteSwarmEnv.reset          -> swarm_reset (+ in-kernel auto-reset)
+ *     SDE:60-80    step_all_agents, SDE:467-475 action_to_move     -> swarm_move
+ *     SDE:269-292  change_position_id, SDE:246-255 re-draw loop    -> inside swarm_step
+ *     SDE:90-165   Predator.__init__/closest_target/follow_target  -> swarm_predator
+ *     SDE:294-380  swarm_reward                     -> swarm_pairwise (+ reward epilogue in swarm_step)
+ *     SDE:382-406  set_env_parameters / set_reward_parameters      -> swarm_config fields
+ *   gym_swarm/__init__.py:6-14  Gym registration (Python host side, not in this ABI)
+ *
+ * Conventions
+ *   - plain C, no torch types: every tensor is a raw device pointer (tensor.data_ptr());
+ *     the caller owns all state / tape / output memory; the library only owns small scratch.
+ *   - every function returns 0 on success, a negative SWARM_E_* code on failure;
+ *     swarm_last_error(h) returns a human readable message (h may be NULL for create errors).
+ *   - all work is enqueued on the caller-supplied cudaStream_t (passed as void*); no hidden
+ *     host threads; a handle is not thread-safe.
+ *   - per-env sticky error bits (SWARM_ERR_*) are accumulated in swarm_state.err.
+ *   - all randomness arrives as explicit tapes (see DESIGN.md "Tapes").
+ */
+#ifndef SWARM_ABI_H
+#define SWARM_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWARM_ABI_VERSION 1
+
+/* return codes */
+#define SWARM_OK 0
+#define SWARM_E_INVALID (-1)   /* bad argument / unsupported shape */
+#define SWARM_E_CUDA (-2)      /* CUDA runtime error (message has the cudaError string) */
+#define SWARM_E_STATE (-3)     /* call order problem (state or tapes not bound) */
+#define SWARM_E_NCCL (-4)      /* NCCL unavailable or failed */
+
+/* per-env error bits (swarm_state.err) */
+#define SWARM_ERR_SLAB_OVERFLOW 1u   /* collision re-draw slab (K) exhausted (SDE:249-255 has no cap) */
+#define SWARM_ERR_PLACE_OVERFLOW 2u  /* placement tape exhausted during reset (SDE:207-211) */
+#define SWARM_ERR_PRED_OVERFLOW 4u   /* predator placement attempts exhausted (SDE:99-105) */
+#define SWARM_ERR_BAD_ACTION 8u      /* action id > 8 (reference: KeyError at SDE:239) */
+#define SWARM_ERR_STEP_WHEN_DONE 16u /* stepped a finished env with auto-reset off (SDE:233-234) */
+
+/* limits */
+#define SWARM_MAX_AGENTS 16384
+#define SWARM_MAX_GRID 16384
+#define SWARM_FUSED_MAX_AGENTS 256   /* N <= this: fused warp-per-env kernel; above: staged kernels */
+
+/* swarm_config.path */
+#define SWARM_PATH_AUTO 0
+#define SWARM_PATH_STAGED 1
+#define SWARM_PATH_FUSED 2
+
+typedef struct swarm_config {
+  int32_t abi_version;       /* SWARM_ABI_VERSION */
+  int32_t device;            /* CUDA device ordinal */
+  int32_t num_envs;          /* E: environments owned by this handle (this GPU's slice) */
+  int32_t num_agents;        /* N   (SDE:184) */
+  int32_t grid_size;         /* S   (SDE:185) */
+  int32_t attraction_thresh; /* ceil() of SDE:193 -- integer distances make ceil exact */
+  int32_t repulsion_thresh;  /* ceil() of SDE:194 */
+  float predator_eat_rew;    /* SDE:195 */
+  int32_t slab_len;          /* K : re-draw actions available per env-step */
+  int32_t place_len;         /* PL: int16 values per env per reset slot (2N + 2*KR) */
+  int32_t pred_attempts;     /* KP: predator placement attempts per reset slot */
+  int32_t reset_slots;       /* R : reset tape slots; n-th reset of an env uses slot n % R */
+  int32_t auto_reset;        /* 1: finished envs reset in-kernel; 0: they freeze */
+  int32_t track_stats;       /* 1: maintain episode statistics (needs the stats pointers) */
+  int32_t path;              /* SWARM_PATH_* */
+} swarm_config;
+
+/* Persistent device state, all caller-allocated. SoA; positions are int16. */
+typedef struct swarm_state {
+  int16_t* x;            /* [E,N] agent x (SDE:214 current_state[i][0]) */
+  int16_t* y;            /* [E,N] agent y */
+  int16_t* px;           /* [E]   predator x (SDE:92 Predator.current_state) */
+  int16_t* py;           /* [E]   predator y */
+  int32_t* target;       /* [E]   Predator.current_target (SDE:109,140) */
+  uint8_t* pred_orient;  /* [E]   Predator.orientation (SDE:107,163) */
+  uint8_t* frozen;       /* [E]   1 = episode finished and not reset (auto_reset == 0) */
+  uint32_t* err;         /* [E]   sticky SWARM_ERR_* bits */
+  uint32_t* reset_count; /* [E]   number of resets performed (selects the reset slot) */
+  /* episode statistics (track_stats == 1, else may be NULL) */
+  uint32_t* ep_len;      /* [E]   length of the running episode */
+  float* ep_ret;         /* [E,4] running episode return: survival, attraction, repulsion, alignment */
+  uint32_t* fin_count;   /* [E]   finished episodes */
+  uint32_t* fin_len;     /* [E]   sum of finished episode lengths */
+  float* fin_ret;        /* [E,4] sum of finished episode returns per component */
+} swarm_state;
+
+/* Per-step inputs. */
+typedef struct swarm_step_in {
+  const uint8_t* actions;  /* [E,N] action ids 0..8 (SDE:467-475) */
+  const uint8_t* retarget; /* [E]   1 iff the reference's np.random.random() < 0.1 (SDE:138-139) */
+  const uint8_t* slab;     /* [E,K] re-draw actions 0..7 in consumption order (SDE:250) */
+  double w_attraction;     /* reward_type["attraction"] (bool or float: the reward curriculum) */
+  double w_repulsion;      /* reward_type["repulsion"] */
+  double w_alignment;      /* reward_type["alignment"] */
+  int32_t vf_size;         /* floor(reward_type["vf_size"]) or -1 for None (SDE:349-355) */
+} swarm_step_in;
+
+/* Per-step outputs; pointers marked (opt) may be NULL. */
+typedef struct swarm_step_out {
+  uint8_t* done;         /* [E]   done flag of this step (SDE:263) */
+  int32_t* eaten;        /* [E]   id of the agent the predator landed on, -1 if none (SDE:323) */
+  float* reward;         /* [E,5] global reward: survival, attraction, repulsion, alignment, sum */
+  int32_t* counts;       /* [E,2] integer rew_rep (SDE:338), rew_attr (SDE:343); 0 on termination */
+  int16_t* pred_prev;    /* [E,2] info["predator_state"] (SDE:258,264) */
+  int16_t* pred_next;    /* [E,2] info["predator_next_state"] (SDE:266) */
+  uint8_t* step_orient;  /* [E]   info["predator_orientation"] (SDE:265) */
+  int32_t* step_target;  /* [E]   predator target after this step, before any auto-reset */
+  int32_t* consumed;     /* [E]   number of re-draw actions consumed */
+  int16_t* term_x;       /* [E,N] (opt) positions produced by the step, written where done == 1 */
+  int16_t* term_y;       /* [E,N] (opt) */
+  float* agent_reward;   /* [E,N,4] (opt) per-agent attraction, repulsion, alignment, sum (SDE:371-379);
+                            survival is predator_eat_rew for agent `eaten`, 0 otherwise */
+  int32_t* agent_counts; /* [E,N,2] (opt) integer rew_rep_i (SDE:372), rew_attr_i (SDE:373) */
+  uint8_t* eff_action;   /* [E,N] (opt) action id each agent finally moved with (after re-draws) */
+} swarm_step_out;
+
+typedef struct swarm_ctx* swarm_handle;
+
+int swarm_create(const swarm_config* cfg, swarm_handle* out);
+int swarm_destroy(swarm_handle h);
+const char* swarm_last_error(swarm_handle h);
+int swarm_abi_version(void);
+
+int swarm_bind_state(swarm_handle h, const swarm_state* st);
+/* place: int16[R,E,PL]  ptape: int16[R,E,KP,2] */
+int swarm_bind_reset_tapes(swarm_handle h, const int16_t* place, const int16_t* ptape);
+
+/* SDE:197-221 for every env (reset_count := 0, slot 0). */
+int swarm_reset(swarm_handle h, void* stream);
+/* SDE:223-267 for every env, plus auto-reset / statistics as configured. */
+int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* out, void* stream);
+/* Name of the kernel path swarm_step uses for this handle ("fused<LPE,APL>" or "staged"). */
+const char* swarm_path_name(swarm_handle h);
+/* Number of kernel launches the last swarm_step / swarm_reset enqueued. */
+int swarm_last_launch_count(swarm_handle h);
+
+/* ---- standalone kernels (roofline runs; they are also the stages of the staged path) ---- */
+
+/* SDE:60-80 + SDE:467-475: out = wrap(pos + move[action]); no collision handling. HBM bound. */
+int swarm_move(int32_t E, int32_t N, int32_t S, const int16_t* x, const int16_t* y, const uint8_t* actions,
+               int16_t* out_x, int16_t* out_y, void* stream);
+/* SDE:133-165 + SDE:111-131 + the termination test SDE:307-309: one warp per env, Chebyshev argmin by
+ * warp shuffles over the agents' OLD positions, pursuit, wrap; done/eaten against the NEW positions. */
+int swarm_predator(int32_t E, int32_t N, int32_t S, const int16_t* x_old, const int16_t* y_old,
+                   const int16_t* x_new, const int16_t* y_new, const uint8_t* retarget, int16_t* px, int16_t* py,
+                   int32_t* target, uint8_t* pred_orient, int16_t* pred_prev, uint8_t* done, int32_t* eaten,
+                   void* stream);
+/* SDE:330-343 integer part: per-agent un-weighted rew_rep_i / rew_attr_i from a tiled O(N^2) pass.
+ * out_counts: int32[E,N,2]; skip (may be NULL): uint8[E], envs with skip != 0 are not computed. */
+int swarm_pairwise(int32_t E, int32_t N, int32_t S, int32_t attraction_thresh, int32_t repulsion_thresh,
+                   const int16_t* x, const int16_t* y, const uint8_t* skip, int32_t* out_counts, void* stream);
+/* SDE:197-221: reset the envs whose mask byte is non-zero (all if mask == NULL) from their next reset slot. */
+int swarm_autoreset(swarm_handle h, const uint8_t* mask, void* stream);
+
+/* ---- episode statistics ---- */
+/* out[8] = episodes, sum length, sum return, sum survival, sum attraction, sum repulsion, sum alignment,
+ * env-steps of running episodes.  Deterministic reduction; synchronises the stream. */
+int swarm_stats_read(swarm_handle h, double out[8], void* stream);
+/* NCCL (dlopen'ed libnccl.so.2): communicator bootstrap + in-place sum all-reduce of the 8 statistics. */
+int swarm_nccl_unique_id(uint8_t out_id[128]);
+int swarm_nccl_init(swarm_handle h, const uint8_t id[128], int32_t nranks, int32_t rank);
+int swarm_stats_allreduce(swarm_handle h, double inout[8], void* stream);
+
+/* ---- measurement helpers ---- */
+/* INT32-pipe micro-benchmarks (independent dependent-chain kernels); returns lane-ops/s in *out.
+ * kind: 0 IADD3, 1 IMNMX, 2 IADD3+IMAD mix, 3 VIADDMNMX.S16x2 (DPX), 4 VIADDMNMX.S16x2 + IMAD mix */
+int swarm_int32_peak(int32_t device, int32_t kind, double* out_lane_ops_per_s, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWARM_ABI_H */

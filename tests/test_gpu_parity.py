@@ -1,0 +1,213 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI / ctypes) against
+  (1) the golden trajectories recorded from the unmodified reference (tests/golden/*.npz),
+  (2) the NumPy oracle on fresh seeded inputs,
+  (3) size-independent properties at BASELINE.json's full shapes (tests/test_gpu_properties.py).
+Bit-exact for positions / predator / target / done / integer counts; float rewards within the
+north-star tolerance 1e-6 relative (golden_utils.RTOL)."""
+import numpy as np
+import pytest
+
+from golden_utils import case_names, load_case, replay
+
+pytestmark = pytest.mark.gpu
+
+
+def make_env(cfg, path="auto", **kw):
+    from gym_swarm_b200.envs import BatchedSwarmEnv
+    return BatchedSwarmEnv(cfg["E"], cfg["N"], cfg["S"], cfg["att"], cfg["rep"], cfg["eat"],
+                           auto_reset=cfg["auto_reset"], slab_len=cfg["K"], place_extra=cfg["KR"],
+                           pred_attempts=cfg["KP"], reset_slots=cfg["R"], per_agent=True, debug_outputs=True,
+                           path=path, **kw)
+
+
+class CudaImpl:
+    def __init__(self, cfg, z, path):
+        self.env = make_env(cfg, path)
+        self.env.set_reset_tapes(z["place"], z["ptape"])
+
+    def reset(self):
+        self.env.reset()
+        return self.env.state_numpy()
+
+    def step(self, actions, slab, retarget, weights, vf, want_agents):
+        return self.env.step_numpy(actions, slab, retarget, weights, vf)
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_golden_default_path(name):
+    cfg, z = load_case(name)
+    impl = CudaImpl(cfg, z, "auto")
+    replay(impl, cfg, z)
+    impl.env.close()
+
+
+@pytest.mark.parametrize("name", [n for n in case_names() if not n.startswith("large")])
+def test_golden_staged_path(name):
+    """The staged kernels (the large-N path) must reproduce the same fixtures at small N too."""
+    cfg, z = load_case(name)
+    impl = CudaImpl(cfg, z, "staged")
+    replay(impl, cfg, z, steps=60)
+    impl.env.close()
+
+
+def _oracle_lockstep(E, N, S, T, seed, path="auto", att=5, rep=2, eat=-10.0, vf=None, n_actions=8, K=None, KR=None,
+                     weights=(1.0, 1.0, 1.0), auto_reset=True, check_agents=True):
+    from gym_swarm_b200 import tapes
+    from gym_swarm_b200.envs import BatchedSwarmEnv
+    from oracle import swarm_oracle as so
+    rng = np.random.default_rng(seed)
+    env = BatchedSwarmEnv(E, N, S, att, rep, eat, auto_reset=auto_reset, slab_len=K, place_extra=KR, reset_slots=3,
+                          per_agent=True, debug_outputs=True, path=path)
+    rt = tapes.make_reset_tapes(rng, env.R, E, N, S, KR=env.KR, KP=env.KP)
+    st = tapes.make_step_tapes(rng, T, E, N, K=env.K, n_actions=n_actions)
+    env.set_reset_tapes(rt.place, rt.ptape)
+    ora = so.OracleBatch(E, N, S, att, rep, eat, auto_reset)
+    ora.set_reset_tapes(rt.place, rt.ptape)
+    env.reset()
+    a, b = env.state_numpy(), ora.reset()
+    for k in ("x", "y", "px", "py", "target"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=f"reset {k}")
+    for t in range(T):
+        a = env.step_numpy(st.actions[t], st.slab[t], st.retarget[t], weights, vf)
+        b = ora.step(st.actions[t], st.slab[t], st.retarget[t], weights, vf, check_agents)
+        live = b["frozen"] == 0
+        for k in ("x", "y", "px", "py", "target", "done"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg=f"step {t} {k}")
+        for k in ("eaten", "cnt", "pred_prev", "pred_next", "pred_orient", "step_target", "consumed"):
+            np.testing.assert_array_equal(a[k][live], b[k][live], err_msg=f"step {t} {k}")
+        np.testing.assert_allclose(a["glob"][live], b["glob"][live], rtol=1e-6, atol=1e-9, err_msg=f"step {t} glob")
+        if check_agents:
+            np.testing.assert_array_equal(a["agent_cnt"][live], b["agent_cnt"][live], err_msg=f"step {t} agent_cnt")
+            np.testing.assert_allclose(a["agent"][live], b["agent"][live], rtol=1e-6, atol=1e-9,
+                                       err_msg=f"step {t} agent")
+            np.testing.assert_array_equal(a["eff"][live], b["eff"][live], err_msg=f"step {t} eff action")
+    env.close()
+
+
+@pytest.mark.parametrize("N,S", [(2, 4), (3, 5), (4, 20), (5, 9), (8, 16), (9, 16), (16, 32), (17, 12), (31, 40),
+                                 (32, 32), (33, 64), (64, 64), (100, 48), (128, 128), (129, 50), (255, 64),
+                                 (256, 300)])
+def test_oracle_lockstep_fused_shapes(N, S):
+    dense = S * S < 4 * N
+    _oracle_lockstep(E=9, N=N, S=S, T=25, seed=N * 1000 + S, n_actions=9, K=512 if dense else None,
+                     KR=2000 if dense else None)
+
+
+@pytest.mark.parametrize("N,S", [(257, 64), (300, 96), (512, 512), (1000, 100), (2048, 1024)])
+def test_oracle_lockstep_staged_shapes(N, S):
+    _oracle_lockstep(E=3, N=N, S=S, T=4, seed=N + S, n_actions=9)
+
+
+def test_oracle_lockstep_large_n16384():
+    """BASELINE configs[3] shape (16384 agents on 1024^2), 2 envs x 2 steps against the oracle."""
+    _oracle_lockstep(E=2, N=16384, S=1024, T=2, seed=4, check_agents=True)
+
+
+@pytest.mark.parametrize("vf", [0, 3, 40])
+def test_vf_gate(vf):
+    _oracle_lockstep(E=5, N=24, S=20, T=20, seed=vf, vf=vf, weights=(0.5, 1.0, 2.0), n_actions=9)
+    _oracle_lockstep(E=2, N=300, S=64, T=3, seed=vf, vf=vf, weights=(0.5, 1.0, 2.0), n_actions=9)
+
+
+def test_fused_equals_staged_at_cfg2():
+    """Same tapes through both kernel paths: every output tensor identical."""
+    from gym_swarm_b200 import tapes
+    from gym_swarm_b200.envs import BatchedSwarmEnv
+    E, N, S, T = 512, 16, 32, 30
+    rng = np.random.default_rng(0)
+    envs = [BatchedSwarmEnv(E, N, S, path=p, reset_slots=4, debug_outputs=True) for p in ("fused", "staged")]
+    rt = tapes.make_reset_tapes(rng, 4, E, N, S, KR=envs[0].KR, KP=envs[0].KP)
+    st = tapes.make_step_tapes(rng, T, E, N, K=envs[0].K)
+    for e in envs:
+        e.set_reset_tapes(rt.place, rt.ptape)
+        e.reset()
+    for t in range(T):
+        outs = [e.step_numpy(st.actions[t], st.slab[t], st.retarget[t], (1.0, 0.7, 0.3), None) for e in envs]
+        for k in outs[0]:
+            np.testing.assert_array_equal(outs[0][k], outs[1][k], err_msg=f"step {t} {k}")
+    for e in envs:
+        e.close()
+
+
+def test_errors_and_freeze():
+    from gym_swarm_b200 import _lib, tapes
+    from gym_swarm_b200.envs import BatchedSwarmEnv
+    E, N, S = 4, 12, 4            # 12 agents on 16 cells: collisions every step
+    rng = np.random.default_rng(1)
+    env = BatchedSwarmEnv(E, N, S, slab_len=2, place_extra=4000, pred_attempts=64, reset_slots=1, auto_reset=False)
+    rt = tapes.make_reset_tapes(rng, 1, E, N, S, KR=4000, KP=64)
+    env.set_reset_tapes(rt.place, rt.ptape)
+    env.reset()
+    st = tapes.make_step_tapes(rng, 30, E, N, K=2)
+    for t in range(30):
+        env.step(st.actions[t], retarget=st.retarget[t], slab=st.slab[t])
+    err = env.state_numpy()["err"]
+    assert np.all(err & (_lib.ERR_SLAB_OVERFLOW | _lib.ERR_STEP_WHEN_DONE)), err
+    with pytest.raises(_lib.SwarmLibraryError):
+        env.check_errors()
+    env2 = BatchedSwarmEnv(2, 4, 20, auto_reset=True)
+    env2.reset()
+    a = np.full((2, 4), 3, np.uint8)
+    a[1, 2] = 9
+    env2.step(a)
+    err2 = env2.state_numpy()["err"]
+    assert err2[0] == 0 and err2[1] & _lib.ERR_BAD_ACTION
+    env.close()
+    env2.close()
+
+
+def test_compat_surface_matches_reference_tests():
+    """The reference's own smoke tests (gym_swarm/tests/test_discrete_swarm.py:12-40) against SwarmEnv."""
+    from gym_swarm_b200.envs import ContinuousSwarmEnv, SwarmEnv
+    for cls in (SwarmEnv, ContinuousSwarmEnv):
+        env = cls()
+        env.reset()
+        state, reward, done, info = env.step({0: 0, 1: 1, 2: 2, 3: 3})
+        assert len(state) == env.num_agents
+        assert set(reward.keys()) == {0, 1, 2, 3, "global"}
+        assert set(reward["global"].keys()) == {"survival", "attraction", "repulsion", "alignment", "sum"}
+        assert set(info.keys()) == {"predator_state", "predator_orientation", "predator_next_state"}
+        env.set_env_parameters(num_agents=10, obs_space_size=200, verbose=False)
+        env.reset()
+        assert env.num_agents == 10 and env.obs_space_size == 200 and len(env.current_state) == 10
+        env.set_reward_parameters(attraction_thresh=10, repulsion_thresh=200, predator_eat_rew=-50, verbose=False)
+        env.reset()
+        assert (env.attraction_thresh, env.repulsion_thresh, env.predator_eat_rew) == (10, 200, -50)
+        with pytest.raises(KeyError):
+            env.step({i: 11 for i in range(10)})
+        env.close()
+
+
+def test_compat_env_lockstep_with_oracle():
+    """SwarmEnv (dict API) reproduces the oracle step by step when fed the same tapes."""
+    from gym_swarm_b200 import tapes
+    from gym_swarm_b200.envs import SwarmEnv
+    from oracle import swarm_oracle as so
+    env = SwarmEnv(seed=5)
+    twin = np.random.default_rng(5)            # mirrors the env's internal generator
+    env.reset()
+    N, S = 4, 20
+    rt = tapes.make_reset_tapes(twin, 1, 1, N, S, KR=env._env.KR, KP=env._env.KP)
+    ora = so.OracleEnv(N, S, 5, 2, -10.0)
+    ora.reset(rt.place[0, 0], rt.ptape[0, 0])
+    act_rng = np.random.default_rng(99)
+    for t in range(200):
+        if env.done:
+            with pytest.raises(RuntimeError):
+                env.step({i: 0 for i in range(N)})
+            break
+        action = {i: int(act_rng.integers(0, 9)) for i in range(N)}
+        roll = twin.random()
+        slab = twin.integers(0, 8, size=(1, env._env.K), dtype=np.uint8)
+        state, reward, done, info = env.step(action)
+        r = ora.step(np.array([action[i] for i in range(N)]), slab[0], roll < 0.1)
+        assert all(tuple(state[i]) == (r["x"][i], r["y"][i]) for i in range(N))
+        assert done == r["done"]
+        assert tuple(info["predator_state"]) == tuple(r["pred_prev"])
+        assert tuple(info["predator_next_state"]) == tuple(r["pred_next"])
+        assert info["predator_orientation"] == r["pred_orient"]
+        for q, k in enumerate(so.REWARD_KEYS):
+            assert abs(reward["global"][k] - r["glob"][q]) <= 1e-6 * abs(r["glob"][q]) + 1e-9
+            for i in range(N):
+                assert abs(reward[i][k] - r["agent"][i, q]) <= 1e-6 * abs(r["agent"][i, q]) + 1e-9
+    env.close()

@@ -41,3 +41,49 @@ def test_redraw_slot_formula():
     for i in range(len(c)):
         if c[i] > 1:
             assert slot[i] == last[i]
+
+
+class COracleImpl:
+    def __init__(self, cfg, z):
+        from oracle import c_oracle
+        self.b = c_oracle.COracleBatch(cfg["E"], cfg["N"], cfg["S"], cfg["att"], cfg["rep"], cfg["eat"],
+                                       cfg["auto_reset"], K=cfg["K"])
+        self.b.set_reset_tapes(z["place"], z["ptape"])
+
+    def reset(self):
+        return self.b.reset()
+
+    def step(self, actions, slab, retarget, weights, vf, want_agents):
+        return self.b.step(actions, slab, retarget, weights, vf, want_agents)
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_c_oracle_reproduces_reference(name):
+    cfg, z = load_case(name)
+    impl = COracleImpl(cfg, z)
+    replay(impl, cfg, z, float_rtol=1e-12)
+    impl.b.close()
+
+
+def test_c_oracle_equals_numpy_oracle_on_fresh_tapes():
+    from gym_swarm_b200 import tapes
+    from oracle import c_oracle
+    for (E, N, S, T, vf) in [(6, 24, 20, 40, None), (3, 70, 30, 10, 4), (2, 300, 90, 3, None)]:
+        rng = np.random.default_rng(N)
+        rt = tapes.make_reset_tapes(rng, 3, E, N, S)
+        st = tapes.make_step_tapes(rng, T, E, N, n_actions=9)
+        a = so.OracleBatch(E, N, S, 5, 2, -10.0, True)
+        b = c_oracle.COracleBatch(E, N, S, 5, 2, -10.0, True, K=st.slab.shape[2])
+        a.set_reset_tapes(rt.place, rt.ptape)
+        b.set_reset_tapes(rt.place, rt.ptape)
+        sa, sb = a.reset(), b.reset()
+        for k in ("x", "y", "px", "py", "target"):
+            np.testing.assert_array_equal(sa[k], sb[k])
+        for t in range(T):
+            oa = a.step(st.actions[t], st.slab[t], st.retarget[t], (0.3, 1.0, 0.6), vf)
+            ob = b.step(st.actions[t], st.slab[t], st.retarget[t], (0.3, 1.0, 0.6), vf)
+            for k in ("x", "y", "px", "py", "target", "done", "eaten", "cnt", "agent_cnt", "consumed", "eff"):
+                np.testing.assert_array_equal(oa[k], ob[k], err_msg=f"{k} step {t}")
+            np.testing.assert_allclose(oa["glob"], ob["glob"], rtol=1e-12, atol=1e-13)
+            np.testing.assert_allclose(oa["agent"], ob["agent"], rtol=1e-12, atol=1e-13)
+        b.close()
