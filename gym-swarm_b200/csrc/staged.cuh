@@ -298,6 +298,159 @@ __device__ __forceinline__ unsigned warp_umin(unsigned v) {
   return v;
 }
 
+// 8 packed agents (one uint4 of x, one of y) against the predator cell: nearest-neighbour keys
+__device__ __forceinline__ void nn_keys8(const uint4& xv, const uint4& yv, int px, int py, int i0, unsigned& klo,
+                                         unsigned& khi) {
+  const unsigned xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int ax = (int)(int16_t)((xs[e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+    const int ay = (int)(int16_t)((ys[e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+    const int d = max(iabs(px - ax), iabs(py - ay));
+    klo = min(klo, nn_key_lo(d, i0 + e));
+    khi = min(khi, nn_key_hi(d, i0 + e));
+  }
+}
+// 8 packed agents against the predator's NEW cell (kx, ky = cell replicated in both halves): lowest hit index
+__device__ __forceinline__ void hit8(const uint4& xv, const uint4& yv, unsigned kx, unsigned ky, int i0, unsigned& hit) {
+  const unsigned z[4] = {(xv.x ^ kx) | (yv.x ^ ky), (xv.y ^ kx) | (yv.y ^ ky), (xv.z ^ kx) | (yv.z ^ ky),
+                         (xv.w ^ kx) | (yv.w ^ ky)};
+#pragma unroll
+  for (int hh = 3; hh >= 0; --hh) {
+    if ((z[hh] >> 16) == 0u) hit = min(hit, (unsigned)(i0 + 2 * hh + 1));
+    if ((z[hh] & 0xFFFFu) == 0u) hit = min(hit, (unsigned)(i0 + 2 * hh));
+  }
+}
+
+__device__ __forceinline__ void predator_write(const PredIO& io, int env, int ppx, int ppy, int px, int py, int target,
+                                               int orient, unsigned hit) {
+  const bool done = hit != 0xFFFFFFFFu;
+  io.px[env] = (int16_t)px;
+  io.py[env] = (int16_t)py;
+  io.target[env] = target;
+  io.orient[env] = (uint8_t)orient;
+  io.done[env] = done ? 1 : 0;
+  io.eaten[env] = done ? (int)hit : -1;
+  if (io.pred_prev) reinterpret_cast<unsigned*>(io.pred_prev)[env] = pack2(ppx, ppy);
+  if (io.pred_next) reinterpret_cast<unsigned*>(io.pred_next)[env] = pack2(px, py);
+  if (io.step_orient) io.step_orient[env] = (uint8_t)orient;
+  if (io.step_target) io.step_target[env] = target;
+}
+
+// Lane-group variant: LPE lanes per env (32/LPE envs per warp), 8 agents per lane and iteration.
+// N % 8 == 0.  All loads that do not depend on the target (state scalars, NEW positions) are issued
+// first so that one DRAM round trip covers them; the target-dependent load follows.
+template <int LPE>
+__global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int env = gtid / LPE;
+  const int li = threadIdx.x % LPE;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned gmask = (LPE == 32) ? 0xFFFFFFFFu : (((1u << LPE) - 1u) << ((lane / LPE) * LPE));
+  if (env >= io.E) return;
+  const int N = io.N, S = io.S;
+  const int NV = N >> 3;
+  if (io.frozen && io.frozen[env]) {
+    if (li == 0) {
+      io.err[env] |= SWARM_ERR_STEP_WHEN_DONE;
+      io.done[env] = 1;
+      io.eaten[env] = -1;
+    }
+    return;
+  }
+  const size_t vbase = ((size_t)env * (size_t)N) >> 3;
+  const uint4* __restrict__ xn4 = reinterpret_cast<const uint4*>(io.xn) + vbase;
+  const uint4* __restrict__ yn4 = reinterpret_cast<const uint4*>(io.yn) + vbase;
+  const uint4* __restrict__ xo4 = reinterpret_cast<const uint4*>(io.xo) + vbase;
+  const uint4* __restrict__ yo4 = reinterpret_cast<const uint4*>(io.yo) + vbase;
+  // round trip 1 (tiny, coalesced over envs): the predator's state
+  int px = io.px[env], py = io.py[env];
+  int target = io.target[env];
+  const int retarget = io.retarget[env];
+  target = min(max(target, 0), N - 1);
+  // round trip 2 (the bulk, all issued together): NEW positions, the stored target's OLD cell, and -- for the
+  // envs that retarget -- the first vector of OLD positions
+  const bool have = li < NV;
+  uint4 xn0 = make_uint4(0, 0, 0, 0), yn0 = xn0, xo0 = xn0, yo0 = xn0;
+  if (have) { xn0 = __ldg(xn4 + li); yn0 = __ldg(yn4 + li); }
+  int tx = 0, ty = 0;
+  if (!retarget) {
+    tx = io.xo[(size_t)env * N + target];
+    ty = io.yo[(size_t)env * N + target];
+  } else if (have) {
+    xo0 = __ldg(xo4 + li); yo0 = __ldg(yo4 + li);
+  }
+  const int ppx = px, ppy = py;
+  if (retarget) {                                              // SDE:138-140
+    unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;
+    if (have) nn_keys8(xo0, yo0, px, py, li * 8, klo, khi);
+#pragma unroll 4
+    for (int v = li + LPE; v < NV; v += LPE) nn_keys8(__ldg(xo4 + v), __ldg(yo4 + v), px, py, v * 8, klo, khi);
+#pragma unroll
+    for (int d = LPE / 2; d > 0; d >>= 1) {
+      klo = min(klo, __shfl_xor_sync(gmask, klo, d));
+      khi = min(khi, __shfl_xor_sync(gmask, khi, d));
+    }
+    target = nn_pick(klo, khi, S);
+    tx = io.xo[(size_t)env * N + target];                      // L1/L2 hit: the line was just streamed
+    ty = io.yo[(size_t)env * N + target];
+  }
+  int orient;
+  pursue(px, py, tx, ty, S, px, py, orient);
+  unsigned hit = 0xFFFFFFFFu;                                  // SDE:307-309 on the NEW positions
+  const unsigned kx = rep2(px), ky = rep2(py);
+  if (have) hit8(xn0, yn0, kx, ky, li * 8, hit);
+#pragma unroll 4
+  for (int v = li + LPE; v < NV; v += LPE) hit8(__ldg(xn4 + v), __ldg(yn4 + v), kx, ky, v * 8, hit);
+#pragma unroll
+  for (int d = LPE / 2; d > 0; d >>= 1) hit = min(hit, __shfl_xor_sync(gmask, hit, d));
+  if (li == 0) predator_write(io, env, ppx, ppy, px, py, target, orient, hit);
+}
+
+// CTA-per-env variant for large N (few, big environments): 256 threads stream one env.
+__global__ void __launch_bounds__(256) predator_block_kernel(const PredIO io) {
+  __shared__ BlockScratch bs;
+  const int N = io.N, S = io.S;
+  const int NV = N >> 3;
+  for (int env = blockIdx.x; env < io.E; env += gridDim.x) {
+    if (io.frozen && io.frozen[env]) {                        // uniform per CTA
+      if (threadIdx.x == 0) {
+        io.err[env] |= SWARM_ERR_STEP_WHEN_DONE;
+        io.done[env] = 1;
+        io.eaten[env] = -1;
+      }
+      continue;
+    }
+    const size_t vbase = ((size_t)env * (size_t)N) >> 3;
+    const uint4* __restrict__ xn4 = reinterpret_cast<const uint4*>(io.xn) + vbase;
+    const uint4* __restrict__ yn4 = reinterpret_cast<const uint4*>(io.yn) + vbase;
+    const uint4* __restrict__ xo4 = reinterpret_cast<const uint4*>(io.xo) + vbase;
+    const uint4* __restrict__ yo4 = reinterpret_cast<const uint4*>(io.yo) + vbase;
+    int px = io.px[env], py = io.py[env];
+    int target = io.target[env];
+    const int ppx = px, ppy = py;
+    if (io.retarget[env]) {
+      unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;
+#pragma unroll 4
+      for (int v = threadIdx.x; v < NV; v += blockDim.x) nn_keys8(__ldg(xo4 + v), __ldg(yo4 + v), px, py, v * 8, klo, khi);
+      klo = block_umin(klo, bs);
+      khi = block_umin(khi, bs);
+      target = nn_pick(klo, khi, S);
+    }
+    target = min(max(target, 0), N - 1);
+    int orient;
+    pursue(px, py, (int)io.xo[(size_t)env * N + target], (int)io.yo[(size_t)env * N + target], S, px, py, orient);
+    unsigned hit = 0xFFFFFFFFu;
+    const unsigned kx = rep2(px), ky = rep2(py);
+#pragma unroll 4
+    for (int v = threadIdx.x; v < NV; v += blockDim.x) hit8(__ldg(xn4 + v), __ldg(yn4 + v), kx, ky, v * 8, hit);
+    hit = block_umin(hit, bs);
+    if (threadIdx.x == 0) predator_write(io, env, ppx, ppy, px, py, target, orient, hit);
+    __syncthreads();   // outputs of this env are written before the state reads of the next iteration
+  }
+}
+
+// Scalar fallback (N not a multiple of 8): one warp per env.
 __global__ void __launch_bounds__(256) predator_kernel(const PredIO io) {
   const int lane = threadIdx.x & 31;
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -315,68 +468,48 @@ __global__ void __launch_bounds__(256) predator_kernel(const PredIO io) {
   int px = io.px[env], py = io.py[env];
   int target = io.target[env];
   const int ppx = px, ppy = py;
-  const bool vec = ((N & 7) == 0);
   if (io.retarget[env]) {                                      // SDE:138-140
     unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;
-    if (vec) {
-      for (int v = lane; v < (N >> 3); v += 32) {
-        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(io.xo + base) + v);
-        const uint4 yv = __ldg(reinterpret_cast<const uint4*>(io.yo + base) + v);
-        const unsigned xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int ax = (int)(int16_t)((xs[e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
-          const int ay = (int)(int16_t)((ys[e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
-          const int d = max(iabs(px - ax), iabs(py - ay));
-          klo = min(klo, nn_key_lo(d, v * 8 + e));
-          khi = min(khi, nn_key_hi(d, v * 8 + e));
-        }
-      }
-    } else {
-      for (int i = lane; i < N; i += 32) {
-        const int d = max(iabs(px - (int)io.xo[base + i]), iabs(py - (int)io.yo[base + i]));
-        klo = min(klo, nn_key_lo(d, i));
-        khi = min(khi, nn_key_hi(d, i));
-      }
+    for (int i = lane; i < N; i += 32) {
+      const int d = max(iabs(px - (int)io.xo[base + i]), iabs(py - (int)io.yo[base + i]));
+      klo = min(klo, nn_key_lo(d, i));
+      khi = min(khi, nn_key_hi(d, i));
     }
     target = nn_pick(warp_umin(klo), warp_umin(khi), S);
   }
   target = min(max(target, 0), N - 1);
   int orient;
   pursue(px, py, (int)io.xo[base + target], (int)io.yo[base + target], S, px, py, orient);
-
   unsigned hit = 0xFFFFFFFFu;                                  // SDE:307-309 on the NEW positions
-  if (vec) {
-    const unsigned kx = rep2(px), ky = rep2(py);
-    for (int v = lane; v < (N >> 3); v += 32) {
-      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(io.xn + base) + v);
-      const uint4 yv = __ldg(reinterpret_cast<const uint4*>(io.yn + base) + v);
-      const unsigned xs[4] = {xv.x ^ kx, xv.y ^ kx, xv.z ^ kx, xv.w ^ kx};
-      const unsigned ys[4] = {yv.x ^ ky, yv.y ^ ky, yv.z ^ ky, yv.w ^ ky};
-#pragma unroll
-      for (int hh = 0; hh < 4; ++hh) {
-        const unsigned z = xs[hh] | ys[hh];
-        if ((z & 0xFFFFu) == 0u) hit = min(hit, (unsigned)(v * 8 + 2 * hh));
-        if ((z >> 16) == 0u) hit = min(hit, (unsigned)(v * 8 + 2 * hh + 1));
-      }
-    }
-  } else {
-    for (int i = lane; i < N; i += 32)
-      if ((int)io.xn[base + i] == px && (int)io.yn[base + i] == py) hit = min(hit, (unsigned)i);
-  }
+  for (int i = lane; i < N; i += 32)
+    if ((int)io.xn[base + i] == px && (int)io.yn[base + i] == py) hit = min(hit, (unsigned)i);
   hit = warp_umin(hit);
-  if (lane == 0) {
-    const bool done = hit != 0xFFFFFFFFu;
-    io.px[env] = (int16_t)px;
-    io.py[env] = (int16_t)py;
-    io.target[env] = target;
-    io.orient[env] = (uint8_t)orient;
-    io.done[env] = done ? 1 : 0;
-    io.eaten[env] = done ? (int)hit : -1;
-    if (io.pred_prev) { io.pred_prev[2 * env] = (int16_t)ppx; io.pred_prev[2 * env + 1] = (int16_t)ppy; }
-    if (io.pred_next) { io.pred_next[2 * env] = (int16_t)px; io.pred_next[2 * env + 1] = (int16_t)py; }
-    if (io.step_orient) io.step_orient[env] = (uint8_t)orient;
-    if (io.step_target) io.step_target[env] = target;
+  if (lane == 0) predator_write(io, env, ppx, ppy, px, py, target, orient, hit);
+}
+
+// host-side dispatch (used by swarm_step's staged path and by swarm_predator)
+static inline void launch_predator(const PredIO& io, int num_sms, cudaStream_t s) {
+  const int N = io.N;
+  const long long E = io.E;
+  if ((N & 7) != 0) {
+    predator_kernel<<<(int)((E * 32 + 255) / 256), 256, 0, s>>>(io);
+    return;
+  }
+  const int nv = N >> 3;
+  if (nv >= 512 && E < (long long)num_sms * 64) {              // few big envs: a CTA streams one env
+    predator_block_kernel<<<(int)std::min<long long>(E, (long long)num_sms * 8), 256, 0, s>>>(io);
+    return;
+  }
+  int lpe = 1;
+  while (lpe < 32 && lpe < nv) lpe <<= 1;
+  const int grid = (int)((E * lpe + 255) / 256);
+  switch (lpe) {
+    case 1: predator_group_kernel<1><<<grid, 256, 0, s>>>(io); break;
+    case 2: predator_group_kernel<2><<<grid, 256, 0, s>>>(io); break;
+    case 4: predator_group_kernel<4><<<grid, 256, 0, s>>>(io); break;
+    case 8: predator_group_kernel<8><<<grid, 256, 0, s>>>(io); break;
+    case 16: predator_group_kernel<16><<<grid, 256, 0, s>>>(io); break;
+    default: predator_group_kernel<32><<<grid, 256, 0, s>>>(io); break;
   }
 }
 

@@ -447,7 +447,7 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     io.retarget = p.retarget; io.frozen = p.frozen; io.px = p.px; io.py = p.py; io.target = p.target;
     io.orient = p.orient; io.pred_prev = p.pred_prev; io.pred_next = p.pred_next; io.step_orient = p.step_orient;
     io.step_target = p.step_target; io.done = p.done; io.eaten = p.eaten; io.err = p.err;
-    predator_kernel<<<(p.E * 32 + 255) / 256, 256, 0, s>>>(io);
+    launch_predator(io, c->num_sms, s);
   }
   {
     const long long words = (long long)p.E * sc.NW;
@@ -497,7 +497,10 @@ int swarm_predator(int32_t E, int32_t N, int32_t S, const int16_t* x_old, const 
   io.E = E; io.N = N; io.S = S; io.xo = x_old; io.yo = y_old; io.xn = x_new; io.yn = y_new;
   io.retarget = retarget; io.px = px; io.py = py; io.target = target; io.orient = pred_orient;
   io.pred_prev = pred_prev; io.done = done; io.eaten = eaten;
-  predator_kernel<<<(int)(((long long)E * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(io);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  launch_predator(io, sms, (cudaStream_t)stream);
   CUDA_TRY(nullptr, cudaGetLastError());
   return SWARM_OK;
 }

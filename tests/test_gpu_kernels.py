@@ -1,0 +1,116 @@
+"""Standalone C-ABI kernels (swarm_move / swarm_predator / swarm_pairwise) against the oracle's functions."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("E,N,S", [(1, 1, 2), (7, 5, 3), (64, 8, 16), (33, 37, 50), (1024, 128, 128), (3, 16384, 1024)])
+def test_swarm_move_matches_reference_rule(E, N, S):
+    import torch
+    from gym_swarm_b200 import _lib
+    from oracle import swarm_oracle as so
+    lib = _lib.load()
+    rng = np.random.default_rng(E * 31 + N)
+    x = rng.integers(0, S, size=(E, N), dtype=np.int16)
+    y = rng.integers(0, S, size=(E, N), dtype=np.int16)
+    a = rng.integers(0, 9, size=(E, N), dtype=np.uint8)
+    dx, dy, da = (torch.from_numpy(v).cuda() for v in (x, y, a))
+    ox, oy = torch.empty_like(dx), torch.empty_like(dy)
+    _lib.check(lib.swarm_move(E, N, S, _ptr(dx), _ptr(dy), _ptr(da), _ptr(ox), _ptr(oy), _stream()))
+    mv = so.ACTION_MOVES[a.astype(np.int64)]
+    np.testing.assert_array_equal(ox.cpu().numpy(), so.wrap(x.astype(np.int64) + mv[..., 0], S))
+    np.testing.assert_array_equal(oy.cpu().numpy(), so.wrap(y.astype(np.int64) + mv[..., 1], S))
+
+
+@pytest.mark.parametrize("E,N,S", [(200, 2, 4), (300, 8, 16), (100, 16, 8), (50, 37, 50), (64, 40, 9), (40, 128, 128),
+                                   (9, 200, 64), (5, 512, 100), (3, 4096, 256), (2, 16384, 1024), (700, 16384, 300)])
+def test_swarm_predator_matches_oracle(E, N, S):
+    """Every dispatch of the predator kernel (lane groups 1..32, CTA per env, scalar fallback): retarget tie rule,
+    pursuit on the OLD positions, wrap, termination test on the NEW positions."""
+    import torch
+    from gym_swarm_b200 import _lib
+    from oracle import swarm_oracle as so
+    if E * N > 4_000_000:
+        E = max(1, 4_000_000 // N)
+    lib = _lib.load()
+    rng = np.random.default_rng(E + N + S)
+    xo = rng.integers(0, S, size=(E, N), dtype=np.int16)
+    yo = rng.integers(0, S, size=(E, N), dtype=np.int16)
+    act = rng.integers(0, 9, size=(E, N))
+    mv = so.ACTION_MOVES[act]
+    xn = so.wrap(xo.astype(np.int64) + mv[..., 0], S).astype(np.int16)
+    yn = so.wrap(yo.astype(np.int64) + mv[..., 1], S).astype(np.int16)
+    ret = (rng.random(E) < 0.5).astype(np.uint8)
+    tgt = rng.integers(0, N, size=E, dtype=np.int32)
+    # predator next to its target in half of the envs so that terminations happen
+    px = np.where(rng.random(E) < 0.5, np.clip(xo[np.arange(E), tgt] + rng.integers(-2, 3, size=E), 0, S - 1),
+                  rng.integers(0, S, size=E)).astype(np.int16)
+    py = np.where(rng.random(E) < 0.5, np.clip(yo[np.arange(E), tgt] + rng.integers(-2, 3, size=E), 0, S - 1),
+                  rng.integers(0, S, size=E)).astype(np.int16)
+    # precondition of closest_target (SDE:111-131): the predator never stands on an agent's (old) cell
+    for _ in range(1000):
+        clash = ((xo == px[:, None]) & (yo == py[:, None])).any(axis=1)
+        if not clash.any():
+            break
+        px[clash] = rng.integers(0, S, size=int(clash.sum()))
+        py[clash] = rng.integers(0, S, size=int(clash.sum()))
+    assert not clash.any()
+    d = {k: torch.from_numpy(v).cuda() for k, v in dict(xo=xo, yo=yo, xn=xn, yn=yn, ret=ret, px=px.copy(), py=py.copy(),
+                                                        tgt=tgt.copy()).items()}
+    ori = torch.zeros(E, dtype=torch.uint8, device="cuda")
+    prev = torch.zeros((E, 2), dtype=torch.int16, device="cuda")
+    done = torch.zeros(E, dtype=torch.uint8, device="cuda")
+    eaten = torch.zeros(E, dtype=torch.int32, device="cuda")
+    _lib.check(lib.swarm_predator(E, N, S, _ptr(d["xo"]), _ptr(d["yo"]), _ptr(d["xn"]), _ptr(d["yn"]), _ptr(d["ret"]),
+                                  _ptr(d["px"]), _ptr(d["py"]), _ptr(d["tgt"]), _ptr(ori), _ptr(prev), _ptr(done),
+                                  _ptr(eaten), _stream()))
+    n_done = 0
+    for e in range(E):
+        npx, npy, t, o = so.follow_target(int(px[e]), int(py[e]), int(tgt[e]), 0, xo[e].astype(np.int64),
+                                          yo[e].astype(np.int64), S, bool(ret[e]))
+        hit = np.nonzero((xn[e] == npx) & (yn[e] == npy))[0]
+        assert (int(d["px"][e]), int(d["py"][e]), int(d["tgt"][e]), int(ori[e])) == (npx, npy, t, o), f"env {e}"
+        assert tuple(prev[e].tolist()) == (int(px[e]), int(py[e]))
+        assert int(done[e]) == (1 if len(hit) else 0) and int(eaten[e]) == (int(hit[0]) if len(hit) else -1), f"env {e}"
+        n_done += len(hit) > 0
+    if S * S < 4 * N:
+        assert n_done > 0
+
+
+@pytest.mark.parametrize("E,N,S,att,rep", [(6, 2, 4, 5, 2), (5, 37, 50, 5, 2), (4, 128, 128, 5, 2), (3, 600, 64, 9, 3),
+                                           (2, 2048, 1024, 5, 2), (3, 100, 20, 10, 200), (3, 100, 20, 2, 5),
+                                           (2, 50, 20, 0, 0), (2, 50, 20, 30, 3)])
+def test_swarm_pairwise_matches_oracle(E, N, S, att, rep):
+    import torch
+    from gym_swarm_b200 import _lib
+    from oracle import swarm_oracle as so
+    lib = _lib.load()
+    rng = np.random.default_rng(N * 7 + S)
+    x = rng.integers(0, S, size=(E, N), dtype=np.int16)
+    y = rng.integers(0, S, size=(E, N), dtype=np.int16)
+    skip = np.zeros(E, np.uint8)
+    skip[E - 1] = 1
+    dx, dy, ds = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(skip).cuda()
+    out = torch.full((E, N, 2), -7, dtype=torch.int32, device="cuda")
+    _lib.check(lib.swarm_pairwise(E, N, S, att, rep, _ptr(dx), _ptr(dy), _ptr(ds), _ptr(out), _stream()))
+    got = out.cpu().numpy()
+    eff = np.zeros(N, dtype=np.int64)
+    for e in range(E):
+        if skip[e]:
+            assert not got[e].any()
+            continue
+        r = so.swarm_reward(x[e].astype(np.int64), y[e].astype(np.int64), eff, -5, -5, N, S, att, rep, -10.0,
+                            (1.0, 1.0, 1.0), None)
+        np.testing.assert_array_equal(got[e], r["agent_cnt"], err_msg=f"env {e}")
