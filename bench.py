@@ -133,6 +133,7 @@ def cpu_port_run(cfg, sample_envs, steps, warmup, seed=123):
     from gym_swarm_b200 import tapes
     from oracle import c_oracle
     E, N, S = sample_envs, cfg["N"], cfg["S"]
+    threads = c_oracle.set_threads(host_cores())        # torchrun exports OMP_NUM_THREADS=1: override it
     rng = np.random.default_rng(seed)
     K = tapes.default_slab_len(N)
     rt = tapes.make_reset_tapes(rng, 2, E, N, S)
@@ -154,15 +155,21 @@ def cpu_port_run(cfg, sample_envs, steps, warmup, seed=123):
                  want_state=False)
     dt = time.perf_counter() - t0
     ora.close()
-    threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return E * N * steps / dt, dt / steps, threads
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def cpu_sample_envs(cfg, target_s=1.0):
     """Envs per CPU step so that one step is roughly target_s of wall time on all cores (bounded sample)."""
     N = cfg["N"]
     per_env = 3.0e-9 * N * N * 2 + 2e-7 * N          # literal O(N^2) collision + reward loops
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     e = int(target_s * cores / per_env)
     return int(max(cores, min(cfg["E"], e)))
 

@@ -311,10 +311,13 @@ __device__ __forceinline__ void nn_keys8(const uint4& xv, const uint4& yv, int p
     khi = min(khi, nn_key_hi(d, i0 + e));
   }
 }
-// 8 packed agents against the predator's NEW cell (kx, ky = cell replicated in both halves): lowest hit index
+// 8 packed agents against the predator's NEW cell (kx, ky = cell replicated in both halves): lowest hit index.
+// z has a zero halfword iff that agent stands on the cell; the exact index is only resolved on the rare hit.
+__device__ __forceinline__ unsigned zero_half(unsigned z) { return (z - 0x00010001u) & ~z & 0x80008000u; }
 __device__ __forceinline__ void hit8(const uint4& xv, const uint4& yv, unsigned kx, unsigned ky, int i0, unsigned& hit) {
   const unsigned z[4] = {(xv.x ^ kx) | (yv.x ^ ky), (xv.y ^ kx) | (yv.y ^ ky), (xv.z ^ kx) | (yv.z ^ ky),
                          (xv.w ^ kx) | (yv.w ^ ky)};
+  if ((zero_half(z[0]) | zero_half(z[1]) | zero_half(z[2]) | zero_half(z[3])) == 0u) return;
 #pragma unroll
   for (int hh = 3; hh >= 0; --hh) {
     if ((z[hh] >> 16) == 0u) hit = min(hit, (unsigned)(i0 + 2 * hh + 1));
@@ -337,9 +340,12 @@ __device__ __forceinline__ void predator_write(const PredIO& io, int env, int pp
   if (io.step_target) io.step_target[env] = target;
 }
 
-// Lane-group variant: LPE lanes per env (32/LPE envs per warp), 8 agents per lane and iteration.
-// N % 8 == 0.  All loads that do not depend on the target (state scalars, NEW positions) are issued
-// first so that one DRAM round trip covers them; the target-dependent load follows.
+// Lane-group variant: LPE lanes per env (32/LPE envs per warp), 8 agents per vector, up to PRED_VPL vectors per
+// lane prefetched into registers.  N % 8 == 0.  Round trip 1 is the predator's state (tiny, coalesced over envs);
+// round trip 2 issues the bulk together: NEW positions, the stored target's OLD cell, and -- for the envs that
+// retarget -- the OLD positions.
+constexpr int PRED_VPL = 4;
+
 template <int LPE>
 __global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -363,29 +369,27 @@ __global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
   const uint4* __restrict__ yn4 = reinterpret_cast<const uint4*>(io.yn) + vbase;
   const uint4* __restrict__ xo4 = reinterpret_cast<const uint4*>(io.xo) + vbase;
   const uint4* __restrict__ yo4 = reinterpret_cast<const uint4*>(io.yo) + vbase;
-  // round trip 1 (tiny, coalesced over envs): the predator's state
   int px = io.px[env], py = io.py[env];
   int target = io.target[env];
   const int retarget = io.retarget[env];
   target = min(max(target, 0), N - 1);
-  // round trip 2 (the bulk, all issued together): NEW positions, the stored target's OLD cell, and -- for the
-  // envs that retarget -- the first vector of OLD positions
-  const bool have = li < NV;
-  uint4 xn0 = make_uint4(0, 0, 0, 0), yn0 = xn0, xo0 = xn0, yo0 = xn0;
-  if (have) { xn0 = __ldg(xn4 + li); yn0 = __ldg(yn4 + li); }
+  uint4 xn[PRED_VPL], yn[PRED_VPL];
+#pragma unroll
+  for (int q = 0; q < PRED_VPL; ++q) {
+    const int v = li + q * LPE;
+    if (v < NV) { xn[q] = __ldg(xn4 + v); yn[q] = __ldg(yn4 + v); }
+    else { xn[q] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu); yn[q] = xn[q]; }
+  }
   int tx = 0, ty = 0;
   if (!retarget) {
     tx = io.xo[(size_t)env * N + target];
     ty = io.yo[(size_t)env * N + target];
-  } else if (have) {
-    xo0 = __ldg(xo4 + li); yo0 = __ldg(yo4 + li);
   }
   const int ppx = px, ppy = py;
   if (retarget) {                                              // SDE:138-140
     unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;
-    if (have) nn_keys8(xo0, yo0, px, py, li * 8, klo, khi);
 #pragma unroll 4
-    for (int v = li + LPE; v < NV; v += LPE) nn_keys8(__ldg(xo4 + v), __ldg(yo4 + v), px, py, v * 8, klo, khi);
+    for (int v = li; v < NV; v += LPE) nn_keys8(__ldg(xo4 + v), __ldg(yo4 + v), px, py, v * 8, klo, khi);
 #pragma unroll
     for (int d = LPE / 2; d > 0; d >>= 1) {
       klo = min(klo, __shfl_xor_sync(gmask, klo, d));
@@ -399,9 +403,10 @@ __global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
   pursue(px, py, tx, ty, S, px, py, orient);
   unsigned hit = 0xFFFFFFFFu;                                  // SDE:307-309 on the NEW positions
   const unsigned kx = rep2(px), ky = rep2(py);
-  if (have) hit8(xn0, yn0, kx, ky, li * 8, hit);
+#pragma unroll
+  for (int q = 0; q < PRED_VPL; ++q) hit8(xn[q], yn[q], kx, ky, (li + q * LPE) * 8, hit);   // padding = 0xFFFF: never a cell
 #pragma unroll 4
-  for (int v = li + LPE; v < NV; v += LPE) hit8(__ldg(xn4 + v), __ldg(yn4 + v), kx, ky, v * 8, hit);
+  for (int v = li + PRED_VPL * LPE; v < NV; v += LPE) hit8(__ldg(xn4 + v), __ldg(yn4 + v), kx, ky, v * 8, hit);
 #pragma unroll
   for (int d = LPE / 2; d > 0; d >>= 1) hit = min(hit, __shfl_xor_sync(gmask, hit, d));
   if (li == 0) predator_write(io, env, ppx, ppy, px, py, target, orient, hit);
@@ -501,7 +506,7 @@ static inline void launch_predator(const PredIO& io, int num_sms, cudaStream_t s
     return;
   }
   int lpe = 1;
-  while (lpe < 32 && lpe < nv) lpe <<= 1;
+  while (lpe < 32 && lpe * PRED_VPL < nv) lpe <<= 1;
   const int grid = (int)((E * lpe + 255) / 256);
   switch (lpe) {
     case 1: predator_group_kernel<1><<<grid, 256, 0, s>>>(io); break;

@@ -36,12 +36,19 @@ def load():
         lib.oracle_reset.argtypes = [C.c_void_p]
         lib.oracle_step.argtypes = [C.c_void_p] * 4 + [C.c_double] * 3 + [C.c_int] + [C.c_void_p] * 14
         lib.oracle_get_state.argtypes = [C.c_void_p] * 8
+        lib.oracle_set_threads.restype = C.c_int
+        lib.oracle_set_threads.argtypes = [C.c_int]
         _lib = lib
     return _lib
 
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def set_threads(n):
+    """Use n OpenMP threads (returns the count in effect)."""
+    return int(load().oracle_set_threads(int(n)))
 
 
 class COracleBatch:

@@ -16,6 +16,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define ERR_SLAB_OVERFLOW 1u
 #define ERR_PLACE_OVERFLOW 2u
@@ -285,6 +288,17 @@ void oracle_step(void* h, const uint8_t* actions, const uint8_t* retarget, const
       step_env(o, e, actions, retarget[e], slab, w_att, w_rep, w_ali, vf, &out, s);
     free(s);
   }
+}
+
+/* bench.py's CPU arms: use n host threads regardless of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1). */
+int oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
 }
 
 void oracle_get_state(void* h, int16_t* x, int16_t* y, int16_t* px, int16_t* py, int32_t* target, uint32_t* err,
