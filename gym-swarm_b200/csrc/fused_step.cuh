@@ -166,11 +166,16 @@ __device__ __forceinline__ void occupancy_counts(const Seg<LPE>& g, unsigned* sk
   g.sync();
 }
 
-// ---- "is any cell shared?" via a per-env occupancy bitmap in smem (S*S bits) ---------------------
+// ---- exact occupancy counts from a per-env occupancy bitmap in smem (S*S bits) -----------------------
+// Every agent sets its cell's bit with atomicOr; an agent that finds the bit already set is a "hit".  A cell
+// holding c agents produces exactly c-1 hits (all but the first arrival), so
+//     c_i = 1 + #{hit agents standing on agent i's cell}.
+// The (few) hit agents broadcast their cell one after the other and everybody compares: O(hits * APL) per lane
+// instead of the O(N * APL) all-pairs sweep.  Returns false (c untouched) when no cell is shared.
 template <int LPE, int APL>
-__device__ __forceinline__ bool bitmap_any_collision(const Seg<LPE>& g, unsigned* sbit, int N, int S, int i0,
-                                                     const int (&cx)[APL], const int (&cy)[APL]) {
-  bool hit = false;
+__device__ __forceinline__ bool bitmap_counts(const Seg<LPE>& g, unsigned* sbit, int N, int S, int i0,
+                                              const int (&cx)[APL], const int (&cy)[APL], int (&c)[APL]) {
+  unsigned pending = 0u;
   int word[APL];
 #pragma unroll
   for (int k = 0; k < APL; ++k) {
@@ -180,16 +185,38 @@ __device__ __forceinline__ bool bitmap_any_collision(const Seg<LPE>& g, unsigned
       word[k] = cell >> 5;
       const unsigned bit = 1u << (cell & 31);
       const unsigned old = atomicOr(&sbit[word[k]], bit);
-      hit |= (old & bit) != 0u;
+      if (old & bit) pending |= 1u << k;
     }
   }
-  const bool any = g.any(hit);   // ballot also orders the atomics before the clears below
+  const bool any = g.any(pending != 0u);   // ballot also orders the atomics before the clears below
   g.sync();
 #pragma unroll
   for (int k = 0; k < APL; ++k)
     if (word[k] >= 0) sbit[word[k]] = 0u;
   g.sync();
-  return any;
+  if (!any) return false;
+  unsigned key[APL];
+#pragma unroll
+  for (int k = 0; k < APL; ++k) {
+    key[k] = (i0 + k < N) ? pack2(cx[k], cy[k]) : (0xFFFF0000u | (unsigned)(i0 + k));
+    c[k] = 1;
+  }
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    const unsigned ball = __ballot_sync(g.mask, pending != 0u) & g.mask;
+    if (ball == 0u) break;
+    const int src = __ffs(ball) - 1;
+    const int kk = __ffs(pending) - 1;           // meaningful in the src lane only
+    unsigned mine = 0u;
+#pragma unroll
+    for (int k = 0; k < APL; ++k)
+      if (k == kk) mine = key[k];
+    const unsigned hk = __shfl_sync(g.mask, mine, src);
+#pragma unroll
+    for (int k = 0; k < APL; ++k) c[k] += (key[k] == hk);
+    if (lane == src) pending &= pending - 1u;
+  }
+  return true;
 }
 
 // ---- nearest agent to (qx,qy) with the canonical tie rule (SDE:111-131) --------------------------
@@ -343,11 +370,12 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
       nx[k] = wrap1(x[k] + move_dx(eff[k]), S);          // SDE:60-80
       ny[k] = wrap1(y[k] + move_dy(eff[k]), S);
     }
-    if (p.bitmap_words) {
-      if (!bitmap_any_collision<LPE, APL>(g, sbit, N, S, i0, nx, ny)) break;
-    }
     int c[APL];
-    occupancy_counts<LPE, APL>(g, skey, N, i0, nx, ny, c);
+    if (p.bitmap_words) {
+      if (!bitmap_counts<LPE, APL>(g, sbit, N, S, i0, nx, ny, c)) break;
+    } else {
+      occupancy_counts<LPE, APL>(g, skey, N, i0, nx, ny, c);
+    }
     int extra = 0;
 #pragma unroll
     for (int k = 0; k < APL; ++k) extra += c[k] - 1;
@@ -438,25 +466,115 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
     }
     const unsigned TR = rep2(p.t_rep), TA = rep2(p.t_att), TRf = rep2(p.t_repf), TAf = rep2(p.t_attf);
     const unsigned TV = rep2(HAS_VF ? p.t_vf : 0);
-    const int NW = (N + 1) >> 1;
-#pragma unroll 2
-    for (int q = 0; q < NW; ++q) {
-      const uint4 w = spw[q];
-      uint4 u = make_uint4(0, 0, 0, 0);
-      if constexpr (HAS_VF) u = *reinterpret_cast<const uint4*>(&svf[2 * q]);
+    if constexpr (!HAS_VF && (APL == 2 || APL == 4) && LPE >= 4) {
+      // ---- symmetric ring sweep: every unordered block pair is evaluated once --------------------
+      // Lane l owns block B_l (APL agents = W pair words).  In round r it meets the block of lane l+r (pair words
+      // read from smem), adds each indicator to its own ROW counters and to the visiting block's COLUMN counters;
+      // the column counters travel round the ring by shuffles together with the block they belong to and are
+      // sent home after the last symmetric round.  Rounds 0 (own block) and LPE/2 (met from both sides) only
+      // count rows.  The accumulations are IMADs by a runtime 1 so that they issue on the FMA pipe and leave the
+      // ALU pipe to the DPX ops.
+      constexpr int W = APL / 2;
+      constexpr int HALF = LPE / 2;
+      const unsigned one = (unsigned)p.one;
+      const unsigned T4[4] = {TR, TA, TRf, TAf};
+      unsigned row[APL][4], col[W][4];
+#pragma unroll
+      for (int k = 0; k < APL; ++k)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) row[k][t] = 0u;
+#pragma unroll
+      for (int w = 0; w < W; ++w)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) col[w][t] = 0u;
+      // round 0: own block, rows only
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const uint4 vw = spw[g.li * W + w];
+#pragma unroll
+        for (int k = 0; k < APL; ++k) {
+          const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) row[k][t] = lt2(T4[t], m) * one + row[k][t];
+        }
+      }
+      const int nxt = (g.li + 1) & (LPE - 1);
+#pragma unroll 1
+      for (int r = 1; r < HALF; ++r) {
+        const int src = (g.li + r) & (LPE - 1);
+        if (r > 1) {
+#pragma unroll
+          for (int w = 0; w < W; ++w)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) col[w][t] = __shfl_sync(g.mask, col[w][t], nxt, LPE);
+        }
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          const uint4 vw = spw[src * W + w];
+#pragma unroll
+          for (int k = 0; k < APL; ++k) {
+            const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const unsigned ind = lt2(T4[t], m);
+              row[k][t] = ind * one + row[k][t];
+              col[w][t] = ind * one + col[w][t];
+            }
+          }
+        }
+      }
+      // send the column counters home: lane l holds those of block l + HALF - 1
+      if constexpr (HALF > 1) {
+        const int from = (g.li - (HALF - 1)) & (LPE - 1);
+#pragma unroll
+        for (int w = 0; w < W; ++w)
+#pragma unroll
+          for (int t = 0; t < 4; ++t) col[w][t] = __shfl_sync(g.mask, col[w][t], from, LPE);
+      }
+      // round LPE/2: met from both sides, rows only
+      {
+        const int src = (g.li + HALF) & (LPE - 1);
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          const uint4 vw = spw[src * W + w];
+#pragma unroll
+          for (int k = 0; k < APL; ++k) {
+            const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) row[k][t] = lt2(T4[t], m) * one + row[k][t];
+          }
+        }
+      }
+      // fold: total count = both halves of the row counter + this agent's half of the column counter
 #pragma unroll
       for (int k = 0; k < APL; ++k) {
-        const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], w);
-        aR[k] += lt2(TR, m);
-        aA[k] += lt2(TA, m);
-        aRf[k] += lt2(TRf, m);
-        aAf[k] += lt2(TAf, m);
-        if constexpr (HAS_VF) {
-          const unsigned gate = lt2(TV, m);
-          const unsigned g0 = gate & 0xFFFFu, g1 = gate >> 16;
-          aV[k] += gate;
-          accA[k] += g0 * u.x + g1 * u.z;
-          accD[k] += g0 * u.y + g1 * u.w;
+        const int sh = 16 * (k & 1);
+        aR[k] = (unsigned)hsum2(row[k][0]) + ((col[k >> 1][0] >> sh) & 0xFFFFu);
+        aA[k] = (unsigned)hsum2(row[k][1]) + ((col[k >> 1][1] >> sh) & 0xFFFFu);
+        aRf[k] = (unsigned)hsum2(row[k][2]) + ((col[k >> 1][2] >> sh) & 0xFFFFu);
+        aAf[k] = (unsigned)hsum2(row[k][3]) + ((col[k >> 1][3] >> sh) & 0xFFFFu);
+      }
+    } else {
+      const int NW = (N + 1) >> 1;
+#pragma unroll 2
+      for (int q = 0; q < NW; ++q) {
+        const uint4 w = spw[q];
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if constexpr (HAS_VF) u = *reinterpret_cast<const uint4*>(&svf[2 * q]);
+#pragma unroll
+        for (int k = 0; k < APL; ++k) {
+          const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], w);
+          aR[k] += lt2(TR, m);
+          aA[k] += lt2(TA, m);
+          aRf[k] += lt2(TRf, m);
+          aAf[k] += lt2(TAf, m);
+          if constexpr (HAS_VF) {
+            const unsigned gate = lt2(TV, m);
+            const unsigned g0 = gate & 0xFFFFu, g1 = gate >> 16;
+            aV[k] += gate;
+            accA[k] += g0 * u.x + g1 * u.z;
+            accD[k] += g0 * u.y + g1 * u.w;
+          }
         }
       }
     }

@@ -78,6 +78,7 @@ static StepParams base_params(const Ctx* c) {
   p.K = g.slab_len; p.PL = g.place_len; p.KP = g.pred_attempts; p.R = g.reset_slots;
   p.auto_reset = g.auto_reset; p.track_stats = g.track_stats;
   p.bitmap_words = c->bitmap_words;
+  p.one = 1;
   const swarm_state& s = c->st;
   p.x = s.x; p.y = s.y; p.px = s.px; p.py = s.py; p.target = s.target; p.orient = s.pred_orient;
   p.frozen = s.frozen; p.err = s.err; p.reset_count = s.reset_count;

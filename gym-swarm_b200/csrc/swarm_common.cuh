@@ -27,6 +27,7 @@ struct StepParams {
   int K, PL, KP, R;
   int auto_reset, track_stats;
   int bitmap_words;  // per-env smem occupancy bitmap words (0: not used)
+  int one;           // runtime 1: `v * one + acc` compiles to IMAD (FMA pipe) instead of IADD3 (ALU pipe)
   // state
   int16_t *x, *y, *px, *py;
   int32_t* target;
