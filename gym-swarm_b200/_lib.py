@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswarm_b200.so")
+# SWARM_B200_LIB selects another build of the same library (kernel A/B experiments); never a CPU path
+LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(_HERE, "libswarm_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "swarm_abi.h")
 
 ABI_VERSION = 1

@@ -14,6 +14,14 @@
 #pragma once
 #include "swarm_common.cuh"
 
+#ifndef FUSED_WARPS
+#define FUSED_WARPS 4    // warps per CTA of the fused kernels
+#endif
+#ifndef FUSED_MINB
+#define FUSED_MINB 6     // minimum resident CTAs per SM the step kernel is compiled for (caps registers at 80:
+                         // measured on cfg3: 8 warps x 2 CTAs 0.339 ms, 4 x 5 0.328 ms, 4 x 6 0.316 ms per step)
+#endif
+
 namespace swarm {
 
 template <int LPE>
@@ -298,14 +306,14 @@ struct FusedCfg {
   static constexpr int EPW = 32 / LPE;       // envs per warp
   static constexpr int NMAX = LPE * APL;     // agents per env capacity
   static constexpr int PW = NMAX / 2;        // pair words per env
-  static constexpr int WARPS = 8;            // warps per CTA
+  static constexpr int WARPS = FUSED_WARPS;  // warps per CTA
   // bytes of smem per warp: pair words (aliased by the collision keys) + VF words + bitmap
   __host__ __device__ static constexpr int pair_bytes() { return EPW * PW * 16; }
   __host__ __device__ static constexpr int vf_bytes() { return EPW * NMAX * 8; }
 };
 
 template <int LPE, int APL, bool HAS_VF>
-__global__ void __launch_bounds__(FusedCfg<LPE, APL>::WARPS * 32)
+__global__ void __launch_bounds__(FusedCfg<LPE, APL>::WARPS * 32, (APL == 8 || HAS_VF) ? 3 : FUSED_MINB)
 fused_step_kernel(const __grid_constant__ StepParams p) {
   using C = FusedCfg<LPE, APL>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -437,10 +445,13 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
         spw[g.li >> 1] = make_uint4(pack2(sx[0], ox), pack2(sy[0], oy), pack2(-sx[0], -ox), pack2(-sy[0], -oy));
       }
     } else {
+      // ring sweep: word w of every lane contiguous ([w][lane]) so that the rotated LDS.128 is conflict free
+      constexpr bool RING = !HAS_VF && (APL == 2 || APL == 4) && LPE >= 4;
 #pragma unroll
       for (int k = 0; k < APL; k += 2)
-        spw[(i0 + k) >> 1] = make_uint4(pack2(sx[k], sx[k + 1]), pack2(sy[k], sy[k + 1]),
-                                        pack2(-sx[k], -sx[k + 1]), pack2(-sy[k], -sy[k + 1]));
+        spw[RING ? (k >> 1) * LPE + g.li : (i0 + k) >> 1] =
+            make_uint4(pack2(sx[k], sx[k + 1]), pack2(sy[k], sy[k + 1]), pack2(-sx[k], -sx[k + 1]),
+                       pack2(-sy[k], -sy[k + 1]));
     }
     if constexpr (HAS_VF) {
 #pragma unroll
@@ -490,7 +501,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
       // round 0: own block, rows only
 #pragma unroll
       for (int w = 0; w < W; ++w) {
-        const uint4 vw = spw[g.li * W + w];
+        const uint4 vw = spw[w * LPE + g.li];
 #pragma unroll
         for (int k = 0; k < APL; ++k) {
           const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
@@ -510,7 +521,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
         }
 #pragma unroll
         for (int w = 0; w < W; ++w) {
-          const uint4 vw = spw[src * W + w];
+          const uint4 vw = spw[w * LPE + src];
 #pragma unroll
           for (int k = 0; k < APL; ++k) {
             const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
@@ -536,7 +547,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
         const int src = (g.li + HALF) & (LPE - 1);
 #pragma unroll
         for (int w = 0; w < W; ++w) {
-          const uint4 vw = spw[src * W + w];
+          const uint4 vw = spw[w * LPE + src];
 #pragma unroll
           for (int k = 0; k < APL; ++k) {
             const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);

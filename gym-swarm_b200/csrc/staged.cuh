@@ -274,6 +274,107 @@ __global__ void __launch_bounds__(1024) collide_kernel(const StepParams p, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2b: collision re-draw rounds with the env's occupancy bitmap in SHARED memory (S*S bits: 128 KB at
+// S = 1024) -- the large-N analogue of bitmap_counts in the fused kernel.  Every agent sets its cell's bit
+// (atomicOr); an agent that finds the bit set is a "hit" and a cell holding c agents yields exactly c-1 hits,
+// so c_i = 1 + #{hits on agent i's cell}.  Hits are counted per cell in a small shared hash table
+// (COLL_HC slots), every agent then looks its cell up once.  If a round has more hits than the table can
+// take (very dense grids) that round falls back to the global hash of collide_kernel.
+// Requires ceil(N / blockDim) <= 16 (c_i - 1 is kept in 4 bits per agent; c_i <= 9 because the old cells
+// are distinct and a move is at most one cell).
+// ------------------------------------------------------------------------------------------------
+constexpr int COLL_HC = 4096;   // shared hash slots (power of two)
+
+__global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p, const StagedScratch sc, int bm_words) {
+  extern __shared__ __align__(16) unsigned coll_smem[];
+  __shared__ BlockScratch bs;
+  unsigned* sbit = coll_smem;                    // [bm_words]
+  unsigned* hkeys = coll_smem + bm_words;        // [COLL_HC]
+  unsigned* hcnt = hkeys + COLL_HC;              // [COLL_HC]
+  const int N = p.N, S = p.S;
+  const EnvHash gh = env_hash(sc, N);
+  const int per = (N + blockDim.x - 1) / blockDim.x;
+  const int lo = min(N, (int)threadIdx.x * per), hi = min(N, lo + per);
+  for (int w = threadIdx.x; w < bm_words; w += blockDim.x) sbit[w] = 0u;
+  for (int w = threadIdx.x; w < COLL_HC; w += blockDim.x) { hkeys[w] = HASH_EMPTY; hcnt[w] = 0u; }
+  __syncthreads();
+  for (int env = blockIdx.x; env < p.E; env += gridDim.x) {
+    if (p.frozen[env]) continue;              // uniform per CTA
+    const size_t base = (size_t)env * (size_t)N;
+    int16_t* __restrict__ nx = sc.nx + base;
+    int16_t* __restrict__ ny = sc.ny + base;
+    uint8_t* __restrict__ eff = sc.eff + base;
+    const uint8_t* __restrict__ slab = p.slab + (size_t)env * (size_t)p.K;
+    int cur = 0;
+    unsigned err = 0;
+    for (;;) {
+      // phase A: bitmap insert, hit flags
+      unsigned hitmask = 0u;
+      for (int i = lo; i < hi; ++i) {
+        const int cell = (int)ny[i] * S + (int)nx[i];
+        const unsigned bit = 1u << (cell & 31);
+        if (atomicOr(&sbit[cell >> 5], bit) & bit) hitmask |= 1u << (i - lo);
+      }
+      const int H = block_sum(__popc(hitmask), bs);     // (syncs: all bits are set)
+      for (int i = lo; i < hi; ++i) sbit[((int)ny[i] * S + (int)nx[i]) >> 5] = 0u;   // leave the bitmap clean
+      if (H == 0) { __syncthreads(); break; }                                       // change_position_id -> None
+      unsigned long long cpack = 0ull;                  // (c_i - 1) in 4 bits per owned agent
+      int extra = 0;
+      const bool small = H <= COLL_HC / 2;
+      if (small) {
+        for (int i = lo; i < hi; ++i)
+          if (hitmask & (1u << (i - lo))) hash_insert(hkeys, hcnt, COLL_HC - 1, 12, pack2(nx[i], ny[i]));
+        __syncthreads();
+        for (int i = lo; i < hi; ++i) {
+          const unsigned key = pack2(nx[i], ny[i]);
+          unsigned sl = hash_slot(key, 12);
+          unsigned cnt = 0u;
+          for (;;) {
+            const unsigned k = hkeys[sl];
+            if (k == key) { cnt = hcnt[sl]; break; }
+            if (k == HASH_EMPTY) break;
+            sl = (sl + 1u) & (COLL_HC - 1);
+          }
+          cnt = min(cnt, 15u);
+          cpack |= (unsigned long long)cnt << (4 * (i - lo));
+          extra += (int)cnt;
+        }
+      } else {
+        extra = hash_count_extra(gh, lo, hi, [&](int i) { return pack2(nx[i], ny[i]); });
+        for (int i = lo; i < hi; ++i) cpack |= (unsigned long long)min(hash_c(gh, i) - 1, 15) << (4 * (i - lo));
+      }
+      int L;
+      int off = block_excl_scan(extra, L, bs);           // (syncs: all lookups are done)
+      const bool overflow = cur + L > p.K;
+      if (!overflow) {
+        for (int i = lo; i < hi; ++i) {
+          const int e = (int)((cpack >> (4 * (i - lo))) & 15ull);
+          if (e > 0) {                                       // SDE:250-255
+            const int a = slab[cur + off + e - 1] & 7;
+            eff[i] = (uint8_t)a;
+            nx[i] = (int16_t)wrap1((int)p.x[base + i] + move_dx(a), S);
+            ny[i] = (int16_t)wrap1((int)p.y[base + i] + move_dy(a), S);
+          }
+          off += e;
+        }
+      }
+      if (small) {
+        for (int w = threadIdx.x; w < COLL_HC; w += blockDim.x) { hkeys[w] = HASH_EMPTY; hcnt[w] = 0u; }
+        __syncthreads();
+      } else {
+        hash_clear(gh, lo, hi);
+      }
+      if (overflow) { err |= SWARM_ERR_SLAB_OVERFLOW; break; }
+      cur += L;
+    }
+    if (threadIdx.x == 0) {
+      p.consumed[env] = cur;
+      if (err) p.err[env] |= err;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: predator, one warp per env (any N).  Reads the OLD positions only when the env retargets.
 // Also the standalone swarm_predator kernel (then frozen == nullptr, outputs subset).
 // ------------------------------------------------------------------------------------------------

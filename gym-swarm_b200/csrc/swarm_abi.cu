@@ -31,6 +31,8 @@ struct Ctx {
   StagedScratch sc{};
   void* scratch_block = nullptr;
   int per_env_threads = 256;
+  int coll_bm_words = 0;      // > 0: collide_bitmap_kernel (per-env occupancy bitmap fits in shared memory)
+  int coll_smem_bytes = 0;
   // stats
   double* d_stats = nullptr;
   // nccl
@@ -159,6 +161,18 @@ static int staged_alloc(Ctx* c) {
   int threads = 128;
   while (threads < 1024 && threads * 4 < N) threads <<= 1;
   c->per_env_threads = threads;
+  {
+    const long long cells = (long long)c->cfg.grid_size * c->cfg.grid_size;
+    const long long words = (cells + 31) / 32;
+    const long long bytes = words * 4 + (long long)COLL_HC * 8;
+    int dev_max = 0;
+    cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->cfg.device);
+    if (bytes + 1024 <= dev_max && (N + threads - 1) / threads <= 16) {
+      c->coll_bm_words = (int)words;
+      c->coll_smem_bytes = (int)bytes;
+      CUDA_TRY(c, cudaFuncSetAttribute(collide_bitmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+  }
   const size_t hs = (size_t)1 << log2hs;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -441,7 +455,10 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     const int grid = (int)std::min<long long>((nvec + 255) / 256, (long long)c->num_sms * 16);
     move_kernel<<<grid, 256, 0, s>>>(total, p.N, p.S, p.x, p.y, p.actions, sc.nx, sc.ny, sc.eff, p.err);
   }
-  collide_kernel<<<sc.env_grid, c->per_env_threads, 0, s>>>(p, sc);
+  if (c->coll_bm_words > 0)
+    collide_bitmap_kernel<<<sc.env_grid, c->per_env_threads, c->coll_smem_bytes, s>>>(p, sc, c->coll_bm_words);
+  else
+    collide_kernel<<<sc.env_grid, c->per_env_threads, 0, s>>>(p, sc);
   {
     PredIO io;
     io.E = p.E; io.N = p.N; io.S = p.S; io.xo = p.x; io.yo = p.y; io.xn = sc.nx; io.yn = sc.ny;

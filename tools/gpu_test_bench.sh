@@ -8,3 +8,5 @@ try:
 except Exception as e: print("fail", e)
 PY
 tail -3 gpurun_out/bench_$c.err; done
+B4="python bench.py --config cfg4 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+$B4 > gpurun_out/plain4.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_cfg4.csv $B4 > gpurun_out/ncu_l4.log 2>&1; echo rc=$?
