@@ -487,37 +487,41 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
       // ALU pipe to the DPX ops.
       constexpr int W = APL / 2;
       constexpr int HALF = LPE / 2;
-      const unsigned one = (unsigned)p.one;
-      const unsigned T4[4] = {TR, TA, TRf, TAf};
-      unsigned row[APL][4], col[W][4];
+      const unsigned one = (unsigned)p.one, c256 = (unsigned)p.one << 8;
+      // Counters are BYTE packed: a 16x2 indicator word holds 0/1 in bytes 0 and 2, so ind(t0) + 256 * ind(t1)
+      // carries two thresholds for two agents in one register ({t0,t1} = {rep,att} and {rep_far,att_far}); it is
+      // built once (IMAD) and added to the row and to the column counter.  No byte can overflow: a row byte
+      // meets at most NMAX / 2 <= 64 pair words, a column byte at most (LPE / 2 - 1) * APL <= 60 rows.
+      unsigned row[APL][2], col[W][2];
 #pragma unroll
-      for (int k = 0; k < APL; ++k)
+      for (int k = 0; k < APL; ++k) row[k][0] = row[k][1] = 0u;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) row[k][t] = 0u;
+      for (int w = 0; w < W; ++w) col[w][0] = col[w][1] = 0u;
+      auto rows_only = [&](int src) {
 #pragma unroll
-      for (int w = 0; w < W; ++w)
+        for (int w = 0; w < W; ++w) {
+          const uint4 vw = spw[w * LPE + src];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) col[w][t] = 0u;
-      // round 0: own block, rows only
-#pragma unroll
-      for (int w = 0; w < W; ++w) {
-        const uint4 vw = spw[w * LPE + g.li];
-#pragma unroll
-        for (int k = 0; k < APL; ++k) {
-          const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) row[k][t] = lt2(T4[t], m) * one + row[k][t];
+          for (int k = 0; k < APL; ++k) {
+            const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
+            row[k][0] = lt2(TR, m) * one + row[k][0];
+            row[k][0] = lt2(TA, m) * c256 + row[k][0];
+            row[k][1] = lt2(TRf, m) * one + row[k][1];
+            row[k][1] = lt2(TAf, m) * c256 + row[k][1];
+          }
         }
-      }
+      };
+      rows_only(g.li);                                       // round 0: own block
       const int nxt = (g.li + 1) & (LPE - 1);
 #pragma unroll 1
       for (int r = 1; r < HALF; ++r) {
         const int src = (g.li + r) & (LPE - 1);
         if (r > 1) {
 #pragma unroll
-          for (int w = 0; w < W; ++w)
-#pragma unroll
-            for (int t = 0; t < 4; ++t) col[w][t] = __shfl_sync(g.mask, col[w][t], nxt, LPE);
+          for (int w = 0; w < W; ++w) {
+            col[w][0] = __shfl_sync(g.mask, col[w][0], nxt, LPE);
+            col[w][1] = __shfl_sync(g.mask, col[w][1], nxt, LPE);
+          }
         }
 #pragma unroll
         for (int w = 0; w < W; ++w) {
@@ -525,12 +529,12 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
           for (int k = 0; k < APL; ++k) {
             const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const unsigned ind = lt2(T4[t], m);
-              row[k][t] = ind * one + row[k][t];
-              col[w][t] = ind * one + col[w][t];
-            }
+            const unsigned n0 = lt2(TA, m) * c256 + lt2(TR, m);
+            const unsigned n1 = lt2(TAf, m) * c256 + lt2(TRf, m);
+            row[k][0] = n0 * one + row[k][0];
+            row[k][1] = n1 * one + row[k][1];
+            col[w][0] = n0 * one + col[w][0];
+            col[w][1] = n1 * one + col[w][1];
           }
         }
       }
@@ -538,32 +542,20 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
       if constexpr (HALF > 1) {
         const int from = (g.li - (HALF - 1)) & (LPE - 1);
 #pragma unroll
-        for (int w = 0; w < W; ++w)
-#pragma unroll
-          for (int t = 0; t < 4; ++t) col[w][t] = __shfl_sync(g.mask, col[w][t], from, LPE);
-      }
-      // round LPE/2: met from both sides, rows only
-      {
-        const int src = (g.li + HALF) & (LPE - 1);
-#pragma unroll
         for (int w = 0; w < W; ++w) {
-          const uint4 vw = spw[w * LPE + src];
-#pragma unroll
-          for (int k = 0; k < APL; ++k) {
-            const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) row[k][t] = lt2(T4[t], m) * one + row[k][t];
-          }
+          col[w][0] = __shfl_sync(g.mask, col[w][0], from, LPE);
+          col[w][1] = __shfl_sync(g.mask, col[w][1], from, LPE);
         }
       }
-      // fold: total count = both halves of the row counter + this agent's half of the column counter
+      rows_only((g.li + HALF) & (LPE - 1));                  // round LPE/2: met from both sides
+      // fold: total = both agents' bytes of the row counter + this agent's bytes of the column counter
 #pragma unroll
       for (int k = 0; k < APL; ++k) {
         const int sh = 16 * (k & 1);
-        aR[k] = (unsigned)hsum2(row[k][0]) + ((col[k >> 1][0] >> sh) & 0xFFFFu);
-        aA[k] = (unsigned)hsum2(row[k][1]) + ((col[k >> 1][1] >> sh) & 0xFFFFu);
-        aRf[k] = (unsigned)hsum2(row[k][2]) + ((col[k >> 1][2] >> sh) & 0xFFFFu);
-        aAf[k] = (unsigned)hsum2(row[k][3]) + ((col[k >> 1][3] >> sh) & 0xFFFFu);
+        aR[k] = __dp4a(row[k][0], 0x00010001u, 0u) + ((col[k >> 1][0] >> sh) & 0xFFu);
+        aA[k] = __dp4a(row[k][0], 0x01000100u, 0u) + ((col[k >> 1][0] >> (sh + 8)) & 0xFFu);
+        aRf[k] = __dp4a(row[k][1], 0x00010001u, 0u) + ((col[k >> 1][1] >> sh) & 0xFFu);
+        aAf[k] = __dp4a(row[k][1], 0x01000100u, 0u) + ((col[k >> 1][1] >> (sh + 8)) & 0xFFu);
       }
     } else {
       const int NW = (N + 1) >> 1;

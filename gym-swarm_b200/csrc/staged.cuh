@@ -32,6 +32,7 @@ struct StagedScratch {
   uint4* pairw;            // [E,NW] packed pair words
   uint2* vfw;              // [E,2*NW] (VF) packed unit-vector words
   unsigned* pcounts;       // [E,N,8] per-agent accumulators {cR,cA,cRf,cAf,cV,accA,accD,-}
+  unsigned* counter;       // work counter of pairwise_sym_kernel (behind pcounts)
   int NW;
 };
 
@@ -626,8 +627,9 @@ static inline void launch_predator(const PredIO& io, int num_sms, cudaStream_t s
 __global__ void __launch_bounds__(256) pairprep_kernel(int E, int N, int S, int NW, const int16_t* __restrict__ x,
                                                        const int16_t* __restrict__ y, const uint8_t* __restrict__ eff,
                                                        uint4* __restrict__ pairw, uint2* __restrict__ vfw,
-                                                       unsigned* __restrict__ pcounts) {
+                                                       unsigned* __restrict__ pcounts, unsigned* __restrict__ counter) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0 && counter) *counter = 0u;              // work counter of pairwise_sym_kernel
   if (t >= (long long)E * NW) return;
   const int env = (int)(t / NW), q = (int)(t % NW);
   const size_t base = (size_t)env * (size_t)N;
@@ -706,6 +708,7 @@ struct PairIO {
   unsigned* pcounts;        // [E,N,8]
   int tiles_per_env, chunks_per_env;
   long long units;
+  int one;                  // runtime 1 (see StepParams::one)
 };
 
 template <bool HAS_VF>
@@ -748,6 +751,7 @@ __global__ void __launch_bounds__(PW_THREADS) pairwise_kernel(const PairIO io) {
 
   const unsigned TR = rep2(io.t_rep), TA = rep2(io.t_att), TRf = rep2(io.t_repf), TAf = rep2(io.t_attf);
   const unsigned TV = rep2(HAS_VF ? io.t_vf : 0);
+  const unsigned one = (unsigned)io.one;
 
   unsigned XI[PW_APL], YI[PW_APL], NXI[PW_APL], NYI[PW_APL];
   unsigned aR[PW_APL], aA[PW_APL], aRf[PW_APL], aAf[PW_APL], aV[PW_APL], accA[PW_APL], accD[PW_APL];
@@ -806,10 +810,10 @@ __global__ void __launch_bounds__(PW_THREADS) pairwise_kernel(const PairIO io) {
 #pragma unroll
         for (int k = 0; k < PW_APL; ++k) {
           const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], w);
-          aR[k] += lt2(TR, m);
-          aA[k] += lt2(TA, m);
-          aRf[k] += lt2(TRf, m);
-          aAf[k] += lt2(TAf, m);
+          aR[k] = lt2(TR, m) * one + aR[k];          // IMAD by a runtime 1: FMA pipe, the ALU pipe keeps the DPX ops
+          aA[k] = lt2(TA, m) * one + aA[k];
+          aRf[k] = lt2(TRf, m) * one + aRf[k];
+          aAf[k] = lt2(TAf, m) * one + aAf[k];
           if (HAS_VF) {
             const unsigned gate = lt2(TV, m);
             aV[k] += gate;
@@ -822,6 +826,180 @@ __global__ void __launch_bounds__(PW_THREADS) pairwise_kernel(const PairIO io) {
     __syncthreads();   // everyone is done with sj[stage] before it is refilled two units later
   }
   flush();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5s: symmetric tiled pairwise kernel (no visual-field gate).  D_ij = D_ji, so every unordered pair of
+// 128-agent tiles (A <= B) of an env is evaluated ONCE by one warp and credited to both sides:
+//   lane l owns 4 agents of tile A (rows, in registers); the 32 blocks of tile B are staged in the warp's
+//   shared memory ([word][lane] layout: the rotated LDS.128 is conflict free) and met one per round; each
+//   indicator goes to the lane's ROW counters and to the visiting block's COLUMN counters, which travel round
+//   the ring by shuffles with the block they belong to (after 32 rotations they are home again).  The diagonal
+//   unit A == B uses the half ring of the fused kernel.  Rows are flushed once per item, columns once per unit
+//   (integer atomicAdd: order independent, results are exact).
+// Work items (env, A, chunk of PS_CHUNK B-tiles) are handed out by an atomic counter (zeroed by pairprep).
+// Executed instruction mix per word evaluation (2 unordered = 4 ordered pairs): 8 DPX on the ALU pipe,
+// 8 IMAD on the FMA pipe -- versus 10 ALU instructions per 2 ordered pairs in the row-only sweep.
+// ------------------------------------------------------------------------------------------------
+constexpr int PS_WARPS = 4;
+constexpr int PS_CHUNK = 8;
+
+struct PairSymIO {
+  int E, N, S, NW, T, CH;          // T tiles of 128 agents per env, CH = ceil(T / PS_CHUNK) chunk columns
+  int t_rep, t_att, t_repf, t_attf;
+  const uint4* pairw;              // [E, NW]
+  const uint8_t* skip;             // [E] (nullable)
+  unsigned* pcounts;               // [E, N, 8]
+  unsigned* counter;               // work counter (zero on entry)
+  long long items;                 // E * T * CH (about half of them are empty and skipped)
+  int one;
+};
+
+__device__ __forceinline__ uint4 pair_word_or_pad(const uint4* __restrict__ pw, int q, int NW, int S) {
+  if (q < NW) return __ldg(pw + q);
+  return make_uint4(pack2(-S, -S), 0u, pack2(S, S), 0u);
+}
+
+__global__ void __launch_bounds__(PS_WARPS * 32, 6) pairwise_sym_kernel(const PairSymIO io) {
+  __shared__ __align__(16) uint4 sB[PS_WARPS][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint4* sb = sB[warp];
+  const unsigned one = (unsigned)io.one, c256 = (unsigned)io.one << 8;
+  const unsigned TR = rep2(io.t_rep), TA = rep2(io.t_att), TRf = rep2(io.t_repf), TAf = rep2(io.t_attf);
+  const int nxt = (lane + 1) & 31;
+  for (;;) {
+    long long item = 0;
+    if (lane == 0) item = (long long)atomicAdd(io.counter, 1u);
+    item = __shfl_sync(0xFFFFFFFFu, item, 0);
+    if (item >= io.items) break;
+    const int per_env = io.T * io.CH;
+    const int env = (int)(item / per_env);
+    const int idx = (int)(item % per_env);
+    const int A = idx / io.CH;
+    const int B0 = A + (idx % io.CH) * PS_CHUNK;
+    if (B0 >= io.T) continue;
+    if (io.skip && io.skip[env]) continue;
+    const int B1 = min(io.T, B0 + PS_CHUNK);
+    const uint4* __restrict__ pw = io.pairw + (size_t)env * io.NW;
+    unsigned* __restrict__ pc = io.pcounts + (size_t)env * io.N * 8;
+
+    unsigned XI[4], YI[4], NXI[4], NYI[4], rowsum[4][4];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const uint4 ow = pair_word_or_pad(pw, A * 64 + 2 * lane + w, io.NW, io.S);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = 2 * w + h;
+        XI[k] = rep2((int)(int16_t)((ow.x >> (16 * h)) & 0xFFFFu));
+        YI[k] = rep2((int)(int16_t)((ow.y >> (16 * h)) & 0xFFFFu));
+        NXI[k] = rep2((int)(int16_t)((ow.z >> (16 * h)) & 0xFFFFu));
+        NYI[k] = rep2((int)(int16_t)((ow.w >> (16 * h)) & 0xFFFFu));
+#pragma unroll
+        for (int t = 0; t < 4; ++t) rowsum[k][t] = 0u;
+      }
+    }
+
+    for (int B = B0; B < B1; ++B) {
+      __syncwarp();                                   // previous unit's reads of sb are done
+      sb[lane] = pair_word_or_pad(pw, B * 64 + 2 * lane, io.NW, io.S);
+      sb[32 + lane] = pair_word_or_pad(pw, B * 64 + 2 * lane + 1, io.NW, io.S);
+      __syncwarp();
+      // BYTE packed counters (see the fused kernel): [.][0] = {rep, att}, [.][1] = {rep_far, att_far}.
+      // Per unit a row byte meets <= 64 pair words and a column byte <= 128 rows: no overflow.
+      unsigned row[4][2], col[2][2];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) row[k][0] = row[k][1] = 0u;
+#pragma unroll
+      for (int w = 0; w < 2; ++w) col[w][0] = col[w][1] = 0u;
+
+      auto rows_only = [&](int src) {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const uint4 vw = sb[w * 32 + src];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
+            row[k][0] = lt2(TR, m) * one + row[k][0];
+            row[k][0] = lt2(TA, m) * c256 + row[k][0];
+            row[k][1] = lt2(TRf, m) * one + row[k][1];
+            row[k][1] = lt2(TAf, m) * c256 + row[k][1];
+          }
+        }
+      };
+      auto rows_cols = [&](int src) {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const uint4 vw = sb[w * 32 + src];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
+            const unsigned n0 = lt2(TA, m) * c256 + lt2(TR, m);
+            const unsigned n1 = lt2(TAf, m) * c256 + lt2(TRf, m);
+            row[k][0] = n0 * one + row[k][0];
+            row[k][1] = n1 * one + row[k][1];
+            col[w][0] = n0 * one + col[w][0];
+            col[w][1] = n1 * one + col[w][1];
+          }
+        }
+      };
+      auto rotate = [&](int from) {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          col[w][0] = __shfl_sync(0xFFFFFFFFu, col[w][0], from);
+          col[w][1] = __shfl_sync(0xFFFFFFFFu, col[w][1], from);
+        }
+      };
+
+      if (B == A) {                                   // diagonal unit: half ring (as in the fused kernel)
+        rows_only(lane);
+#pragma unroll 1
+        for (int r = 1; r < 16; ++r) {
+          if (r > 1) rotate(nxt);
+          rows_cols((lane + r) & 31);
+        }
+        rotate((lane - 15) & 31);                     // lane l held the counters of block l + 15
+        rows_only((lane + 16) & 31);
+      } else {                                        // off-diagonal unit: full ring, 32 rounds
+#pragma unroll 1
+        for (int r = 0; r < 32; ++r) {
+          if (r > 0) rotate(nxt);
+          rows_cols((lane + r) & 31);
+        }
+        rotate(nxt);                                  // 32nd rotation: home
+      }
+      // widen the row bytes, flush the column counters of tile B
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        rowsum[k][0] += __dp4a(row[k][0], 0x00010001u, 0u);
+        rowsum[k][1] += __dp4a(row[k][0], 0x01000100u, 0u);
+        rowsum[k][2] += __dp4a(row[k][1], 0x00010001u, 0u);
+        rowsum[k][3] += __dp4a(row[k][1], 0x01000100u, 0u);
+      }
+#pragma unroll
+      for (int w = 0; w < 2; ++w)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = B * 128 + 4 * lane + 2 * w + h;
+          if (j < io.N) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const unsigned v = (col[w][t >> 1] >> (16 * h + 8 * (t & 1))) & 0xFFu;
+              if (v) atomicAdd(pc + (size_t)j * 8 + t, v);
+            }
+          }
+        }
+    }
+    // flush the row counters of tile A
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = A * 128 + 4 * lane + k;
+      if (i < io.N) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (rowsum[k][t]) atomicAdd(pc + (size_t)i * 8 + t, rowsum[k][t]);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

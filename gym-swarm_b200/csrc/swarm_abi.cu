@@ -180,11 +180,13 @@ static int staged_alloc(Ctx* c) {
   const size_t o_hash = take((size_t)sc.env_grid * 2 * hs * 4), o_aslot = take((size_t)sc.env_grid * N * 4);
   const size_t o_pairw = take((size_t)E * sc.NW * 16), o_vfw = take((size_t)E * sc.NW * 16);
   const size_t o_pc = take((size_t)E * N * 32 + 64);
+  const size_t o_cnt = take(256);
   CUDA_TRY(c, cudaMalloc(&c->scratch_block, off));
   char* b = (char*)c->scratch_block;
   sc.nx = (int16_t*)(b + o_nx); sc.ny = (int16_t*)(b + o_ny); sc.eff = (uint8_t*)(b + o_eff);
   sc.hash = (unsigned*)(b + o_hash); sc.aslot = (unsigned*)(b + o_aslot);
   sc.pairw = (uint4*)(b + o_pairw); sc.vfw = (uint2*)(b + o_vfw); sc.pcounts = (unsigned*)(b + o_pc);
+  sc.counter = (unsigned*)(b + o_cnt);
   CUDA_TRY(c, cudaMemset(b + o_hash, 0xFF, (size_t)sc.env_grid * hs * 4 * 2));   // keys = EMPTY ...
   // ... and counts = 0: keys and counts are interleaved per CTA ({keys[HS], cnt[HS]}), fix the counts
   for (int g = 0; g < sc.env_grid; ++g)
@@ -194,6 +196,21 @@ static int staged_alloc(Ctx* c) {
 
 static int pairwise_launch(const StepParams& p, const StagedScratch& sc, const int16_t* x, const int16_t* y,
                            const uint8_t* skip, bool vf, int num_sms, cudaStream_t s) {
+  if (!vf) {                                   // symmetric tile sweep (every unordered tile pair once)
+    PairSymIO io;
+    io.E = p.E; io.N = p.N; io.S = p.S; io.NW = sc.NW;
+    io.T = (p.N + 127) / 128;
+    io.CH = (io.T + PS_CHUNK - 1) / PS_CHUNK;
+    io.t_rep = p.t_rep; io.t_att = p.t_att; io.t_repf = p.t_repf; io.t_attf = p.t_attf;
+    io.pairw = sc.pairw; io.skip = skip; io.pcounts = sc.pcounts; io.counter = sc.counter;
+    io.items = (long long)p.E * io.T * io.CH;
+    io.one = 1;
+    const long long real_items = (io.items + 1) / 2 + (long long)p.E * io.T;   // upper bound of non-empty items
+    long long grid = std::min<long long>((real_items + PS_WARPS - 1) / PS_WARPS, (long long)num_sms * 6);
+    if (grid < 1) grid = 1;
+    pairwise_sym_kernel<<<(int)grid, PS_WARPS * 32, 0, s>>>(io);
+    return 0;
+  }
   PairIO io;
   io.E = p.E; io.N = p.N; io.S = p.S; io.NW = sc.NW;
   io.t_rep = p.t_rep; io.t_att = p.t_att; io.t_repf = p.t_repf; io.t_attf = p.t_attf; io.t_vf = p.t_vf;
@@ -201,11 +218,11 @@ static int pairwise_launch(const StepParams& p, const StagedScratch& sc, const i
   io.tiles_per_env = (p.N + PW_TILE - 1) / PW_TILE;
   io.chunks_per_env = (sc.NW + PW_JC - 1) / PW_JC;
   io.units = (long long)p.E * io.tiles_per_env * io.chunks_per_env;
+  io.one = 1;
   // 4 resident CTAs per SM (128 threads, ~8-16 KB smem each); never more CTAs than units
   long long grid = std::min<long long>(io.units, (long long)num_sms * 4);
   if (grid < 1) grid = 1;
-  if (vf) pairwise_kernel<true><<<(int)grid, PW_THREADS, 0, s>>>(io);
-  else pairwise_kernel<false><<<(int)grid, PW_THREADS, 0, s>>>(io);
+  pairwise_kernel<true><<<(int)grid, PW_THREADS, 0, s>>>(io);
   return 0;
 }
 
@@ -470,7 +487,7 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
   {
     const long long words = (long long)p.E * sc.NW;
     pairprep_kernel<<<(int)((words + 255) / 256), 256, 0, s>>>(p.E, p.N, p.S, sc.NW, sc.nx, sc.ny, sc.eff, sc.pairw,
-                                                              vf ? sc.vfw : nullptr, sc.pcounts);
+                                                              vf ? sc.vfw : nullptr, sc.pcounts, sc.counter);
   }
   pairwise_launch(p, sc, sc.nx, sc.ny, p.done, vf, c->num_sms, s);
   if (vf) finalize_kernel<true><<<sc.env_grid, 256, 0, s>>>(p, sc);
@@ -537,13 +554,14 @@ int swarm_pairwise(int32_t E, int32_t N, int32_t S, int32_t attraction_thresh, i
   memset(&sc, 0, sizeof(sc));
   sc.NW = (N + 1) / 2;
   void* block = nullptr;
-  const size_t b_pairw = align_up((size_t)E * sc.NW * 16, 256), b_pc = (size_t)E * N * 32 + 64;
-  CUDA_TRY(nullptr, cudaMallocAsync(&block, b_pairw + b_pc, s));
+  const size_t b_pairw = align_up((size_t)E * sc.NW * 16, 256), b_pc = align_up((size_t)E * N * 32 + 64, 256);
+  CUDA_TRY(nullptr, cudaMallocAsync(&block, b_pairw + b_pc + 256, s));
   sc.pairw = (uint4*)block;
   sc.pcounts = (unsigned*)((char*)block + b_pairw);
+  sc.counter = (unsigned*)((char*)block + b_pairw + b_pc);
   const long long words = (long long)E * sc.NW;
   pairprep_kernel<<<(int)((words + 255) / 256), 256, 0, s>>>(E, N, S, sc.NW, x, y, nullptr, sc.pairw, nullptr,
-                                                            sc.pcounts);
+                                                            sc.pcounts, sc.counter);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
