@@ -46,7 +46,7 @@ CONFIGS = {
     "cfg5": dict(E=1048576, N=8, S=16, per_agent=False, curriculum=False,
                  desc="configs[4]: 1,048,576 envs x 8 agents, 16x16 grid, auto-reset + episode statistics"),
     # streaming shape for an honest DRAM number: 16 M envs x 8 agents
-    "stream": dict(E=16777216, N=8, S=16, per_agent=False, curriculum=False,
+    "stream": dict(E=16777216, N=8, S=16, per_agent=False, curriculum=False, place_extra=64,
                    desc="streaming shape: 16,777,216 envs x 8 agents, 16x16 grid (>= 1 GB of traffic per launch)"),
 }
 METRIC = "agent-steps/sec"
@@ -211,7 +211,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--path", default="auto", choices=["auto", "fused", "staged"])
+    ap.add_argument("--path", default="auto", choices=["auto", "fused", "group", "staged"])
     ap.add_argument("--vf", type=int, default=None, help="reward_type['vf_size'] (default None)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
@@ -249,7 +249,8 @@ def main():
     # ---- synthetic tapes, seeded per (config, rank) -------------------------------------
     rng = np.random.default_rng(sorted(CONFIGS).index(args.config) * 1000 + rank)
     env = BatchedSwarmEnv(E, N, S, device=f"cuda:{local_rank}", auto_reset=True, track_stats=True, reset_slots=4,
-                          per_agent=per_agent, debug_outputs=False, path=args.path)
+                          per_agent=per_agent, debug_outputs=False, path=args.path,
+                          place_extra=cfg.get("place_extra"))
     K = env.K
     place = torch.from_numpy(rng.integers(0, S, size=(env.R, E, env.PL), dtype=np.int16))
     ptape = torch.from_numpy(rng.integers(0, S, size=(env.R, E, env.KP, 2), dtype=np.int16))

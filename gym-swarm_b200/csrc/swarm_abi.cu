@@ -8,6 +8,7 @@
 #include <string>
 
 #include "fused_step.cuh"
+#include "tiny_step.cuh"
 #include "staged.cuh"
 
 namespace swarm {
@@ -23,6 +24,7 @@ struct Ctx {
   std::string err;
   std::string path_name;
   bool fused = false;
+  bool tiny = false;          // N <= 8: thread-per-env kernel (steps without a visual-field gate)
   int lpe = 0, apl = 0;
   int bitmap_words = 0;
   int launches = 0;
@@ -320,7 +322,7 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
     return fail(nullptr, SWARM_E_INVALID, "swarm_create: need more cells than agents + predator");
   if (cfg->slab_len < 0 || cfg->place_len < 2 * cfg->num_agents || cfg->pred_attempts < 1 || cfg->reset_slots < 1)
     return fail(nullptr, SWARM_E_INVALID, "swarm_create: bad tape geometry");
-  if (cfg->path == SWARM_PATH_FUSED && cfg->num_agents > SWARM_FUSED_MAX_AGENTS)
+  if ((cfg->path == SWARM_PATH_FUSED || cfg->path == SWARM_PATH_GROUP) && cfg->num_agents > SWARM_FUSED_MAX_AGENTS)
     return fail(nullptr, SWARM_E_INVALID, "swarm_create: fused path needs num_agents <= 256");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
@@ -332,14 +334,17 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
   cudaDeviceProp prop;
   CUDA_TRY(c, cudaGetDeviceProperties(&prop, cfg->device));
   c->num_sms = prop.multiProcessorCount;
-  c->fused = cfg->path == SWARM_PATH_FUSED || (cfg->path == SWARM_PATH_AUTO && cfg->num_agents <= SWARM_FUSED_MAX_AGENTS);
+  c->fused = cfg->path == SWARM_PATH_FUSED || cfg->path == SWARM_PATH_GROUP ||
+             (cfg->path == SWARM_PATH_AUTO && cfg->num_agents <= SWARM_FUSED_MAX_AGENTS);
+  c->tiny = c->fused && cfg->path != SWARM_PATH_GROUP && cfg->num_agents <= TINY_N;
   if (c->fused) {
     choose_fused_shape(cfg->num_agents, c->lpe, c->apl);
     const long long cells = (long long)cfg->grid_size * cfg->grid_size;
     const long long words = ((cells + 31) / 32 + 3) / 4 * 4;
     c->bitmap_words = (words <= 2048 && cfg->num_agents >= 16) ? (int)words : 0;
     char buf[64];
-    snprintf(buf, sizeof(buf), "fused<%d,%d>%s", c->lpe, c->apl, c->bitmap_words ? "+bitmap" : "");
+    if (c->tiny) snprintf(buf, sizeof(buf), "tiny<%d> (vf: fused<%d,%d>)", TINY_N, c->lpe, c->apl);
+    else snprintf(buf, sizeof(buf), "fused<%d,%d>%s", c->lpe, c->apl, c->bitmap_words ? "+bitmap" : "");
     c->path_name = buf;
   } else {
     c->path_name = "staged";
@@ -457,6 +462,14 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
   p.agent_reward = out->agent_reward; p.agent_counts = out->agent_counts; p.eff_action = out->eff_action;
   const bool vf = p.t_vf >= 0;
   c->launches = 0;
+  if (c->tiny && !vf) {
+    if (p.N == TINY_N && ((uintptr_t)in->actions & 7))
+      return fail(c, SWARM_E_INVALID, "swarm_step: actions must be 8-byte aligned");
+    tiny_step_kernel<<<(p.E + TINY_THREADS - 1) / TINY_THREADS, TINY_THREADS, 0, s>>>(p);
+    CUDA_TRY(c, cudaGetLastError());
+    c->launches = 1;
+    return SWARM_OK;
+  }
   if (c->fused) {
 #define CALL(L, A) CUDA_TRY(c, (launch_fused_step<L, A>(p, vf, s)))
     FUSED_DISPATCH(c, CALL);

@@ -1,0 +1,373 @@
+// tiny_step.cuh -- the fused transition for tiny environments (N <= 8): ONE THREAD PER ENVIRONMENT (sm_100a).
+//
+// With 8 agents an env's whole state is 16 B of x, 16 B of y and 8 B of actions: one LDG.128 + LDG.128 +
+// LDG.64 per thread, perfectly coalesced across the warp's 32 consecutive envs.  Everything the lane-group
+// kernel does with shuffles (collision counts, re-draw prefix sum, predator arg-min, reward reductions) is a
+// fully unrolled loop over registers here, and every per-env scalar (predator pursuit, outputs, statistics)
+// is executed once per thread instead of once per lane group: ~10x fewer issued instructions per env than
+// fused_step_kernel<8,1>.  Same semantics, same reference citations (SDE = swarm_discrete_env.py):
+//   move + wrap SDE:237-244, 60-80; collision re-draw SDE:246-255, 269-292; predator SDE:258-259, 111-165;
+//   termination SDE:307-309, 321-327; reward SDE:330-379; reset SDE:197-221, 90-109.
+// The pairwise reward uses the symmetric evaluation: agent i (replicated into both 16-bit halves) meets only
+// the pair words holding agents j > i; each DPX indicator is credited to i's row counter and to the word's
+// column counter (byte-packed two-threshold counters as in the ring sweeps).
+// vf_size != None is not handled here (the host dispatches those steps to fused_step_kernel<8,1>).
+#pragma once
+#include "swarm_common.cuh"
+
+namespace swarm {
+
+constexpr int TINY_N = 8;
+constexpr int TINY_THREADS = 128;
+
+// c[k] = number of agents on agent k's cell (SDE:269-292); keys of padding agents are unique. Returns sum(c-1).
+__device__ __forceinline__ int tiny_counts(const unsigned (&key)[TINY_N], int (&c)[TINY_N]) {
+#pragma unroll
+  for (int k = 0; k < TINY_N; ++k) c[k] = 1;
+#pragma unroll
+  for (int i = 0; i < TINY_N; ++i)
+#pragma unroll
+    for (int j = i + 1; j < TINY_N; ++j) {
+      const int eq = key[i] == key[j];
+      c[i] += eq;
+      c[j] += eq;
+    }
+  int L = 0;
+#pragma unroll
+  for (int k = 0; k < TINY_N; ++k) L += c[k] - 1;
+  return L;
+}
+
+__device__ __forceinline__ int tiny_closest(int N, int S, int qx, int qy, const int (&ax)[TINY_N], const int (&ay)[TINY_N]) {
+  unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;
+#pragma unroll
+  for (int k = 0; k < TINY_N; ++k) {
+    if (k < N) {
+      const int d = max(iabs(qx - ax[k]), iabs(qy - ay[k]));
+      klo = min(klo, nn_key_lo(d, k));
+      khi = min(khi, nn_key_hi(d, k));
+    }
+  }
+  return nn_pick(klo, khi, S);
+}
+
+// reference reset (SDE:197-221 + SDE:90-109) of one env by one thread
+__device__ __forceinline__ void tiny_reset(const StepParams& p, int env, int (&x)[TINY_N], int (&y)[TINY_N], int& px, int& py,
+                                        int& target, unsigned& err) {
+  const int N = p.N, S = p.S;
+  const unsigned rc = p.reset_count[env];
+  p.reset_count[env] = rc + 1u;
+  const size_t slot = (size_t)(rc % (unsigned)p.R) * (size_t)p.E + (size_t)env;
+  const int16_t* __restrict__ tape = p.place + slot * (size_t)p.PL;
+#pragma unroll
+  for (int k = 0; k < TINY_N; ++k) {
+    x[k] = k < N ? (int)tape[k] : 0;                 // SDE:202-203: all x's then all y's
+    y[k] = k < N ? (int)tape[N + k] : 0;
+  }
+  int cur = 2 * N;
+  for (;;) {
+    unsigned key[TINY_N];
+    int c[TINY_N];
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) key[k] = k < N ? pack2(x[k], y[k]) : (0xFFFF0000u | (unsigned)k);
+    const int L = tiny_counts(key, c);
+    if (L == 0) break;
+    if (cur + 2 * L > p.PL) { err |= SWARM_ERR_PLACE_OVERFLOW; break; }
+    int off = 0;
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) {
+      const int e = c[k] - 1;
+      if (e > 0) {                                    // SDE:208-209: (2,L) block, last duplicate wins
+        const int s = off + e - 1;
+        x[k] = tape[cur + s];
+        y[k] = tape[cur + L + s];
+      }
+      off += e;
+    }
+    cur += 2 * L;
+  }
+  const int16_t* __restrict__ pt = p.ptape + slot * (size_t)p.KP * 2;
+  int a = 0;
+  px = 0; py = 0;
+  for (;;) {                                          // SDE:92-105
+    if (a >= p.KP) { err |= SWARM_ERR_PRED_OVERFLOW; break; }
+    px = pt[2 * a]; py = pt[2 * a + 1];
+    ++a;
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) hit |= (k < N) && x[k] == px && y[k] == py;
+    if (!hit) break;
+  }
+  target = tiny_closest(N, S, px, py, x, y);          // SDE:109
+}
+
+__global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_constant__ StepParams p) {
+  const int env = blockIdx.x * TINY_THREADS + threadIdx.x;
+  if (env >= p.E) return;
+  const int N = p.N, S = p.S;
+  const size_t base = (size_t)env * (size_t)N;
+
+  if (p.frozen[env]) {                      // SDE:233-234: finished episode, auto-reset off
+    p.err[env] |= SWARM_ERR_STEP_WHEN_DONE;
+    p.done[env] = 1;
+    p.eaten[env] = -1;
+    p.counts[2 * env] = 0; p.counts[2 * env + 1] = 0;
+    p.consumed[env] = 0;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) p.reward[5 * env + q] = 0.f;
+    return;
+  }
+
+  // ---- load ---------------------------------------------------------------------------------------
+  int x[TINY_N], y[TINY_N], eff[TINY_N];
+  if (N == TINY_N) {
+    const uint4 xv = *reinterpret_cast<const uint4*>(p.x + base);
+    const uint4 yv = *reinterpret_cast<const uint4*>(p.y + base);
+    const uint2 av = *reinterpret_cast<const uint2*>(p.actions + base);
+    const unsigned xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) {
+      x[k] = (int)(int16_t)((xs[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
+      y[k] = (int)(int16_t)((ys[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
+      eff[k] = (int)(((k < 4 ? av.x : av.y) >> (8 * (k & 3))) & 0xFFu);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) {
+      x[k] = k < N ? (int)p.x[base + k] : 0;
+      y[k] = k < N ? (int)p.y[base + k] : 0;
+      eff[k] = k < N ? (int)p.actions[base + k] : 8;
+    }
+  }
+  int px = p.px[env], py = p.py[env];
+  int target = p.target[env];
+  const int retarget = p.retarget[env];
+  unsigned err = 0;
+  {
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) { bad |= eff[k] > 8; eff[k] = min(eff[k], 8); }
+    if (bad) err |= SWARM_ERR_BAD_ACTION;
+  }
+
+  // ---- move + collision re-draw rounds (SDE:237-255) --------------------------------------------
+  int nx[TINY_N], ny[TINY_N];
+  int cur = 0;
+  const uint8_t* __restrict__ slab = p.slab + (size_t)env * (size_t)p.K;
+  for (;;) {
+    unsigned key[TINY_N];
+    int c[TINY_N];
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) {
+      nx[k] = wrap1(x[k] + move_dx(eff[k]), S);          // SDE:60-80
+      ny[k] = wrap1(y[k] + move_dy(eff[k]), S);
+      key[k] = k < N ? pack2(nx[k], ny[k]) : (0xFFFF0000u | (unsigned)k);
+    }
+    const int L = tiny_counts(key, c);
+    if (L == 0) break;                                   // change_position_id returned None
+    if (cur + L > p.K) { err |= SWARM_ERR_SLAB_OVERFLOW; break; }
+    int off = 0;
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) {
+      const int e = c[k] - 1;
+      if (e > 0) eff[k] = slab[cur + off + e - 1] & 7;   // SDE:250-252: last of its c-1 draws wins
+      off += e;
+    }
+    cur += L;
+  }
+
+  // ---- predator (SDE:258-259, 133-165) on the OLD agent positions ------------------------------
+  const int prev_px = px, prev_py = py;
+  if (retarget) target = tiny_closest(N, S, px, py, x, y);
+  target = min(max(target, 0), N - 1);
+  int orient;
+  {
+    int tx = 0, ty = 0;
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k)
+      if (k == target) { tx = x[k]; ty = y[k]; }
+    pursue(px, py, tx, ty, S, px, py, orient);
+  }
+  const int step_target = target;
+
+  // ---- termination (SDE:307-309, 321-327) on the NEW positions ---------------------------------
+  int eaten = -1;
+#pragma unroll
+  for (int k = TINY_N - 1; k >= 0; --k)
+    if (k < N && nx[k] == px && ny[k] == py) eaten = k;
+  const bool done = eaten >= 0;
+
+  // ---- reward (SDE:330-379) ---------------------------------------------------------------------
+  double r_surv = 0.0, r_att = 0.0, r_rep = 0.0, r_ali = 0.0, r_sum = 0.0;
+  int g_rep = 0, g_att = 0;
+  if (!done) {
+    int sx[TINY_N], sy[TINY_N];
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) { sx[k] = k < N ? nx[k] : -S; sy[k] = k < N ? ny[k] : 0; }
+    uint4 pw[TINY_N / 2];
+#pragma unroll
+    for (int w = 0; w < TINY_N / 2; ++w)
+      pw[w] = make_uint4(pack2(sx[2 * w], sx[2 * w + 1]), pack2(sy[2 * w], sy[2 * w + 1]),
+                         pack2(-sx[2 * w], -sx[2 * w + 1]), pack2(-sy[2 * w], -sy[2 * w + 1]));
+    const unsigned TR = rep2(p.t_rep), TA = rep2(p.t_att), TRf = rep2(p.t_repf), TAf = rep2(p.t_attf);
+    const unsigned one = (unsigned)p.one, c256 = (unsigned)p.one << 8;
+    // byte-packed counters: [.][0] = {rep, att}, [.][1] = {rep_far, att_far}; a byte meets at most 8 pairs
+    unsigned row[TINY_N][2], col[TINY_N / 2][2];
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) row[k][0] = row[k][1] = 0u;
+#pragma unroll
+    for (int w = 0; w < TINY_N / 2; ++w) col[w][0] = col[w][1] = 0u;
+#pragma unroll
+    for (int i = 0; i < TINY_N; ++i) {
+      const unsigned XI = rep2(sx[i]), YI = rep2(sy[i]), NXI = rep2(-sx[i]), NYI = rep2(-sy[i]);
+      // even i: its own word holds (i, i+1): low half = the self pair (row only), high half = pair (i, i+1);
+      // odd i: its own word holds only pairs already met; the self pair is added analytically below
+#pragma unroll
+      for (int w = (i + 1) / 2; w < TINY_N / 2; ++w) {
+        const unsigned m = neg_cheb2(XI, YI, NXI, NYI, pw[w]);
+        const unsigned n0 = lt2(TA, m) * c256 + lt2(TR, m);
+        const unsigned n1 = lt2(TAf, m) * c256 + lt2(TRf, m);
+        row[i][0] = n0 * one + row[i][0];
+        row[i][1] = n1 * one + row[i][1];
+        if (2 * w == i) {                                   // own word of an even agent: no column credit for self
+          col[w][0] = (n0 & 0xFFFF0000u) * one + col[w][0];
+          col[w][1] = (n1 & 0xFFFF0000u) * one + col[w][1];
+        } else {
+          col[w][0] = n0 * one + col[w][0];
+          col[w][1] = n1 * one + col[w][1];
+        }
+      }
+    }
+    // alignment sums (SDE:346-359), vf_size == None
+    int Ax = 0, Ay = 0, Dx = 0, Dy = 0;
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) {
+      const int a = eff[k];
+      if (k < N && a < 8) {
+        const int mx = move_dx(a), my = move_dy(a);
+        if (a & 1) { Dx += mx; Dy += my; } else { Ax += mx; Ay += my; }
+      }
+    }
+    const int selfR = p.t_rep >= 1, selfA = p.t_att >= 1, selfRf = p.t_repf >= 1, selfAf = p.t_attf >= 1;
+    int s_P = 0, s_Q = 0;
+    float4* __restrict__ ar = p.agent_reward ? reinterpret_cast<float4*>(p.agent_reward) + base : nullptr;
+    int2* __restrict__ ac = p.agent_counts ? reinterpret_cast<int2*>(p.agent_counts) + base : nullptr;
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) {
+      if (k < N) {
+        const int sh = 16 * (k & 1);
+        // counts over j != k: row (pairs met as the row agent; includes the self pair for even k) + column
+        int cR = (int)__dp4a(row[k][0], 0x00010001u, 0u) + (int)((col[k >> 1][0] >> sh) & 0xFFu);
+        int cA = (int)__dp4a(row[k][0], 0x01000100u, 0u) + (int)((col[k >> 1][0] >> (sh + 8)) & 0xFFu);
+        int cRf = (int)__dp4a(row[k][1], 0x00010001u, 0u) + (int)((col[k >> 1][1] >> sh) & 0xFFu);
+        int cAf = (int)__dp4a(row[k][1], 0x01000100u, 0u) + (int)((col[k >> 1][1] >> (sh + 8)) & 0xFFu);
+        if ((k & 1) == 0) { cR -= selfR; cA -= selfA; cRf -= selfRf; cAf -= selfAf; }
+        int P, Q;
+        align_PQ(eff[k], Ax, Ay, Dx, Dy, 1, P, Q);
+        const AgentTerms t = agent_terms(p, cR, cA, cRf, cAf, N - 1, P, Q);
+        g_rep += t.rep_i; g_att += t.att_i; s_P += P; s_Q += Q;
+        if (ar) {                                           // SDE:371-379
+          const double a_rep = p.w_rep * (double)t.rep_i * p.inv_nn;
+          const double a_att = p.w_att * (double)t.att_i * p.inv_nn;
+          const double a_ali = p.w_ali * (-t.una) * p.inv_nn;
+          ar[k] = make_float4((float)a_att, (float)a_rep, (float)a_ali, (float)(a_rep + a_att + a_ali));
+        }
+        if (ac) ac[k] = make_int2(t.rep_i, t.att_i);
+      }
+    }
+    const double g_una = 0.5 * (double)(N * (N - 1)) - 0.25 * (double)s_P - 0.35355339059327376220 * (double)s_Q;
+    r_rep = p.w_rep * (double)g_rep * p.inv_nn;             // SDE:363-366
+    r_att = p.w_att * (double)g_att * p.inv_nn;
+    r_ali = p.w_ali * (-g_una) * p.inv_nn;
+    r_sum = r_rep + r_att + r_ali;
+  } else {
+    r_surv = (double)p.eat;
+    r_sum = (double)p.eat;
+    if (p.agent_reward) {
+      float4* __restrict__ ar = reinterpret_cast<float4*>(p.agent_reward) + base;
+#pragma unroll
+      for (int k = 0; k < TINY_N; ++k)
+        if (k < N) ar[k] = make_float4(0.f, 0.f, 0.f, k == eaten ? p.eat : 0.f);
+    }
+    if (p.agent_counts) {
+      int2* __restrict__ ac = reinterpret_cast<int2*>(p.agent_counts) + base;
+#pragma unroll
+      for (int k = 0; k < TINY_N; ++k)
+        if (k < N) ac[k] = make_int2(0, 0);
+    }
+  }
+  if (p.eff_action) {
+    if (N == TINY_N) {
+      *reinterpret_cast<uint2*>(p.eff_action + base) =
+          make_uint2((unsigned)(eff[0] | (eff[1] << 8) | (eff[2] << 16) | (eff[3] << 24)),
+                     (unsigned)(eff[4] | (eff[5] << 8) | (eff[6] << 16) | (eff[7] << 24)));
+    } else {
+#pragma unroll
+      for (int k = 0; k < TINY_N; ++k)
+        if (k < N) p.eff_action[base + k] = (uint8_t)eff[k];
+    }
+  }
+
+  // ---- per-env outputs ---------------------------------------------------------------------------
+  p.done[env] = done ? 1 : 0;
+  p.eaten[env] = eaten;
+  {
+    float* rw = p.reward + 5 * (size_t)env;
+    rw[0] = (float)r_surv; rw[1] = (float)r_att; rw[2] = (float)r_rep; rw[3] = (float)r_ali; rw[4] = (float)r_sum;
+  }
+  reinterpret_cast<int2*>(p.counts)[env] = make_int2(g_rep, g_att);
+  reinterpret_cast<unsigned*>(p.pred_prev)[env] = pack2(prev_px, prev_py);
+  reinterpret_cast<unsigned*>(p.pred_next)[env] = pack2(px, py);
+  p.step_orient[env] = (uint8_t)orient;
+  p.step_target[env] = step_target;
+  p.consumed[env] = cur;
+  if (p.track_stats) {
+    const unsigned len = p.ep_len[env] + 1u;
+    float4 ret = reinterpret_cast<float4*>(p.ep_ret)[env];
+    ret.x += (float)r_surv; ret.y += (float)r_att; ret.z += (float)r_rep; ret.w += (float)r_ali;
+    if (done) {
+      p.fin_count[env] += 1u;
+      p.fin_len[env] += len;
+      float4 f = reinterpret_cast<float4*>(p.fin_ret)[env];
+      f.x += ret.x; f.y += ret.y; f.z += ret.z; f.w += ret.w;
+      reinterpret_cast<float4*>(p.fin_ret)[env] = f;
+      p.ep_len[env] = 0u;
+      reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      p.ep_len[env] = len;
+      reinterpret_cast<float4*>(p.ep_ret)[env] = ret;
+    }
+  }
+
+  // ---- commit / auto-reset (SDE:260; reset semantics SDE:197-221) -----------------------------
+  if (done) {
+    if (p.term_x) {
+#pragma unroll
+      for (int k = 0; k < TINY_N; ++k)
+        if (k < N) { p.term_x[base + k] = (int16_t)nx[k]; p.term_y[base + k] = (int16_t)ny[k]; }
+    }
+    if (p.auto_reset) {
+      tiny_reset(p, env, nx, ny, px, py, target, err);
+      orient = 0;                                           // SDE:107
+    } else {
+      p.frozen[env] = 1;
+    }
+  }
+  if (N == TINY_N) {
+    *reinterpret_cast<uint4*>(p.x + base) =
+        make_uint4(pack2(nx[0], nx[1]), pack2(nx[2], nx[3]), pack2(nx[4], nx[5]), pack2(nx[6], nx[7]));
+    *reinterpret_cast<uint4*>(p.y + base) =
+        make_uint4(pack2(ny[0], ny[1]), pack2(ny[2], ny[3]), pack2(ny[4], ny[5]), pack2(ny[6], ny[7]));
+  } else {
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k)
+      if (k < N) { p.x[base + k] = (int16_t)nx[k]; p.y[base + k] = (int16_t)ny[k]; }
+  }
+  p.px[env] = (int16_t)px;
+  p.py[env] = (int16_t)py;
+  p.target[env] = target;
+  p.orient[env] = (uint8_t)orient;
+  if (err) p.err[env] |= err;
+}
+
+}  // namespace swarm

@@ -83,7 +83,8 @@ class BatchedSwarmEnv:
             repulsion_thresh=int(math.ceil(repulsion_thresh)), predator_eat_rew=float(predator_eat_rew),
             slab_len=self.K, place_len=self.PL, pred_attempts=self.KP, reset_slots=self.R,
             auto_reset=int(self.auto_reset), track_stats=int(self.track_stats),
-            path={"auto": _lib.PATH_AUTO, "staged": _lib.PATH_STAGED, "fused": _lib.PATH_FUSED}[path])
+            path={"auto": _lib.PATH_AUTO, "staged": _lib.PATH_STAGED, "fused": _lib.PATH_FUSED,
+                  "group": _lib.PATH_GROUP}[path])
         self._h = C.c_void_p()
         _lib.check(self.lib.swarm_create(C.byref(cfg), C.byref(self._h)))
         self.path_name = self.lib.swarm_path_name(self._h).decode()

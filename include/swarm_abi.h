@@ -51,12 +51,14 @@ extern "C" {
 /* limits */
 #define SWARM_MAX_AGENTS 16384
 #define SWARM_MAX_GRID 16384
-#define SWARM_FUSED_MAX_AGENTS 256   /* N <= this: fused warp-per-env kernel; above: staged kernels */
+#define SWARM_FUSED_MAX_AGENTS 256   /* N <= this: fused kernels (thread per env for N <= 8, lane group per env
+                                        above); larger N: staged kernels */
 
 /* swarm_config.path */
 #define SWARM_PATH_AUTO 0
 #define SWARM_PATH_STAGED 1
 #define SWARM_PATH_FUSED 2
+#define SWARM_PATH_GROUP 3   /* fused lane-group kernel even where the thread-per-env kernel (N <= 8) would be used */
 
 typedef struct swarm_config {
   int32_t abi_version;       /* SWARM_ABI_VERSION */
@@ -140,7 +142,7 @@ int swarm_bind_reset_tapes(swarm_handle h, const int16_t* place, const int16_t* 
 int swarm_reset(swarm_handle h, void* stream);
 /* SDE:223-267 for every env, plus auto-reset / statistics as configured. */
 int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* out, void* stream);
-/* Name of the kernel path swarm_step uses for this handle ("fused<LPE,APL>" or "staged"). */
+/* Name of the kernel path swarm_step uses for this handle ("tiny<8>", "fused<LPE,APL>" or "staged"). */
 const char* swarm_path_name(swarm_handle h);
 /* Number of kernel launches the last swarm_step / swarm_reset enqueued. */
 int swarm_last_launch_count(swarm_handle h);

@@ -93,6 +93,29 @@ def test_oracle_lockstep_fused_shapes(N, S):
                      KR=2000 if dense else None)
 
 
+@pytest.mark.parametrize("N,S", [(2, 4), (3, 5), (4, 20), (5, 9), (7, 6), (8, 16), (8, 5)])
+def test_oracle_lockstep_tiny_and_group_kernels(N, S):
+    """N <= 8: the thread-per-env kernel (default) and the lane-group kernel it replaces (path="group", still the
+    kernel behind vf_size steps) both reproduce the oracle; many envs so that every lane of a warp is used."""
+    dense = S * S < 4 * N
+    for path in ("auto", "group"):
+        _oracle_lockstep(E=70, N=N, S=S, T=30, seed=N * 77 + S, n_actions=9, path=path, K=512 if dense else None,
+                         KR=2000 if dense else None, weights=(0.5, 1.0, 0.25))
+    _oracle_lockstep(E=40, N=N, S=S, T=10, seed=N + S, n_actions=9, vf=2, K=512 if dense else None,
+                     KR=2000 if dense else None)
+
+
+def test_tiny_kernel_is_the_default_for_small_n():
+    from gym_swarm_b200.envs import BatchedSwarmEnv
+    for N, name in ((8, "tiny<8>"), (4, "tiny<8>"), (9, "fused<8,2>"), (16, "fused<8,2>")):
+        env = BatchedSwarmEnv(4, N, 20)
+        assert env.path_name.startswith(name), env.path_name
+        env.close()
+    env = BatchedSwarmEnv(4, 8, 20, path="group")
+    assert env.path_name.startswith("fused<8,1>")
+    env.close()
+
+
 @pytest.mark.parametrize("N,S", [(257, 64), (300, 96), (512, 512), (1000, 100), (2048, 1024)])
 def test_oracle_lockstep_staged_shapes(N, S):
     _oracle_lockstep(E=3, N=N, S=S, T=4, seed=N + S, n_actions=9)
