@@ -761,7 +761,8 @@ fused_reset_kernel(const __grid_constant__ StepParams p, const uint8_t* __restri
     p.target[env] = target;
     p.orient[env] = 0;
     p.frozen[env] = 0;
-    p.err[env] = err;
+    if (zero_counts) p.err[env] = err;
+    else if (err) p.err[env] |= err;              // masked re-reset: error bits stay sticky
     if (p.track_stats) {
       p.ep_len[env] = 0u;
       reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -465,9 +465,14 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
   if (c->tiny && !vf) {
     if (p.N == TINY_N && ((uintptr_t)in->actions & 7))
       return fail(c, SWARM_E_INVALID, "swarm_step: actions must be 8-byte aligned");
-    tiny_step_kernel<<<(p.E + TINY_THREADS - 1) / TINY_THREADS, TINY_THREADS, 0, s>>>(p);
-    CUDA_TRY(c, cudaGetLastError());
+    const int grid = (p.E + TINY_THREADS - 1) / TINY_THREADS;
+    tiny_step_kernel<<<grid, TINY_THREADS, 0, s>>>(p);
     c->launches = 1;
+    if (p.auto_reset) {
+      tiny_reset_kernel<<<grid, TINY_THREADS, 0, s>>>(p, p.done);
+      c->launches = 2;
+    }
+    CUDA_TRY(c, cudaGetLastError());
     return SWARM_OK;
   }
   if (c->fused) {

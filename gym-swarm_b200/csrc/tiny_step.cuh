@@ -12,6 +12,10 @@
 // the pair words holding agents j > i; each DPX indicator is credited to i's row counter and to the word's
 // column counter (byte-packed two-threshold counters as in the ring sweeps).
 // vf_size != None is not handled here (the host dispatches those steps to fused_step_kernel<8,1>).
+// Auto-reset is a second, masked launch (tiny_reset_kernel, thread per env, exits at once unless done): the step
+// kernel is one long straight-line instruction stream per warp, and keeping the rarely taken reset code out of
+// it is what keeps it inside the instruction cache (measured: 30 % of the stall samples were instruction
+// fetches with the reset inlined).
 #pragma once
 #include "swarm_common.cuh"
 
@@ -52,11 +56,9 @@ __device__ __forceinline__ int tiny_closest(int N, int S, int qx, int qy, const 
 }
 
 // reference reset (SDE:197-221 + SDE:90-109) of one env by one thread
-__device__ __forceinline__ void tiny_reset(const StepParams& p, int env, int (&x)[TINY_N], int (&y)[TINY_N], int& px, int& py,
-                                        int& target, unsigned& err) {
+__device__ __forceinline__ void tiny_reset(const StepParams& p, int env, unsigned rc, int (&x)[TINY_N], int (&y)[TINY_N],
+                                           int& px, int& py, int& target, unsigned& err) {
   const int N = p.N, S = p.S;
-  const unsigned rc = p.reset_count[env];
-  p.reset_count[env] = rc + 1u;
   const size_t slot = (size_t)(rc % (unsigned)p.R) * (size_t)p.E + (size_t)env;
   const int16_t* __restrict__ tape = p.place + slot * (size_t)p.PL;
 #pragma unroll
@@ -142,6 +144,10 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   int px = p.px[env], py = p.py[env];
   int target = p.target[env];
   const int retarget = p.retarget[env];
+  // everything else the step will read, issued now so that one DRAM round trip covers all of it
+  unsigned ep_len0 = 0u;
+  float4 ep_ret0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.track_stats) { ep_len0 = p.ep_len[env]; ep_ret0 = reinterpret_cast<const float4*>(p.ep_ret)[env]; }
   unsigned err = 0;
   {
     bool bad = false;
@@ -150,30 +156,24 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
     if (bad) err |= SWARM_ERR_BAD_ACTION;
   }
 
-  // ---- move + collision re-draw rounds (SDE:237-255) --------------------------------------------
-  int nx[TINY_N], ny[TINY_N];
-  int cur = 0;
+  // ---- move (SDE:237-244, 60-80) + first collision count (SDE:246, 269-292) ---------------------------
+  int nx[TINY_N], ny[TINY_N], c[TINY_N];
+  unsigned key[TINY_N];
+#pragma unroll
+  for (int k = 0; k < TINY_N; ++k) {
+    nx[k] = wrap1(x[k] + move_dx(eff[k]), S);
+    ny[k] = wrap1(y[k] + move_dy(eff[k]), S);
+    key[k] = k < N ? pack2(nx[k], ny[k]) : (0xFFFF0000u | (unsigned)k);
+  }
+  int L = tiny_counts(key, c);
+  // the first 8 re-draw actions of this env are fetched now (only by envs that collided) and consumed after the
+  // predator has been computed, so the load's latency is hidden
   const uint8_t* __restrict__ slab = p.slab + (size_t)env * (size_t)p.K;
-  for (;;) {
-    unsigned key[TINY_N];
-    int c[TINY_N];
-#pragma unroll
-    for (int k = 0; k < TINY_N; ++k) {
-      nx[k] = wrap1(x[k] + move_dx(eff[k]), S);          // SDE:60-80
-      ny[k] = wrap1(y[k] + move_dy(eff[k]), S);
-      key[k] = k < N ? pack2(nx[k], ny[k]) : (0xFFFF0000u | (unsigned)k);
-    }
-    const int L = tiny_counts(key, c);
-    if (L == 0) break;                                   // change_position_id returned None
-    if (cur + L > p.K) { err |= SWARM_ERR_SLAB_OVERFLOW; break; }
-    int off = 0;
-#pragma unroll
-    for (int k = 0; k < TINY_N; ++k) {
-      const int e = c[k] - 1;
-      if (e > 0) eff[k] = slab[cur + off + e - 1] & 7;   // SDE:250-252: last of its c-1 draws wins
-      off += e;
-    }
-    cur += L;
+  unsigned long long slab8 = 0ull;
+  const bool slab_vec = p.K >= 8 && (((uintptr_t)slab) & 7) == 0;
+  if (L > 0 && slab_vec) {
+    const uint2 v = *reinterpret_cast<const uint2*>(slab);
+    slab8 = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
   }
 
   // ---- predator (SDE:258-259, 133-165) on the OLD agent positions ------------------------------
@@ -189,6 +189,28 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
     pursue(px, py, tx, ty, S, px, py, orient);
   }
   const int step_target = target;
+
+  // ---- collision re-draw rounds (SDE:246-255) ---------------------------------------------------
+  int cur = 0;
+  while (L > 0) {
+    if (cur + L > p.K) { err |= SWARM_ERR_SLAB_OVERFLOW; break; }
+    int off = 0;
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) {
+      const int e = c[k] - 1;
+      if (e > 0) {                                        // SDE:250-252: last of its c-1 draws wins
+        const int d = cur + off + e - 1;
+        const int a = (slab_vec && d < 8) ? (int)((slab8 >> (8 * d)) & 7ull) : (int)(slab[d] & 7);
+        eff[k] = a;
+        nx[k] = wrap1(x[k] + move_dx(a), S);
+        ny[k] = wrap1(y[k] + move_dy(a), S);
+        key[k] = pack2(nx[k], ny[k]);
+      }
+      off += e;
+    }
+    cur += L;
+    L = tiny_counts(key, c);                              // change_position_id again
+  }
 
   // ---- termination (SDE:307-309, 321-327) on the NEW positions ---------------------------------
   int eaten = -1;
@@ -322,15 +344,17 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   p.step_target[env] = step_target;
   p.consumed[env] = cur;
   if (p.track_stats) {
-    const unsigned len = p.ep_len[env] + 1u;
-    float4 ret = reinterpret_cast<float4*>(p.ep_ret)[env];
+    const unsigned len = ep_len0 + 1u;
+    float4 ret = ep_ret0;
     ret.x += (float)r_surv; ret.y += (float)r_att; ret.z += (float)r_rep; ret.w += (float)r_ali;
     if (done) {
-      p.fin_count[env] += 1u;
-      p.fin_len[env] += len;
-      float4 f = reinterpret_cast<float4*>(p.fin_ret)[env];
-      f.x += ret.x; f.y += ret.y; f.z += ret.z; f.w += ret.w;
-      reinterpret_cast<float4*>(p.fin_ret)[env] = f;
+      // single writer per env: the reductions are deterministic and need no read round trip
+      atomicAdd(&p.fin_count[env], 1u);
+      atomicAdd(&p.fin_len[env], len);
+      atomicAdd(&p.fin_ret[4 * env + 0], ret.x);
+      atomicAdd(&p.fin_ret[4 * env + 1], ret.y);
+      atomicAdd(&p.fin_ret[4 * env + 2], ret.z);
+      atomicAdd(&p.fin_ret[4 * env + 3], ret.w);
       p.ep_len[env] = 0u;
       reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
@@ -346,12 +370,7 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
       for (int k = 0; k < TINY_N; ++k)
         if (k < N) { p.term_x[base + k] = (int16_t)nx[k]; p.term_y[base + k] = (int16_t)ny[k]; }
     }
-    if (p.auto_reset) {
-      tiny_reset(p, env, nx, ny, px, py, target, err);
-      orient = 0;                                           // SDE:107
-    } else {
-      p.frozen[env] = 1;
-    }
+    if (!p.auto_reset) p.frozen[env] = 1;               // auto-reset: tiny_reset_kernel follows, masked by done
   }
   if (N == TINY_N) {
     *reinterpret_cast<uint4*>(p.x + base) =
@@ -367,6 +386,28 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   p.py[env] = (int16_t)py;
   p.target[env] = target;
   p.orient[env] = (uint8_t)orient;
+  if (err) p.err[env] |= err;
+}
+
+// Masked reset of finished envs (auto-reset after tiny_step_kernel): thread per env.
+__global__ void __launch_bounds__(TINY_THREADS) tiny_reset_kernel(const __grid_constant__ StepParams p,
+                                                                   const uint8_t* __restrict__ mask) {
+  const int env = blockIdx.x * TINY_THREADS + threadIdx.x;
+  if (env >= p.E || !mask[env]) return;
+  const int N = p.N;
+  const size_t base = (size_t)env * (size_t)N;
+  const unsigned rc = p.reset_count[env];
+  p.reset_count[env] = rc + 1u;
+  int x[TINY_N], y[TINY_N], px, py, target;
+  unsigned err = 0;
+  tiny_reset(p, env, rc, x, y, px, py, target, err);
+#pragma unroll
+  for (int k = 0; k < TINY_N; ++k)
+    if (k < N) { p.x[base + k] = (int16_t)x[k]; p.y[base + k] = (int16_t)y[k]; }
+  p.px[env] = (int16_t)px;
+  p.py[env] = (int16_t)py;
+  p.target[env] = target;
+  p.orient[env] = 0;                                    // SDE:107
   if (err) p.err[env] |= err;
 }
 
