@@ -466,7 +466,8 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     if (p.N == TINY_N && ((uintptr_t)in->actions & 7))
       return fail(c, SWARM_E_INVALID, "swarm_step: actions must be 8-byte aligned");
     const int grid = (p.E + TINY_THREADS - 1) / TINY_THREADS;
-    tiny_step_kernel<<<grid, TINY_THREADS, 0, s>>>(p);
+    if (p.agent_reward || p.agent_counts) tiny_step_kernel<true><<<grid, TINY_THREADS, 0, s>>>(p);
+    else tiny_step_kernel<false><<<grid, TINY_THREADS, 0, s>>>(p);
     c->launches = 1;
     if (p.auto_reset) {
       tiny_reset_kernel<<<grid, TINY_THREADS, 0, s>>>(p, p.done);

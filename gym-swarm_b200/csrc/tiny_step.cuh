@@ -103,6 +103,9 @@ __device__ __forceinline__ void tiny_reset(const StepParams& p, int env, unsigne
   target = tiny_closest(N, S, px, py, x, y);          // SDE:109
 }
 
+// AGENT_OUT: per-agent rewards / counts are written (otherwise only the env totals are formed, from the packed
+// counters, without ever unpacking a per-agent value).
+template <bool AGENT_OUT>
 __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_constant__ StepParams p) {
   const int env = blockIdx.x * TINY_THREADS + threadIdx.x;
   if (env >= p.E) return;
@@ -261,41 +264,67 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
       }
     }
     // alignment sums (SDE:346-359), vf_size == None
-    int Ax = 0, Ay = 0, Dx = 0, Dy = 0;
+    int Ax = 0, Ay = 0, Dx = 0, Dy = 0, n_axis = 0, n_diag = 0;
 #pragma unroll
     for (int k = 0; k < TINY_N; ++k) {
       const int a = eff[k];
       if (k < N && a < 8) {
         const int mx = move_dx(a), my = move_dy(a);
-        if (a & 1) { Dx += mx; Dy += my; } else { Ax += mx; Ay += my; }
+        if (a & 1) { Dx += mx; Dy += my; ++n_diag; } else { Ax += mx; Ay += my; ++n_axis; }
       }
     }
     const int selfR = p.t_rep >= 1, selfA = p.t_att >= 1, selfRf = p.t_repf >= 1, selfAf = p.t_attf >= 1;
-    int s_P = 0, s_Q = 0;
-    float4* __restrict__ ar = p.agent_reward ? reinterpret_cast<float4*>(p.agent_reward) + base : nullptr;
-    int2* __restrict__ ac = p.agent_counts ? reinterpret_cast<int2*>(p.agent_counts) + base : nullptr;
+    int s_P, s_Q;
+    if constexpr (AGENT_OUT) {
+      s_P = 0; s_Q = 0;
+      float4* __restrict__ ar = p.agent_reward ? reinterpret_cast<float4*>(p.agent_reward) + base : nullptr;
+      int2* __restrict__ ac = p.agent_counts ? reinterpret_cast<int2*>(p.agent_counts) + base : nullptr;
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k) {
-      if (k < N) {
-        const int sh = 16 * (k & 1);
-        // counts over j != k: row (pairs met as the row agent; includes the self pair for even k) + column
-        int cR = (int)__dp4a(row[k][0], 0x00010001u, 0u) + (int)((col[k >> 1][0] >> sh) & 0xFFu);
-        int cA = (int)__dp4a(row[k][0], 0x01000100u, 0u) + (int)((col[k >> 1][0] >> (sh + 8)) & 0xFFu);
-        int cRf = (int)__dp4a(row[k][1], 0x00010001u, 0u) + (int)((col[k >> 1][1] >> sh) & 0xFFu);
-        int cAf = (int)__dp4a(row[k][1], 0x01000100u, 0u) + (int)((col[k >> 1][1] >> (sh + 8)) & 0xFFu);
-        if ((k & 1) == 0) { cR -= selfR; cA -= selfA; cRf -= selfRf; cAf -= selfAf; }
-        int P, Q;
-        align_PQ(eff[k], Ax, Ay, Dx, Dy, 1, P, Q);
-        const AgentTerms t = agent_terms(p, cR, cA, cRf, cAf, N - 1, P, Q);
-        g_rep += t.rep_i; g_att += t.att_i; s_P += P; s_Q += Q;
-        if (ar) {                                           // SDE:371-379
-          const double a_rep = p.w_rep * (double)t.rep_i * p.inv_nn;
-          const double a_att = p.w_att * (double)t.att_i * p.inv_nn;
-          const double a_ali = p.w_ali * (-t.una) * p.inv_nn;
-          ar[k] = make_float4((float)a_att, (float)a_rep, (float)a_ali, (float)(a_rep + a_att + a_ali));
+      for (int k = 0; k < TINY_N; ++k) {
+        if (k < N) {
+          const int sh = 16 * (k & 1);
+          // counts over j != k: row (pairs met as the row agent; includes the self pair for even k) + column
+          int cR = (int)__dp4a(row[k][0], 0x00010001u, 0u) + (int)((col[k >> 1][0] >> sh) & 0xFFu);
+          int cA = (int)__dp4a(row[k][0], 0x01000100u, 0u) + (int)((col[k >> 1][0] >> (sh + 8)) & 0xFFu);
+          int cRf = (int)__dp4a(row[k][1], 0x00010001u, 0u) + (int)((col[k >> 1][1] >> sh) & 0xFFu);
+          int cAf = (int)__dp4a(row[k][1], 0x01000100u, 0u) + (int)((col[k >> 1][1] >> (sh + 8)) & 0xFFu);
+          if ((k & 1) == 0) { cR -= selfR; cA -= selfA; cRf -= selfRf; cAf -= selfAf; }
+          int P, Q;
+          align_PQ(eff[k], Ax, Ay, Dx, Dy, 1, P, Q);
+          const AgentTerms t = agent_terms(p, cR, cA, cRf, cAf, N - 1, P, Q);
+          g_rep += t.rep_i; g_att += t.att_i; s_P += P; s_Q += Q;
+          if (ar) {                                           // SDE:371-379
+            const double a_rep = p.w_rep * (double)t.rep_i * p.inv_nn;
+            const double a_att = p.w_att * (double)t.att_i * p.inv_nn;
+            const double a_ali = p.w_ali * (-t.una) * p.inv_nn;
+            ar[k] = make_float4((float)a_att, (float)a_rep, (float)a_ali, (float)(a_rep + a_att + a_ali));
+          }
+          if (ac) ac[k] = make_int2(t.rep_i, t.att_i);
         }
-        if (ac) ac[k] = make_int2(t.rep_i, t.att_i);
       }
+    } else {
+      // Env totals straight from the byte-packed counters.  Per pair word w the four bytes of T are
+      // (c1, c2) of agent 2w and (c1, c2) of agent 2w+1 with (c1, c2) = (cR, cA) or (cRf, cAf):
+      //   sum cR, sum cRf: one dp4a per word; sum |c2 - c1|: VABSDIFF4.U8 of the even / odd bytes + dp4a.
+      unsigned sR = 0u, sRf = 0u, sAbsN = 0u, sAbsF = 0u;
+      const unsigned selfN = (unsigned)(selfR | (selfA << 8)), selfF = (unsigned)(selfRf | (selfAf << 8));
+#pragma unroll
+      for (int w = 0; w < TINY_N / 2; ++w) {
+        const unsigned vm = (2 * w < N ? 0x0000FFFFu : 0u) | (2 * w + 1 < N ? 0xFFFF0000u : 0u);
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          const unsigned f0 = row[2 * w][f] + (row[2 * w][f] >> 16), f1 = row[2 * w + 1][f] + (row[2 * w + 1][f] >> 16);
+          const unsigned T = (__byte_perm(f0, f1, 0x5410) + col[w][f] - (f ? selfF : selfN)) & vm;
+          const unsigned ad = __vabsdiffu4(T & 0x00FF00FFu, (T >> 8) & 0x00FF00FFu);
+          if (f == 0) { sR = __dp4a(T, 0x00010001u, sR); sAbsN = __dp4a(ad, 0x00010001u, sAbsN); }
+          else { sRf = __dp4a(T, 0x00010001u, sRf); sAbsF = __dp4a(ad, 0x00010001u, sAbsF); }
+        }
+      }
+      g_rep = -((int)sR - (int)sRf + N * ((N - 1) + p.diag_rep - 1));   // sum_i -(cR + (N-1) - cRf + diag - 1)
+      g_att = (int)sAbsN + (int)sAbsF + N * p.diag_att;                // sum_i |cA-cR| + |cRf-cAf| + diag
+      // sum_i P_i = 2 A.A - 2 n_axis + D.D - 2 n_diag,  sum_i Q_i = 2 A.D  (align_PQ summed over the agents)
+      s_P = 2 * (Ax * Ax + Ay * Ay) - 2 * n_axis + (Dx * Dx + Dy * Dy) - 2 * n_diag;
+      s_Q = 2 * (Ax * Dx + Ay * Dy);
     }
     const double g_una = 0.5 * (double)(N * (N - 1)) - 0.25 * (double)s_P - 0.35355339059327376220 * (double)s_Q;
     r_rep = p.w_rep * (double)g_rep * p.inv_nn;             // SDE:363-366
@@ -305,13 +334,13 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   } else {
     r_surv = (double)p.eat;
     r_sum = (double)p.eat;
-    if (p.agent_reward) {
+    if (AGENT_OUT && p.agent_reward) {
       float4* __restrict__ ar = reinterpret_cast<float4*>(p.agent_reward) + base;
 #pragma unroll
       for (int k = 0; k < TINY_N; ++k)
         if (k < N) ar[k] = make_float4(0.f, 0.f, 0.f, k == eaten ? p.eat : 0.f);
     }
-    if (p.agent_counts) {
+    if (AGENT_OUT && p.agent_counts) {
       int2* __restrict__ ac = reinterpret_cast<int2*>(p.agent_counts) + base;
 #pragma unroll
       for (int k = 0; k < TINY_N; ++k)

@@ -51,13 +51,14 @@ def test_golden_staged_path(name):
 
 
 def _oracle_lockstep(E, N, S, T, seed, path="auto", att=5, rep=2, eat=-10.0, vf=None, n_actions=8, K=None, KR=None,
-                     weights=(1.0, 1.0, 1.0), auto_reset=True, check_agents=True):
+                     weights=(1.0, 1.0, 1.0), auto_reset=True, check_agents=True, agent_out=True):
     from gym_swarm_b200 import tapes
     from gym_swarm_b200.envs import BatchedSwarmEnv
     from oracle import swarm_oracle as so
     rng = np.random.default_rng(seed)
     env = BatchedSwarmEnv(E, N, S, att, rep, eat, auto_reset=auto_reset, slab_len=K, place_extra=KR, reset_slots=3,
-                          per_agent=True, debug_outputs=True, path=path)
+                          per_agent=agent_out, debug_outputs=agent_out, path=path)
+    check_agents = check_agents and agent_out
     rt = tapes.make_reset_tapes(rng, env.R, E, N, S, KR=env.KR, KP=env.KP)
     st = tapes.make_step_tapes(rng, T, E, N, K=env.K, n_actions=n_actions)
     env.set_reset_tapes(rt.place, rt.ptape)
@@ -103,6 +104,10 @@ def test_oracle_lockstep_tiny_and_group_kernels(N, S):
                          KR=2000 if dense else None, weights=(0.5, 1.0, 0.25))
     _oracle_lockstep(E=40, N=N, S=S, T=10, seed=N + S, n_actions=9, vf=2, K=512 if dense else None,
                      KR=2000 if dense else None)
+    # env totals only (no per-agent outputs): the packed-counter epilogue of tiny_step_kernel<false>
+    for (att, rep) in ((5, 2), (2, 5), (0, 0), (30, 3), (10, 200)):
+        _oracle_lockstep(E=70, N=N, S=S, T=12, seed=N * 5 + S + att, n_actions=9, att=att, rep=rep, agent_out=False,
+                         K=512 if dense else None, KR=2000 if dense else None, weights=(0.5, 1.0, 0.25))
 
 
 def test_tiny_kernel_is_the_default_for_small_n():
