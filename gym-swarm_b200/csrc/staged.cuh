@@ -33,6 +33,7 @@ struct StagedScratch {
   uint2* vfw;              // [E,2*NW] (VF) packed unit-vector words
   unsigned* pcounts;       // [E,N,8] per-agent accumulators {cR,cA,cRf,cAf,cV,accA,accD,-}
   unsigned* counter;       // work counter of pairwise_sym_kernel (behind pcounts)
+  int* envacc;             // [E,12] per-env integer sums {Ax,Ay,Dx,Dy, s_rep,s_att,s_P,s_Q,s_vis,-,-,-}
   int NW;
 };
 
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(1024) collide_kernel(const StepParams p, const
   const int per = (N + blockDim.x - 1) / blockDim.x;
   const int lo = min(N, (int)threadIdx.x * per), hi = min(N, lo + per);
   for (int env = blockIdx.x; env < p.E; env += gridDim.x) {
+    if (threadIdx.x < 12) sc.envacc[(size_t)env * 12 + threadIdx.x] = 0;   // per-env sums of this step
     if (p.frozen[env]) continue;              // uniform per CTA
     const size_t base = (size_t)env * (size_t)N;
     int16_t* __restrict__ nx = sc.nx + base;
@@ -300,6 +302,7 @@ __global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p
   for (int w = threadIdx.x; w < COLL_HC; w += blockDim.x) { hkeys[w] = HASH_EMPTY; hcnt[w] = 0u; }
   __syncthreads();
   for (int env = blockIdx.x; env < p.E; env += gridDim.x) {
+    if (threadIdx.x < 12) sc.envacc[(size_t)env * 12 + threadIdx.x] = 0;   // per-env sums of this step
     if (p.frozen[env]) continue;              // uniform per CTA
     const size_t base = (size_t)env * (size_t)N;
     int16_t* __restrict__ nx = sc.nx + base;
@@ -620,6 +623,14 @@ static inline void launch_predator(const PredIO& io, int num_sms, cudaStream_t s
   }
 }
 
+// Add v of every lane to acc[env] with one atomic per distinct env in the warp (integer: order independent).
+__device__ __forceinline__ void warp_env_add(int env, bool active, int v, int* __restrict__ acc, int stride, int slot) {
+  const unsigned peers = __match_any_sync(0xFFFFFFFFu, active ? env : -1);
+  const int sum = __reduce_add_sync(peers, v);
+  const int lane = threadIdx.x & 31;
+  if (active && lane == __ffs(peers) - 1 && sum != 0) atomicAdd(acc + (size_t)env * stride + slot, sum);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4: pack positions into pair words {x2, y2, -x2, -y2} (+ VF unit-vector words) and zero the
 // per-agent accumulators.  One thread per pair word.
@@ -627,11 +638,31 @@ static inline void launch_predator(const PredIO& io, int num_sms, cudaStream_t s
 __global__ void __launch_bounds__(256) pairprep_kernel(int E, int N, int S, int NW, const int16_t* __restrict__ x,
                                                        const int16_t* __restrict__ y, const uint8_t* __restrict__ eff,
                                                        uint4* __restrict__ pairw, uint2* __restrict__ vfw,
-                                                       unsigned* __restrict__ pcounts, unsigned* __restrict__ counter) {
+                                                       unsigned* __restrict__ pcounts, unsigned* __restrict__ counter,
+                                                       int* __restrict__ envacc) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t == 0 && counter) *counter = 0u;              // work counter of pairwise_sym_kernel
-  if (t >= (long long)E * NW) return;
-  const int env = (int)(t / NW), q = (int)(t % NW);
+  const bool live = t < (long long)E * NW;
+  const int env = live ? (int)(t / NW) : 0, q = live ? (int)(t % NW) : 0;
+  if (envacc) {                                      // summed axis / diagonal move vectors of the env (SDE:346-347)
+    int ax = 0, ay = 0, dx = 0, dy = 0;
+    if (live) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = 2 * q + h;
+        const int a = j < N ? (int)eff[(size_t)env * N + j] : 8;
+        if (a < 8) {
+          const int mx = move_dx(a), my = move_dy(a);
+          if (a & 1) { dx += mx; dy += my; } else { ax += mx; ay += my; }
+        }
+      }
+    }
+    warp_env_add(env, live, ax, envacc, 12, 0);
+    warp_env_add(env, live, ay, envacc, 12, 1);
+    warp_env_add(env, live, dx, envacc, 12, 2);
+    warp_env_add(env, live, dy, envacc, 12, 3);
+  }
+  if (!live) return;
   const size_t base = (size_t)env * (size_t)N;
   const int j0 = 2 * q, j1 = 2 * q + 1;
   const int x0 = x[base + j0], y0 = y[base + j0];
@@ -1003,124 +1034,117 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 6) pairwise_sym_kernel(const Pa
 }
 
 // ------------------------------------------------------------------------------------------------
-// K6: finalize, CTA per env (grid-stride).  Reads the per-agent accumulators, the effective
-// actions and the new positions; writes rewards, outputs, statistics and commits the positions.
+// K6a: finalize, per agent (flat, one thread per agent): per-agent terms from the pairwise accumulators,
+// per-agent outputs, commit of the new positions, and the env's integer sums (one atomic per warp and env).
+// K6b: finalize, per env (one thread per env): global reward from the integer sums, outputs, statistics.
 // ------------------------------------------------------------------------------------------------
 template <bool HAS_VF>
-__global__ void __launch_bounds__(256) finalize_kernel(const StepParams p, const StagedScratch sc) {
-  __shared__ BlockScratch bs;
+__global__ void __launch_bounds__(256) finalize_agents_kernel(const StepParams p, const StagedScratch sc) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)p.E * p.N;
+  const bool live = i < total;
   const int N = p.N;
-  for (int env = blockIdx.x; env < p.E; env += gridDim.x) {
-    const size_t base = (size_t)env * (size_t)N;
-    const bool frozen = p.frozen[env] != 0;
-    const bool done = p.done[env] != 0;
-    __syncthreads();                                // flags are read by everyone before thread 0 updates them
-    if (frozen) {                                   // SDE:233-234 (flagged by K3)
-      if (threadIdx.x == 0) {
-        p.counts[2 * env] = 0; p.counts[2 * env + 1] = 0;
-        p.consumed[env] = 0;
-        for (int q = 0; q < 5; ++q) p.reward[5 * env + q] = 0.f;
-      }
-      continue;
-    }
-    const int eaten = p.eaten[env];
-    double r_surv = 0.0, r_att = 0.0, r_rep = 0.0, r_ali = 0.0, r_sum = 0.0;
-    int g_rep = 0, g_att = 0;
-    if (!done) {
-      int Ax = 0, Ay = 0, Dx = 0, Dy = 0;
-      if (!HAS_VF) {
-        int ax = 0, ay = 0, dx = 0, dy = 0;
-        for (int i = threadIdx.x; i < N; i += blockDim.x) {
-          const int a = sc.eff[base + i];
-          if (a < 8) {
-            const int mx = move_dx(a), my = move_dy(a);
-            if (a & 1) { dx += mx; dy += my; } else { ax += mx; ay += my; }
-          }
-        }
-        Ax = block_sum(ax, bs); Ay = block_sum(ay, bs); Dx = block_sum(dx, bs); Dy = block_sum(dy, bs);
-      }
-      const int selfR = p.t_rep >= 1, selfA = p.t_att >= 1, selfRf = p.t_repf >= 1, selfAf = p.t_attf >= 1;
-      const int selfV = HAS_VF ? (p.t_vf >= 1) : 1;
-      int s_rep = 0, s_att = 0, s_vis = 0;
-      long long s_P = 0, s_Q = 0;
-      for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const uint4 c0 = reinterpret_cast<const uint4*>(sc.pcounts + (base + i) * 8)[0];
-        const int a = sc.eff[base + i];
-        int vis, P, Q;
-        if (HAS_VF) {
-          const uint4 c1 = reinterpret_cast<const uint4*>(sc.pcounts + (base + i) * 8)[1];
-          const int vin = (int)c1.x;
-          vis = vin - selfV;
-          align_PQ(a, (int)(c1.y & 0xFFFFu) - vin, (int)(c1.y >> 16) - vin, (int)(c1.z & 0xFFFFu) - vin,
-                   (int)(c1.z >> 16) - vin, selfV, P, Q);
-        } else {
-          vis = N - 1;
-          align_PQ(a, Ax, Ay, Dx, Dy, 1, P, Q);
-        }
-        const AgentTerms t = agent_terms(p, (int)c0.x - selfR, (int)c0.y - selfA, (int)c0.z - selfRf,
-                                         (int)c0.w - selfAf, vis, P, Q);
-        s_rep += t.rep_i; s_att += t.att_i; s_vis += vis; s_P += P; s_Q += Q;
-        if (p.agent_reward) {
-          const double a_rep = p.w_rep * (double)t.rep_i * p.inv_nn;
-          const double a_att = p.w_att * (double)t.att_i * p.inv_nn;
-          const double a_ali = p.w_ali * (-t.una) * p.inv_nn;
-          reinterpret_cast<float4*>(p.agent_reward)[base + i] =
-              make_float4((float)a_att, (float)a_rep, (float)a_ali, (float)(a_rep + a_att + a_ali));
-        }
-        if (p.agent_counts) reinterpret_cast<int2*>(p.agent_counts)[base + i] = make_int2(t.rep_i, t.att_i);
-      }
-      // N <= 16384: |sum P|, |sum Q| <= 2 N^2 = 5.4e8 fits int32; vis sum N(N-1) = 2.7e8 fits too
-      g_rep = block_sum(s_rep, bs);
-      g_att = block_sum(s_att, bs);
-      const int g_P = block_sum((int)s_P, bs), g_Q = block_sum((int)s_Q, bs);
-      const int g_vis = HAS_VF ? block_sum(s_vis, bs) : N * (N - 1);
-      const double g_una = 0.5 * (double)g_vis - 0.25 * (double)g_P - 0.35355339059327376220 * (double)g_Q;
-      r_rep = p.w_rep * (double)g_rep * p.inv_nn;
-      r_att = p.w_att * (double)g_att * p.inv_nn;
-      r_ali = p.w_ali * (-g_una) * p.inv_nn;
-      r_sum = r_rep + r_att + r_ali;
+  const int env = live ? (int)(i / N) : 0;
+  const int k = live ? (int)(i - (long long)env * N) : 0;
+  const bool frozen = live && p.frozen[env] != 0;
+  const bool done = live && p.done[env] != 0;
+  const bool scored = live && !frozen && !done;
+  int rep_i = 0, att_i = 0, P = 0, Q = 0, vis = 0;
+  if (scored) {
+    const int* __restrict__ ea = sc.envacc + (size_t)env * 12;
+    const uint4 c0 = reinterpret_cast<const uint4*>(sc.pcounts + i * 8)[0];
+    const int a = sc.eff[i];
+    const int selfR = p.t_rep >= 1, selfA = p.t_att >= 1, selfRf = p.t_repf >= 1, selfAf = p.t_attf >= 1;
+    const int selfV = HAS_VF ? (p.t_vf >= 1) : 1;
+    if (HAS_VF) {
+      const uint4 c1 = reinterpret_cast<const uint4*>(sc.pcounts + i * 8)[1];
+      const int vin = (int)c1.x;
+      vis = vin - selfV;
+      align_PQ(a, (int)(c1.y & 0xFFFFu) - vin, (int)(c1.y >> 16) - vin, (int)(c1.z & 0xFFFFu) - vin,
+               (int)(c1.z >> 16) - vin, selfV, P, Q);
     } else {
-      r_surv = (double)p.eat;
-      r_sum = (double)p.eat;
-      for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        if (p.agent_reward)
-          reinterpret_cast<float4*>(p.agent_reward)[base + i] = make_float4(0.f, 0.f, 0.f, i == eaten ? p.eat : 0.f);
-        if (p.agent_counts) reinterpret_cast<int2*>(p.agent_counts)[base + i] = make_int2(0, 0);
-      }
+      vis = N - 1;
+      align_PQ(a, ea[0], ea[1], ea[2], ea[3], 1, P, Q);
     }
-    // commit (SDE:260) + terminal copy
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-      const int16_t vx = sc.nx[base + i], vy = sc.ny[base + i];
-      p.x[base + i] = vx;
-      p.y[base + i] = vy;
-      if (done && p.term_x) { p.term_x[base + i] = vx; p.term_y[base + i] = vy; }
-      if (p.eff_action) p.eff_action[base + i] = sc.eff[base + i];
+    const AgentTerms t = agent_terms(p, (int)c0.x - selfR, (int)c0.y - selfA, (int)c0.z - selfRf, (int)c0.w - selfAf, vis,
+                                     P, Q);
+    rep_i = t.rep_i; att_i = t.att_i;
+    if (p.agent_reward) {                                   // SDE:371-379
+      const double a_rep = p.w_rep * (double)t.rep_i * p.inv_nn;
+      const double a_att = p.w_att * (double)t.att_i * p.inv_nn;
+      const double a_ali = p.w_ali * (-t.una) * p.inv_nn;
+      reinterpret_cast<float4*>(p.agent_reward)[i] =
+          make_float4((float)a_att, (float)a_rep, (float)a_ali, (float)(a_rep + a_att + a_ali));
     }
-    if (threadIdx.x == 0) {
-      float* rw = p.reward + 5 * (size_t)env;
-      rw[0] = (float)r_surv; rw[1] = (float)r_att; rw[2] = (float)r_rep; rw[3] = (float)r_ali; rw[4] = (float)r_sum;
-      p.counts[2 * env] = g_rep;
-      p.counts[2 * env + 1] = g_att;
-      if (done && !p.auto_reset) p.frozen[env] = 1;
-      if (p.track_stats) {
-        const unsigned len = p.ep_len[env] + 1u;
-        float4 ret = reinterpret_cast<float4*>(p.ep_ret)[env];
-        ret.x += (float)r_surv; ret.y += (float)r_att; ret.z += (float)r_rep; ret.w += (float)r_ali;
-        if (done) {
-          p.fin_count[env] += 1u;
-          p.fin_len[env] += len;
-          float4 f = reinterpret_cast<float4*>(p.fin_ret)[env];
-          f.x += ret.x; f.y += ret.y; f.z += ret.z; f.w += ret.w;
-          reinterpret_cast<float4*>(p.fin_ret)[env] = f;
-          p.ep_len[env] = 0u;
-          reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          p.ep_len[env] = len;
-          reinterpret_cast<float4*>(p.ep_ret)[env] = ret;
-        }
-      }
+    if (p.agent_counts) reinterpret_cast<int2*>(p.agent_counts)[i] = make_int2(rep_i, att_i);
+  } else if (live && !frozen) {                             // terminated this step (SDE:321-327)
+    if (p.agent_reward)
+      reinterpret_cast<float4*>(p.agent_reward)[i] = make_float4(0.f, 0.f, 0.f, k == p.eaten[env] ? p.eat : 0.f);
+    if (p.agent_counts) reinterpret_cast<int2*>(p.agent_counts)[i] = make_int2(0, 0);
+  }
+  if (live && !frozen) {                                    // commit (SDE:260) + terminal copy
+    const int16_t vx = sc.nx[i], vy = sc.ny[i];
+    p.x[i] = vx;
+    p.y[i] = vy;
+    if (done && p.term_x) { p.term_x[i] = vx; p.term_y[i] = vy; }
+    if (p.eff_action) p.eff_action[i] = sc.eff[i];
+  }
+  // N <= 16384: |sum P|, |sum Q| <= 2 N^2 = 5.4e8 and sum vis <= N(N-1) = 2.7e8 fit int32
+  warp_env_add(env, scored, rep_i, sc.envacc, 12, 4);
+  warp_env_add(env, scored, att_i, sc.envacc, 12, 5);
+  warp_env_add(env, scored, P, sc.envacc, 12, 6);
+  warp_env_add(env, scored, Q, sc.envacc, 12, 7);
+  if (HAS_VF) warp_env_add(env, scored, vis, sc.envacc, 12, 8);
+}
+
+template <bool HAS_VF>
+__global__ void __launch_bounds__(128) finalize_env_kernel(const StepParams p, const StagedScratch sc) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= p.E) return;
+  const int N = p.N;
+  if (p.frozen[env]) {                                      // SDE:233-234 (flagged by K3)
+    p.counts[2 * env] = 0; p.counts[2 * env + 1] = 0;
+    p.consumed[env] = 0;
+    for (int q = 0; q < 5; ++q) p.reward[5 * env + q] = 0.f;
+    return;
+  }
+  const bool done = p.done[env] != 0;
+  double r_surv = 0.0, r_att = 0.0, r_rep = 0.0, r_ali = 0.0, r_sum = 0.0;
+  int g_rep = 0, g_att = 0;
+  if (!done) {
+    const int* __restrict__ ea = sc.envacc + (size_t)env * 12;
+    g_rep = ea[4]; g_att = ea[5];
+    const int g_vis = HAS_VF ? ea[8] : N * (N - 1);
+    const double g_una = 0.5 * (double)g_vis - 0.25 * (double)ea[6] - 0.35355339059327376220 * (double)ea[7];
+    r_rep = p.w_rep * (double)g_rep * p.inv_nn;             // SDE:363-366
+    r_att = p.w_att * (double)g_att * p.inv_nn;
+    r_ali = p.w_ali * (-g_una) * p.inv_nn;
+    r_sum = r_rep + r_att + r_ali;
+  } else {
+    r_surv = (double)p.eat;
+    r_sum = (double)p.eat;
+  }
+  float* rw = p.reward + 5 * (size_t)env;
+  rw[0] = (float)r_surv; rw[1] = (float)r_att; rw[2] = (float)r_rep; rw[3] = (float)r_ali; rw[4] = (float)r_sum;
+  p.counts[2 * env] = g_rep;
+  p.counts[2 * env + 1] = g_att;
+  if (done && !p.auto_reset) p.frozen[env] = 1;
+  if (p.track_stats) {
+    const unsigned len = p.ep_len[env] + 1u;
+    float4 ret = reinterpret_cast<float4*>(p.ep_ret)[env];
+    ret.x += (float)r_surv; ret.y += (float)r_att; ret.z += (float)r_rep; ret.w += (float)r_ali;
+    if (done) {
+      p.fin_count[env] += 1u;
+      p.fin_len[env] += len;
+      float4 f = reinterpret_cast<float4*>(p.fin_ret)[env];
+      f.x += ret.x; f.y += ret.y; f.z += ret.z; f.w += ret.w;
+      reinterpret_cast<float4*>(p.fin_ret)[env] = f;
+      p.ep_len[env] = 0u;
+      reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      p.ep_len[env] = len;
+      reinterpret_cast<float4*>(p.ep_ret)[env] = ret;
     }
-    __syncthreads();
   }
 }
 

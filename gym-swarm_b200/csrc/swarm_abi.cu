@@ -183,12 +183,14 @@ static int staged_alloc(Ctx* c) {
   const size_t o_pairw = take((size_t)E * sc.NW * 16), o_vfw = take((size_t)E * sc.NW * 16);
   const size_t o_pc = take((size_t)E * N * 32 + 64);
   const size_t o_cnt = take(256);
+  const size_t o_ea = take((size_t)E * 12 * 4);
   CUDA_TRY(c, cudaMalloc(&c->scratch_block, off));
   char* b = (char*)c->scratch_block;
   sc.nx = (int16_t*)(b + o_nx); sc.ny = (int16_t*)(b + o_ny); sc.eff = (uint8_t*)(b + o_eff);
   sc.hash = (unsigned*)(b + o_hash); sc.aslot = (unsigned*)(b + o_aslot);
   sc.pairw = (uint4*)(b + o_pairw); sc.vfw = (uint2*)(b + o_vfw); sc.pcounts = (unsigned*)(b + o_pc);
   sc.counter = (unsigned*)(b + o_cnt);
+  sc.envacc = (int*)(b + o_ea);
   CUDA_TRY(c, cudaMemset(b + o_hash, 0xFF, (size_t)sc.env_grid * hs * 4 * 2));   // keys = EMPTY ...
   // ... and counts = 0: keys and counts are interleaved per CTA ({keys[HS], cnt[HS]}), fix the counts
   for (int g = 0; g < sc.env_grid; ++g)
@@ -506,15 +508,18 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
   {
     const long long words = (long long)p.E * sc.NW;
     pairprep_kernel<<<(int)((words + 255) / 256), 256, 0, s>>>(p.E, p.N, p.S, sc.NW, sc.nx, sc.ny, sc.eff, sc.pairw,
-                                                              vf ? sc.vfw : nullptr, sc.pcounts, sc.counter);
+                                                              vf ? sc.vfw : nullptr, sc.pcounts, sc.counter, sc.envacc);
   }
   pairwise_launch(p, sc, sc.nx, sc.ny, p.done, vf, c->num_sms, s);
-  if (vf) finalize_kernel<true><<<sc.env_grid, 256, 0, s>>>(p, sc);
-  else finalize_kernel<false><<<sc.env_grid, 256, 0, s>>>(p, sc);
-  c->launches = 6;
+  {
+    const int ga = (int)((total + 255) / 256), ge = (p.E + 127) / 128;
+    if (vf) { finalize_agents_kernel<true><<<ga, 256, 0, s>>>(p, sc); finalize_env_kernel<true><<<ge, 128, 0, s>>>(p, sc); }
+    else { finalize_agents_kernel<false><<<ga, 256, 0, s>>>(p, sc); finalize_env_kernel<false><<<ge, 128, 0, s>>>(p, sc); }
+  }
+  c->launches = 7;
   if (p.auto_reset) {
     reset_kernel<<<sc.env_grid, c->per_env_threads, 0, s>>>(p, sc, p.done, 1);
-    c->launches = 7;
+    c->launches = 8;
   }
   CUDA_TRY(c, cudaGetLastError());
   return SWARM_OK;
@@ -580,7 +585,7 @@ int swarm_pairwise(int32_t E, int32_t N, int32_t S, int32_t attraction_thresh, i
   sc.counter = (unsigned*)((char*)block + b_pairw + b_pc);
   const long long words = (long long)E * sc.NW;
   pairprep_kernel<<<(int)((words + 255) / 256), 256, 0, s>>>(E, N, S, sc.NW, x, y, nullptr, sc.pairw, nullptr,
-                                                            sc.pcounts, sc.counter);
+                                                            sc.pcounts, sc.counter, nullptr);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
