@@ -211,7 +211,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--path", default="auto", choices=["auto", "fused", "group", "staged"])
+    ap.add_argument("--path", default="auto", choices=["auto", "fused", "group", "staged", "staged_pairwise"])
     ap.add_argument("--vf", type=int, default=None, help="reward_type['vf_size'] (default None)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(_HERE, "libswarm_b20
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "swarm_abi.h")
 
 ABI_VERSION = 1
-PATH_AUTO, PATH_STAGED, PATH_FUSED, PATH_GROUP = 0, 1, 2, 3
+PATH_AUTO, PATH_STAGED, PATH_FUSED, PATH_GROUP, PATH_STAGED_PAIRWISE = 0, 1, 2, 3, 4
 
 ERR_SLAB_OVERFLOW = 1
 ERR_PLACE_OVERFLOW = 2

@@ -25,6 +25,7 @@ struct Ctx {
   std::string path_name;
   bool fused = false;
   bool tiny = false;          // N <= 8: thread-per-env kernel (steps without a visual-field gate)
+  bool force_pairwise = false;  // SWARM_PATH_STAGED_PAIRWISE: never use the box-count reward path
   int lpe = 0, apl = 0;
   int bitmap_words = 0;
   int launches = 0;
@@ -35,6 +36,7 @@ struct Ctx {
   int per_env_threads = 256;
   int coll_bm_words = 0;      // > 0: collide_bitmap_kernel (per-env occupancy bitmap fits in shared memory)
   int coll_smem_bytes = 0;
+  BoxPlan box{};              // sub-quadratic reward counts inside collide_bitmap_kernel (steps without vf_size)
   // stats
   double* d_stats = nullptr;
   // nccl
@@ -172,7 +174,36 @@ static int staged_alloc(Ctx* c) {
     if (bytes + 1024 <= dev_max && (N + threads - 1) / threads <= 16) {
       c->coll_bm_words = (int)words;
       c->coll_smem_bytes = (int)bytes;
-      CUDA_TRY(c, cudaFuncSetAttribute(collide_bitmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      // box-count plan: per threshold the cheaper of the direct box and the complement; enabled only when the
+      // whole plan costs far less per agent than the pairwise sweep (N pair evaluations)
+      StepParams tp;
+      memset(&tp, 0, sizeof(tp));
+      fill_thresholds(tp, N, c->cfg.grid_size, c->cfg.attraction_thresh, c->cfg.repulsion_thresh);
+      const int S = c->cfg.grid_size;
+      const int ts[4] = {tp.t_rep, tp.t_att, tp.t_repf, tp.t_attf};
+      double cost = 0.0;
+      BoxPlan bp{};
+      for (int q = 0; q < 4; ++q) {
+        const int t = ts[q];
+        bp.t[q] = t;
+        if (t <= 0) bp.mode[q] = BOX_ZERO;
+        else if (t >= S) bp.mode[q] = BOX_ALL;
+        else {
+          const double side = 2.0 * t - 1.0, direct = side * (side / 32.0 + 2.0);
+          const double b = (double)(S - t), comp = 8.0 + 4.0 * b * (b / 32.0 + 2.0);
+          if (direct <= comp) { bp.mode[q] = BOX_DIRECT; cost += direct; }
+          else { bp.mode[q] = BOX_COMPLEMENT; bp.need_hist = 1; cost += comp; }
+        }
+      }
+      const long long hist_bytes = bp.need_hist ? 2LL * S * 4 : 0;
+      // (a box word-op is ~5 instructions, the symmetric pair sweep ~1.5 ALU instructions per agent pair)
+      if (cost * 3.0 < (double)N && bytes + hist_bytes + 1024 <= dev_max) {
+        bp.enabled = 1;
+        c->coll_smem_bytes = (int)(bytes + hist_bytes);
+      }
+      c->box = bp;
+      CUDA_TRY(c, cudaFuncSetAttribute(collide_bitmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       c->coll_smem_bytes));
     }
   }
   const size_t hs = (size_t)1 << log2hs;
@@ -336,6 +367,7 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
   cudaDeviceProp prop;
   CUDA_TRY(c, cudaGetDeviceProperties(&prop, cfg->device));
   c->num_sms = prop.multiProcessorCount;
+  c->force_pairwise = cfg->path == SWARM_PATH_STAGED_PAIRWISE;
   c->fused = cfg->path == SWARM_PATH_FUSED || cfg->path == SWARM_PATH_GROUP ||
              (cfg->path == SWARM_PATH_AUTO && cfg->num_agents <= SWARM_FUSED_MAX_AGENTS);
   c->tiny = c->fused && cfg->path != SWARM_PATH_GROUP && cfg->num_agents <= TINY_N;
@@ -349,12 +381,14 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
     else snprintf(buf, sizeof(buf), "fused<%d,%d>%s", c->lpe, c->apl, c->bitmap_words ? "+bitmap" : "");
     c->path_name = buf;
   } else {
-    c->path_name = "staged";
+    c->path_name = "staged";   // refined after staged_alloc (box-count plan)
   }
   // the staged scratch also backs swarm_autoreset / masks on the fused path only when needed
   if (!c->fused) {
     int rc = staged_alloc(c);
     if (rc != SWARM_OK) { std::string m = c->err; delete c; return fail(nullptr, rc, m); }
+    if (c->coll_bm_words > 0 && c->box.enabled && !c->force_pairwise) c->path_name = "staged+box (vf: staged pairwise)";
+    else if (c->coll_bm_words > 0) c->path_name = "staged+bitmap";
   }
   cudaError_t e = cudaMalloc(&c->d_stats, 8 * sizeof(double));
   if (e != cudaSuccess) { delete c; return fail(nullptr, SWARM_E_CUDA, "cudaMalloc stats"); }
@@ -493,10 +527,14 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     const int grid = (int)std::min<long long>((nvec + 255) / 256, (long long)c->num_sms * 16);
     move_kernel<<<grid, 256, 0, s>>>(total, p.N, p.S, p.x, p.y, p.actions, sc.nx, sc.ny, sc.eff, p.err);
   }
-  if (c->coll_bm_words > 0)
-    collide_bitmap_kernel<<<sc.env_grid, c->per_env_threads, c->coll_smem_bytes, s>>>(p, sc, c->coll_bm_words);
-  else
+  const bool box = c->coll_bm_words > 0 && c->box.enabled && !vf && !c->force_pairwise;
+  if (c->coll_bm_words > 0) {
+    BoxPlan bp = c->box;
+    bp.enabled = box ? 1 : 0;
+    collide_bitmap_kernel<<<sc.env_grid, c->per_env_threads, c->coll_smem_bytes, s>>>(p, sc, c->coll_bm_words, bp);
+  } else {
     collide_kernel<<<sc.env_grid, c->per_env_threads, 0, s>>>(p, sc);
+  }
   {
     PredIO io;
     io.E = p.E; io.N = p.N; io.S = p.S; io.xo = p.x; io.yo = p.y; io.xn = sc.nx; io.yn = sc.ny;
@@ -505,21 +543,22 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     io.step_target = p.step_target; io.done = p.done; io.eaten = p.eaten; io.err = p.err;
     launch_predator(io, c->num_sms, s);
   }
-  {
+  c->launches = 5;
+  if (!box) {                                  // tiled pairwise kernels compute the threshold counts
     const long long words = (long long)p.E * sc.NW;
     pairprep_kernel<<<(int)((words + 255) / 256), 256, 0, s>>>(p.E, p.N, p.S, sc.NW, sc.nx, sc.ny, sc.eff, sc.pairw,
                                                               vf ? sc.vfw : nullptr, sc.pcounts, sc.counter, sc.envacc);
+    pairwise_launch(p, sc, sc.nx, sc.ny, p.done, vf, c->num_sms, s);
+    c->launches = 7;
   }
-  pairwise_launch(p, sc, sc.nx, sc.ny, p.done, vf, c->num_sms, s);
   {
     const int ga = (int)((total + 255) / 256), ge = (p.E + 127) / 128;
     if (vf) { finalize_agents_kernel<true><<<ga, 256, 0, s>>>(p, sc); finalize_env_kernel<true><<<ge, 128, 0, s>>>(p, sc); }
     else { finalize_agents_kernel<false><<<ga, 256, 0, s>>>(p, sc); finalize_env_kernel<false><<<ge, 128, 0, s>>>(p, sc); }
   }
-  c->launches = 7;
   if (p.auto_reset) {
     reset_kernel<<<sc.env_grid, c->per_env_threads, 0, s>>>(p, sc, p.done, 1);
-    c->launches = 8;
+    c->launches += 1;
   }
   CUDA_TRY(c, cudaGetLastError());
   return SWARM_OK;

@@ -84,7 +84,7 @@ class BatchedSwarmEnv:
             slab_len=self.K, place_len=self.PL, pred_attempts=self.KP, reset_slots=self.R,
             auto_reset=int(self.auto_reset), track_stats=int(self.track_stats),
             path={"auto": _lib.PATH_AUTO, "staged": _lib.PATH_STAGED, "fused": _lib.PATH_FUSED,
-                  "group": _lib.PATH_GROUP}[path])
+                  "group": _lib.PATH_GROUP, "staged_pairwise": _lib.PATH_STAGED_PAIRWISE}[path])
         self._h = C.c_void_p()
         _lib.check(self.lib.swarm_create(C.byref(cfg), C.byref(self._h)))
         self.path_name = self.lib.swarm_path_name(self._h).decode()

@@ -58,6 +58,8 @@ extern "C" {
 #define SWARM_PATH_AUTO 0
 #define SWARM_PATH_STAGED 1
 #define SWARM_PATH_FUSED 2
+#define SWARM_PATH_STAGED_PAIRWISE 4 /* staged kernels, reward counts always by the tiled pairwise kernel (never the
+                                       box-count path) */
 #define SWARM_PATH_GROUP 3   /* fused lane-group kernel even where the thread-per-env kernel (N <= 8) would be used */
 
 typedef struct swarm_config {

@@ -123,7 +123,27 @@ def test_tiny_kernel_is_the_default_for_small_n():
 
 @pytest.mark.parametrize("N,S", [(257, 64), (300, 96), (512, 512), (1000, 100), (2048, 1024)])
 def test_oracle_lockstep_staged_shapes(N, S):
+    """Large-N path, reward counts by the box-count kernel (default) and by the tiled pairwise kernels."""
     _oracle_lockstep(E=3, N=N, S=S, T=4, seed=N + S, n_actions=9)
+    _oracle_lockstep(E=3, N=N, S=S, T=3, seed=N + S + 1, n_actions=9, path="staged_pairwise")
+
+
+@pytest.mark.parametrize("att,rep", [(5, 2), (2, 5), (0, 0), (1, 1), (9, 3), (3, 12), (10, 200), (70, 3), (200, 200),
+                                     (64, 65), (5, 60)])
+def test_box_count_path_thresholds(att, rep):
+    """Every method of the box-count plan (zero / all / direct box / complement with histograms and corner boxes)
+    against the oracle, on a grid small enough that border bands and corners are populated; thresholds the plan
+    rejects fall back to the pairwise kernels inside the same handle."""
+    _oracle_lockstep(E=3, N=700, S=64, T=3, seed=att * 31 + rep, n_actions=9, att=att, rep=rep, weights=(0.5, 1.0, 0.25))
+    _oracle_lockstep(E=2, N=1500, S=50, T=2, seed=att + rep, n_actions=9, att=att, rep=rep, K=4096, KR=6000)
+
+
+def test_staged_path_names():
+    from gym_swarm_b200.envs import BatchedSwarmEnv
+    for kw, name in ((dict(path="auto"), "staged+box"), (dict(path="staged_pairwise"), "staged+bitmap")):
+        env = BatchedSwarmEnv(2, 1024, 256, **kw)
+        assert env.path_name.startswith(name), env.path_name
+        env.close()
 
 
 def test_oracle_lockstep_large_n16384():

@@ -1,0 +1,7 @@
+# Summarise what tools/gpu_final_profiles.sh brought back into tracked files under profiles/.
+R=${1:-r01}
+for f in gpurun_out/${R}_bench_*.json gpurun_out/${R}_kernel_roofline.jsonl; do [ -s "$f" ] && cp "$f" profiles/; done
+for c in cfg3 cfg4 cfg5; do [ -s gpurun_out/${R}_${c}_launches.csv ] && cp gpurun_out/${R}_${c}_launches.csv profiles/ && python tools/ncu_summary.py launches gpurun_out/${R}_${c}_launches.csv > profiles/${R}_${c}_launches.txt; done
+for n in cfg3_fused cfg5_tiny cfg4_staged move predator_n128 predator_n16384; do [ -s gpurun_out/${R}_$n.ncu-rep ] && python tools/ncu_summary.py full gpurun_out/${R}_$n.ncu-rep > profiles/${R}_${n}_full.txt; done
+[ -s gpurun_out/${R}_cfg3_fused.ncu-rep ] && python tools/ncu_regions.py gpurun_out/${R}_cfg3_fused.ncu-rep > profiles/${R}_cfg3_fused_regions.txt
+ls -la profiles
