@@ -180,9 +180,22 @@ __device__ __forceinline__ void occupancy_counts(const Seg<LPE>& g, unsigned* sk
 //     c_i = 1 + #{hit agents standing on agent i's cell}.
 // The (few) hit agents broadcast their cell one after the other and everybody compares: O(hits * APL) per lane
 // instead of the O(N * APL) all-pairs sweep.  Returns false (c untouched) when no cell is shared.
+// keep_clean: when no cell is shared, leave the bits set (the caller runs the box-count reward on the bitmap and
+// clears it afterwards with bitmap_clear).
+template <int LPE, int APL>
+__device__ __forceinline__ void bitmap_clear(const Seg<LPE>& g, unsigned* sbit, int N, int S, int i0,
+                                             const int (&cx)[APL], const int (&cy)[APL]) {
+  g.sync();
+#pragma unroll
+  for (int k = 0; k < APL; ++k)
+    if (i0 + k < N) sbit[(cy[k] * S + cx[k]) >> 5] = 0u;
+  g.sync();
+}
+
 template <int LPE, int APL>
 __device__ __forceinline__ bool bitmap_counts(const Seg<LPE>& g, unsigned* sbit, int N, int S, int i0,
-                                              const int (&cx)[APL], const int (&cy)[APL], int (&c)[APL]) {
+                                              const int (&cx)[APL], const int (&cy)[APL], int (&c)[APL],
+                                              bool keep_clean) {
   unsigned pending = 0u;
   int word[APL];
 #pragma unroll
@@ -198,6 +211,7 @@ __device__ __forceinline__ bool bitmap_counts(const Seg<LPE>& g, unsigned* sbit,
   }
   const bool any = g.any(pending != 0u);   // ballot also orders the atomics before the clears below
   g.sync();
+  if (!any && keep_clean) return false;    // bitmap = exact occupancy of the final positions, left in place
 #pragma unroll
   for (int k = 0; k < APL; ++k)
     if (word[k] >= 0) sbit[word[k]] = 0u;
@@ -323,13 +337,15 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
   const int N = p.N, S = p.S;
 
   // smem carve-up (per warp, then per env group)
-  const int warp_bytes = C::pair_bytes() + (HAS_VF ? C::vf_bytes() : 0) + C::EPW * p.bitmap_words * 4;
+  const int hist_words = (p.box.enabled && p.box.need_hist) ? 2 * S : 0;   // per-env column / row histograms
+  const int warp_bytes = C::pair_bytes() + (HAS_VF ? C::vf_bytes() : 0) + C::EPW * (p.bitmap_words + hist_words) * 4;
   unsigned char* wbase = smem_raw + (size_t)warp * warp_bytes;
   uint4* spw = reinterpret_cast<uint4*>(wbase) + g.seg * C::PW;
   unsigned* skey = reinterpret_cast<unsigned*>(spw);   // aliases the pair words (NMAX words <= PW*4 words)
   uint2* svf = reinterpret_cast<uint2*>(wbase + C::pair_bytes()) + g.seg * C::NMAX;
   unsigned* sbit = reinterpret_cast<unsigned*>(wbase + C::pair_bytes() + (HAS_VF ? C::vf_bytes() : 0)) +
-                   g.seg * p.bitmap_words;
+                   g.seg * (p.bitmap_words + hist_words);
+  int* shist = reinterpret_cast<int*>(sbit + p.bitmap_words);
   if (p.bitmap_words) {
     for (int w = g.li; w < p.bitmap_words; w += LPE) sbit[w] = 0u;
   }
@@ -372,6 +388,8 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
   }
   int cur = 0;
   const uint8_t* __restrict__ slab = p.slab + (size_t)env * (size_t)p.K;
+  const bool use_box = !HAS_VF && p.box.enabled && p.bitmap_words > 0;
+  bool bits_live = false;        // the bitmap holds the final (collision free) positions: box-count reward
   for (;;) {
 #pragma unroll
     for (int k = 0; k < APL; ++k) {
@@ -380,7 +398,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
     }
     int c[APL];
     if (p.bitmap_words) {
-      if (!bitmap_counts<LPE, APL>(g, sbit, N, S, i0, nx, ny, c)) break;
+      if (!bitmap_counts<LPE, APL>(g, sbit, N, S, i0, nx, ny, c, use_box)) { bits_live = use_box; break; }
     } else {
       occupancy_counts<LPE, APL>(g, skey, N, i0, nx, ny, c);
     }
@@ -429,157 +447,193 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
   double r_surv = 0.0, r_att = 0.0, r_rep = 0.0, r_ali = 0.0, r_sum = 0.0;
   int g_rep = 0, g_att = 0;
   if (!done) {
-    // stage the env's positions as packed pair words {x2, y2, -x2, -y2}; padding agents sit at x=-S
-    int sx[APL], sy[APL];
-#pragma unroll
-    for (int k = 0; k < APL; ++k) {
-      const bool v = i0 + k < N;
-      sx[k] = v ? nx[k] : -S;
-      sy[k] = v ? ny[k] : 0;
-    }
-    if constexpr (APL == 1) {
-      const unsigned mine = pack2(sx[0], sy[0]);
-      const unsigned oth = __shfl_xor_sync(g.mask, mine, 1, LPE);
-      if ((g.li & 1) == 0) {
-        const int ox = (int)(int16_t)(oth & 0xFFFFu), oy = (int)(int16_t)(oth >> 16);
-        spw[g.li >> 1] = make_uint4(pack2(sx[0], ox), pack2(sy[0], oy), pack2(-sx[0], -ox), pack2(-sy[0], -oy));
-      }
-    } else {
-      // ring sweep: word w of every lane contiguous ([w][lane]) so that the rotated LDS.128 is conflict free
-      constexpr bool RING = !HAS_VF && (APL == 2 || APL == 4) && LPE >= 4;
-#pragma unroll
-      for (int k = 0; k < APL; k += 2)
-        spw[RING ? (k >> 1) * LPE + g.li : (i0 + k) >> 1] =
-            make_uint4(pack2(sx[k], sx[k + 1]), pack2(sy[k], sy[k + 1]), pack2(-sx[k], -sx[k + 1]),
-                       pack2(-sy[k], -sy[k + 1]));
-    }
-    if constexpr (HAS_VF) {
-#pragma unroll
-      for (int k = 0; k < APL; ++k) {
-        const int a = eff[k];
-        const bool mover = (i0 + k < N) && a < 8;
-        const int mx = mover ? move_dx(a) : 0, my = mover ? move_dy(a) : 0;
-        const bool diag = (a & 1) != 0;
-        svf[i0 + k] = make_uint2(pack2((diag ? 0 : mx) + 1, (diag ? 0 : my) + 1),
-                                 pack2((diag ? mx : 0) + 1, (diag ? my : 0) + 1));
-      }
-    }
-    g.sync();
-
-    unsigned XI[APL], YI[APL], NXI[APL], NYI[APL];
-    unsigned aR[APL], aA[APL], aRf[APL], aAf[APL];
+    unsigned aR[APL], aA[APL], aRf[APL], aAf[APL];       // threshold counts of each owned agent, self included
     unsigned aV[APL], accA[APL], accD[APL];
 #pragma unroll
-    for (int k = 0; k < APL; ++k) {
-      XI[k] = rep2(sx[k]); YI[k] = rep2(sy[k]); NXI[k] = rep2(-sx[k]); NYI[k] = rep2(-sy[k]);
-      aR[k] = aA[k] = aRf[k] = aAf[k] = 0u;
-      aV[k] = accA[k] = accD[k] = 0u;
-    }
-    const unsigned TR = rep2(p.t_rep), TA = rep2(p.t_att), TRf = rep2(p.t_repf), TAf = rep2(p.t_attf);
-    const unsigned TV = rep2(HAS_VF ? p.t_vf : 0);
-    if constexpr (!HAS_VF && (APL == 2 || APL == 4) && LPE >= 4) {
-      // ---- symmetric ring sweep: every unordered block pair is evaluated once --------------------
-      // Lane l owns block B_l (APL agents = W pair words).  In round r it meets the block of lane l+r (pair words
-      // read from smem), adds each indicator to its own ROW counters and to the visiting block's COLUMN counters;
-      // the column counters travel round the ring by shuffles together with the block they belong to and are
-      // sent home after the last symmetric round.  Rounds 0 (own block) and LPE/2 (met from both sides) only
-      // count rows.  The accumulations are IMADs by a runtime 1 so that they issue on the FMA pipe and leave the
-      // ALU pipe to the DPX ops.
-      constexpr int W = APL / 2;
-      constexpr int HALF = LPE / 2;
-      const unsigned one = (unsigned)p.one, c256 = (unsigned)p.one << 8;
-      // Counters are BYTE packed: a 16x2 indicator word holds 0/1 in bytes 0 and 2, so ind(t0) + 256 * ind(t1)
-      // carries two thresholds for two agents in one register ({t0,t1} = {rep,att} and {rep_far,att_far}); it is
-      // built once (IMAD) and added to the row and to the column counter.  No byte can overflow: a row byte
-      // meets at most NMAX / 2 <= 64 pair words, a column byte at most (LPE / 2 - 1) * APL <= 60 rows.
-      unsigned row[APL][2], col[W][2];
+    for (int k = 0; k < APL; ++k) aR[k] = aA[k] = aRf[k] = aAf[k] = aV[k] = accA[k] = accD[k] = 0u;
+    if (bits_live) {
+      // ---- box counts on the env's occupancy bitmap (see swarm_common.cuh) ----------
+      int* hx = shist;
+      int* hy = shist + S;
+      if (p.box.need_hist) {
+        for (int a = g.li; a < 2 * S; a += LPE) shist[a] = 0;
+        g.sync();
 #pragma unroll
-      for (int k = 0; k < APL; ++k) row[k][0] = row[k][1] = 0u;
+        for (int k = 0; k < APL; ++k)
+          if (i0 + k < N) { atomicAdd(&hx[nx[k]], 1); atomicAdd(&hy[ny[k]], 1); }
+        g.sync();
+        const int hper = (S + LPE - 1) / LPE;
+        const int h0 = min(S, g.li * hper), h1 = min(S, h0 + hper);
 #pragma unroll
-      for (int w = 0; w < W; ++w) col[w][0] = col[w][1] = 0u;
-      auto rows_only = [&](int src) {
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-          const uint4 vw = spw[w * LPE + src];
-#pragma unroll
-          for (int k = 0; k < APL; ++k) {
-            const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
-            row[k][0] = lt2(TR, m) * one + row[k][0];
-            row[k][0] = lt2(TA, m) * c256 + row[k][0];
-            row[k][1] = lt2(TRf, m) * one + row[k][1];
-            row[k][1] = lt2(TAf, m) * c256 + row[k][1];
-          }
+        for (int q = 0; q < 2; ++q) {
+          int* h = q ? hy : hx;
+          int run = 0;
+          for (int a = h0; a < h1; ++a) run += h[a];
+          int tot;
+          int carry = g.excl_scan(run, tot);
+          for (int a = h0; a < h1; ++a) { carry += h[a]; h[a] = carry; }
         }
-      };
-      rows_only(g.li);                                       // round 0: own block
-      const int nxt = (g.li + 1) & (LPE - 1);
-#pragma unroll 1
-      for (int r = 1; r < HALF; ++r) {
-        const int src = (g.li + r) & (LPE - 1);
-        if (r > 1) {
-#pragma unroll
-          for (int w = 0; w < W; ++w) {
-            col[w][0] = __shfl_sync(g.mask, col[w][0], nxt, LPE);
-            col[w][1] = __shfl_sync(g.mask, col[w][1], nxt, LPE);
-          }
-        }
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-          const uint4 vw = spw[w * LPE + src];
-#pragma unroll
-          for (int k = 0; k < APL; ++k) {
-            const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
-            const unsigned n0 = lt2(TA, m) * c256 + lt2(TR, m);
-            const unsigned n1 = lt2(TAf, m) * c256 + lt2(TRf, m);
-            row[k][0] = n0 * one + row[k][0];
-            row[k][1] = n1 * one + row[k][1];
-            col[w][0] = n0 * one + col[w][0];
-            col[w][1] = n1 * one + col[w][1];
-          }
-        }
+        g.sync();
       }
-      // send the column counters home: lane l holds those of block l + HALF - 1
-      if constexpr (HALF > 1) {
-        const int from = (g.li - (HALF - 1)) & (LPE - 1);
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-          col[w][0] = __shfl_sync(g.mask, col[w][0], from, LPE);
-          col[w][1] = __shfl_sync(g.mask, col[w][1], from, LPE);
-        }
-      }
-      rows_only((g.li + HALF) & (LPE - 1));                  // round LPE/2: met from both sides
-      // fold: total = both agents' bytes of the row counter + this agent's bytes of the column counter
 #pragma unroll
       for (int k = 0; k < APL; ++k) {
-        const int sh = 16 * (k & 1);
-        aR[k] = __dp4a(row[k][0], 0x00010001u, 0u) + ((col[k >> 1][0] >> sh) & 0xFFu);
-        aA[k] = __dp4a(row[k][0], 0x01000100u, 0u) + ((col[k >> 1][0] >> (sh + 8)) & 0xFFu);
-        aRf[k] = __dp4a(row[k][1], 0x00010001u, 0u) + ((col[k >> 1][1] >> sh) & 0xFFu);
-        aAf[k] = __dp4a(row[k][1], 0x01000100u, 0u) + ((col[k >> 1][1] >> (sh + 8)) & 0xFFu);
+        if (i0 + k < N) {
+          aR[k] = (unsigned)box_count(p.box, 0, sbit, hx, hy, nx[k], ny[k], S, N);
+          aA[k] = (unsigned)box_count(p.box, 1, sbit, hx, hy, nx[k], ny[k], S, N);
+          aRf[k] = (unsigned)box_count(p.box, 2, sbit, hx, hy, nx[k], ny[k], S, N);
+          aAf[k] = (unsigned)box_count(p.box, 3, sbit, hx, hy, nx[k], ny[k], S, N);
+        }
       }
     } else {
-      const int NW = (N + 1) >> 1;
-#pragma unroll 2
-      for (int q = 0; q < NW; ++q) {
-        const uint4 w = spw[q];
-        uint4 u = make_uint4(0, 0, 0, 0);
-        if constexpr (HAS_VF) u = *reinterpret_cast<const uint4*>(&svf[2 * q]);
-#pragma unroll
+      // stage the env's positions as packed pair words {x2, y2, -x2, -y2}; padding agents sit at x=-S
+      int sx[APL], sy[APL];
+  #pragma unroll
+      for (int k = 0; k < APL; ++k) {
+        const bool v = i0 + k < N;
+        sx[k] = v ? nx[k] : -S;
+        sy[k] = v ? ny[k] : 0;
+      }
+      if constexpr (APL == 1) {
+        const unsigned mine = pack2(sx[0], sy[0]);
+        const unsigned oth = __shfl_xor_sync(g.mask, mine, 1, LPE);
+        if ((g.li & 1) == 0) {
+          const int ox = (int)(int16_t)(oth & 0xFFFFu), oy = (int)(int16_t)(oth >> 16);
+          spw[g.li >> 1] = make_uint4(pack2(sx[0], ox), pack2(sy[0], oy), pack2(-sx[0], -ox), pack2(-sy[0], -oy));
+        }
+      } else {
+        // ring sweep: word w of every lane contiguous ([w][lane]) so that the rotated LDS.128 is conflict free
+        constexpr bool RING = !HAS_VF && (APL == 2 || APL == 4) && LPE >= 4;
+  #pragma unroll
+        for (int k = 0; k < APL; k += 2)
+          spw[RING ? (k >> 1) * LPE + g.li : (i0 + k) >> 1] =
+              make_uint4(pack2(sx[k], sx[k + 1]), pack2(sy[k], sy[k + 1]), pack2(-sx[k], -sx[k + 1]),
+                         pack2(-sy[k], -sy[k + 1]));
+      }
+      if constexpr (HAS_VF) {
+  #pragma unroll
         for (int k = 0; k < APL; ++k) {
-          const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], w);
-          aR[k] += lt2(TR, m);
-          aA[k] += lt2(TA, m);
-          aRf[k] += lt2(TRf, m);
-          aAf[k] += lt2(TAf, m);
-          if constexpr (HAS_VF) {
-            const unsigned gate = lt2(TV, m);
-            const unsigned g0 = gate & 0xFFFFu, g1 = gate >> 16;
-            aV[k] += gate;
-            accA[k] += g0 * u.x + g1 * u.z;
-            accD[k] += g0 * u.y + g1 * u.w;
+          const int a = eff[k];
+          const bool mover = (i0 + k < N) && a < 8;
+          const int mx = mover ? move_dx(a) : 0, my = mover ? move_dy(a) : 0;
+          const bool diag = (a & 1) != 0;
+          svf[i0 + k] = make_uint2(pack2((diag ? 0 : mx) + 1, (diag ? 0 : my) + 1),
+                                   pack2((diag ? mx : 0) + 1, (diag ? my : 0) + 1));
+        }
+      }
+      g.sync();
+
+      unsigned XI[APL], YI[APL], NXI[APL], NYI[APL];
+  #pragma unroll
+      for (int k = 0; k < APL; ++k) {
+        XI[k] = rep2(sx[k]); YI[k] = rep2(sy[k]); NXI[k] = rep2(-sx[k]); NYI[k] = rep2(-sy[k]);
+      }
+      const unsigned TR = rep2(p.t_rep), TA = rep2(p.t_att), TRf = rep2(p.t_repf), TAf = rep2(p.t_attf);
+      const unsigned TV = rep2(HAS_VF ? p.t_vf : 0);
+      if constexpr (!HAS_VF && (APL == 2 || APL == 4) && LPE >= 4) {
+        // ---- symmetric ring sweep: every unordered block pair is evaluated once --------------------
+        // Lane l owns block B_l (APL agents = W pair words).  In round r it meets the block of lane l+r (pair words
+        // read from smem), adds each indicator to its own ROW counters and to the visiting block's COLUMN counters;
+        // the column counters travel round the ring by shuffles together with the block they belong to and are
+        // sent home after the last symmetric round.  Rounds 0 (own block) and LPE/2 (met from both sides) only
+        // count rows.  The accumulations are IMADs by a runtime 1 so that they issue on the FMA pipe and leave the
+        // ALU pipe to the DPX ops.
+        constexpr int W = APL / 2;
+        constexpr int HALF = LPE / 2;
+        const unsigned one = (unsigned)p.one, c256 = (unsigned)p.one << 8;
+        // Counters are BYTE packed: a 16x2 indicator word holds 0/1 in bytes 0 and 2, so ind(t0) + 256 * ind(t1)
+        // carries two thresholds for two agents in one register ({t0,t1} = {rep,att} and {rep_far,att_far}); it is
+        // built once (IMAD) and added to the row and to the column counter.  No byte can overflow: a row byte
+        // meets at most NMAX / 2 <= 64 pair words, a column byte at most (LPE / 2 - 1) * APL <= 60 rows.
+        unsigned row[APL][2], col[W][2];
+  #pragma unroll
+        for (int k = 0; k < APL; ++k) row[k][0] = row[k][1] = 0u;
+  #pragma unroll
+        for (int w = 0; w < W; ++w) col[w][0] = col[w][1] = 0u;
+        auto rows_only = [&](int src) {
+  #pragma unroll
+          for (int w = 0; w < W; ++w) {
+            const uint4 vw = spw[w * LPE + src];
+  #pragma unroll
+            for (int k = 0; k < APL; ++k) {
+              const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
+              row[k][0] = lt2(TR, m) * one + row[k][0];
+              row[k][0] = lt2(TA, m) * c256 + row[k][0];
+              row[k][1] = lt2(TRf, m) * one + row[k][1];
+              row[k][1] = lt2(TAf, m) * c256 + row[k][1];
+            }
+          }
+        };
+        rows_only(g.li);                                       // round 0: own block
+        const int nxt = (g.li + 1) & (LPE - 1);
+  #pragma unroll 1
+        for (int r = 1; r < HALF; ++r) {
+          const int src = (g.li + r) & (LPE - 1);
+          if (r > 1) {
+  #pragma unroll
+            for (int w = 0; w < W; ++w) {
+              col[w][0] = __shfl_sync(g.mask, col[w][0], nxt, LPE);
+              col[w][1] = __shfl_sync(g.mask, col[w][1], nxt, LPE);
+            }
+          }
+  #pragma unroll
+          for (int w = 0; w < W; ++w) {
+            const uint4 vw = spw[w * LPE + src];
+  #pragma unroll
+            for (int k = 0; k < APL; ++k) {
+              const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
+              const unsigned n0 = lt2(TA, m) * c256 + lt2(TR, m);
+              const unsigned n1 = lt2(TAf, m) * c256 + lt2(TRf, m);
+              row[k][0] = n0 * one + row[k][0];
+              row[k][1] = n1 * one + row[k][1];
+              col[w][0] = n0 * one + col[w][0];
+              col[w][1] = n1 * one + col[w][1];
+            }
+          }
+        }
+        // send the column counters home: lane l holds those of block l + HALF - 1
+        if constexpr (HALF > 1) {
+          const int from = (g.li - (HALF - 1)) & (LPE - 1);
+  #pragma unroll
+          for (int w = 0; w < W; ++w) {
+            col[w][0] = __shfl_sync(g.mask, col[w][0], from, LPE);
+            col[w][1] = __shfl_sync(g.mask, col[w][1], from, LPE);
+          }
+        }
+        rows_only((g.li + HALF) & (LPE - 1));                  // round LPE/2: met from both sides
+        // fold: total = both agents' bytes of the row counter + this agent's bytes of the column counter
+  #pragma unroll
+        for (int k = 0; k < APL; ++k) {
+          const int sh = 16 * (k & 1);
+          aR[k] = __dp4a(row[k][0], 0x00010001u, 0u) + ((col[k >> 1][0] >> sh) & 0xFFu);
+          aA[k] = __dp4a(row[k][0], 0x01000100u, 0u) + ((col[k >> 1][0] >> (sh + 8)) & 0xFFu);
+          aRf[k] = __dp4a(row[k][1], 0x00010001u, 0u) + ((col[k >> 1][1] >> sh) & 0xFFu);
+          aAf[k] = __dp4a(row[k][1], 0x01000100u, 0u) + ((col[k >> 1][1] >> (sh + 8)) & 0xFFu);
+        }
+      } else {
+        const int NW = (N + 1) >> 1;
+  #pragma unroll 2
+        for (int q = 0; q < NW; ++q) {
+          const uint4 w = spw[q];
+          uint4 u = make_uint4(0, 0, 0, 0);
+          if constexpr (HAS_VF) u = *reinterpret_cast<const uint4*>(&svf[2 * q]);
+  #pragma unroll
+          for (int k = 0; k < APL; ++k) {
+            const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], w);
+            aR[k] += lt2(TR, m);
+            aA[k] += lt2(TA, m);
+            aRf[k] += lt2(TRf, m);
+            aAf[k] += lt2(TAf, m);
+            if constexpr (HAS_VF) {
+              const unsigned gate = lt2(TV, m);
+              const unsigned g0 = gate & 0xFFFFu, g1 = gate >> 16;
+              aV[k] += gate;
+              accA[k] += g0 * u.x + g1 * u.z;
+              accD[k] += g0 * u.y + g1 * u.w;
+            }
           }
         }
       }
+
     }
 
     // alignment sums (SDE:346-359)
@@ -672,6 +726,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
         if (i0 + k < N) ac[i0 + k] = make_int2(0, 0);
     }
   }
+  if (bits_live) bitmap_clear<LPE, APL>(g, sbit, N, S, i0, nx, ny);
   if (p.eff_action) store_u8<APL>(p.eff_action + base, i0, N, vec, eff);
 
   // ---- per-env outputs ---------------------------------------------------------------------------

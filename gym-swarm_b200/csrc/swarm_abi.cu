@@ -2,6 +2,7 @@
 // Plain pointers in, kernel launches on the caller's stream out; no torch, no CPU fallback.
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -37,6 +38,7 @@ struct Ctx {
   int coll_bm_words = 0;      // > 0: collide_bitmap_kernel (per-env occupancy bitmap fits in shared memory)
   int coll_smem_bytes = 0;
   BoxPlan box{};              // sub-quadratic reward counts inside collide_bitmap_kernel (steps without vf_size)
+  BoxPlan fused_box{};        // the same plan for the fused lane-group kernels (per-env bitmap in shared memory)
   // stats
   double* d_stats = nullptr;
   // nccl
@@ -72,6 +74,30 @@ static void fill_thresholds(StepParams& p, int N, int S, int att, int rep) {
   p.inv_nn = 1.0 / ((double)N * (double)(N - 1));
 }
 
+// Box-count plan: per threshold the cheaper of the direct box and the complement (cost in bitmap word reads per
+// agent).  The caller enables it when that cost is far below the pairwise sweep's.
+static BoxPlan make_box_plan(int N, int S, int att, int rep, double& cost) {
+  StepParams tp;
+  memset(&tp, 0, sizeof(tp));
+  fill_thresholds(tp, N, S, att, rep);
+  const int ts[4] = {tp.t_rep, tp.t_att, tp.t_repf, tp.t_attf};
+  BoxPlan bp{};
+  cost = 0.0;
+  for (int q = 0; q < 4; ++q) {
+    const int t = ts[q];
+    bp.t[q] = t;
+    if (t <= 0) bp.mode[q] = BOX_ZERO;
+    else if (t >= S) bp.mode[q] = BOX_ALL;
+    else {
+      const double side = 2.0 * t - 1.0, direct = side * (side / 32.0 + 2.0);
+      const double b = (double)(S - t), comp = 8.0 + 4.0 * b * (b / 32.0 + 2.0);
+      if (direct <= comp) { bp.mode[q] = BOX_DIRECT; cost += direct; }
+      else { bp.mode[q] = BOX_COMPLEMENT; bp.need_hist = 1; cost += comp; }
+    }
+  }
+  return bp;
+}
+
 static StepParams base_params(const Ctx* c) {
   StepParams p;
   memset(&p, 0, sizeof(p));
@@ -84,6 +110,7 @@ static StepParams base_params(const Ctx* c) {
   p.K = g.slab_len; p.PL = g.place_len; p.KP = g.pred_attempts; p.R = g.reset_slots;
   p.auto_reset = g.auto_reset; p.track_stats = g.track_stats;
   p.bitmap_words = c->bitmap_words;
+  p.box = c->fused_box;
   p.one = 1;
   const swarm_state& s = c->st;
   p.x = s.x; p.y = s.y; p.px = s.px; p.py = s.py; p.target = s.target; p.orient = s.pred_orient;
@@ -95,9 +122,10 @@ static StepParams base_params(const Ctx* c) {
 
 // ---- fused dispatch -------------------------------------------------------------------------------
 template <int LPE, int APL>
-static int fused_smem_bytes(int bitmap_words, bool vf) {
+static int fused_smem_bytes(const StepParams& p, bool vf) {
   using C = FusedCfg<LPE, APL>;
-  return C::WARPS * (C::pair_bytes() + (vf ? C::vf_bytes() : 0) + C::EPW * bitmap_words * 4);
+  const int hist_words = (p.box.enabled && p.box.need_hist) ? 2 * p.S : 0;
+  return C::WARPS * (C::pair_bytes() + (vf ? C::vf_bytes() : 0) + C::EPW * (p.bitmap_words + hist_words) * 4);
 }
 
 template <int LPE, int APL>
@@ -105,7 +133,7 @@ static cudaError_t launch_fused_step(const StepParams& p, bool vf, cudaStream_t 
   using C = FusedCfg<LPE, APL>;
   const int envs_per_cta = C::WARPS * C::EPW;
   const int grid = (p.E + envs_per_cta - 1) / envs_per_cta;
-  const int smem = fused_smem_bytes<LPE, APL>(p.bitmap_words, vf);
+  const int smem = fused_smem_bytes<LPE, APL>(p, vf);
   cudaError_t e;
   if (vf) {
     e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -174,27 +202,9 @@ static int staged_alloc(Ctx* c) {
     if (bytes + 1024 <= dev_max && (N + threads - 1) / threads <= 16) {
       c->coll_bm_words = (int)words;
       c->coll_smem_bytes = (int)bytes;
-      // box-count plan: per threshold the cheaper of the direct box and the complement; enabled only when the
-      // whole plan costs far less per agent than the pairwise sweep (N pair evaluations)
-      StepParams tp;
-      memset(&tp, 0, sizeof(tp));
-      fill_thresholds(tp, N, c->cfg.grid_size, c->cfg.attraction_thresh, c->cfg.repulsion_thresh);
       const int S = c->cfg.grid_size;
-      const int ts[4] = {tp.t_rep, tp.t_att, tp.t_repf, tp.t_attf};
       double cost = 0.0;
-      BoxPlan bp{};
-      for (int q = 0; q < 4; ++q) {
-        const int t = ts[q];
-        bp.t[q] = t;
-        if (t <= 0) bp.mode[q] = BOX_ZERO;
-        else if (t >= S) bp.mode[q] = BOX_ALL;
-        else {
-          const double side = 2.0 * t - 1.0, direct = side * (side / 32.0 + 2.0);
-          const double b = (double)(S - t), comp = 8.0 + 4.0 * b * (b / 32.0 + 2.0);
-          if (direct <= comp) { bp.mode[q] = BOX_DIRECT; cost += direct; }
-          else { bp.mode[q] = BOX_COMPLEMENT; bp.need_hist = 1; cost += comp; }
-        }
-      }
+      BoxPlan bp = make_box_plan(N, S, c->cfg.attraction_thresh, c->cfg.repulsion_thresh, cost);
       const long long hist_bytes = bp.need_hist ? 2LL * S * 4 : 0;
       // (a box word-op is ~5 instructions, the symmetric pair sweep ~1.5 ALU instructions per agent pair)
       if (cost * 3.0 < (double)N && bytes + hist_bytes + 1024 <= dev_max) {
@@ -376,9 +386,23 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
     const long long cells = (long long)cfg->grid_size * cfg->grid_size;
     const long long words = ((cells + 31) / 32 + 3) / 4 * 4;
     c->bitmap_words = (words <= 2048 && cfg->num_agents >= 16) ? (int)words : 0;
+    if (c->bitmap_words > 0 && !c->tiny) {
+      double cost = 0.0;
+      BoxPlan bp = make_box_plan(cfg->num_agents, cfg->grid_size, cfg->attraction_thresh, cfg->repulsion_thresh, cost);
+      // Measured on B200 at cfg3 (N = 128, S = 128, default thresholds): ring sweep 0.275 ms / step, box counts
+      // 0.422 ms / step (random shared-memory reads, divergent row loops, per-env histograms) -- so for the lane-group
+      // kernels (N <= 256) the box path is OFF unless SWARM_FUSED_BOX=1 asks for it; it pays off from N ~ 1000 up,
+      // which is the staged path.
+      bp.enabled = 0;
+      (void)cost;
+      const char* force = getenv("SWARM_FUSED_BOX");          // kernel A/B experiments / tests
+      if (force && (force[0] == '0' || force[0] == '1')) bp.enabled = force[0] == '1';
+      c->fused_box = bp;
+    }
     char buf[64];
     if (c->tiny) snprintf(buf, sizeof(buf), "tiny<%d> (vf: fused<%d,%d>)", TINY_N, c->lpe, c->apl);
-    else snprintf(buf, sizeof(buf), "fused<%d,%d>%s", c->lpe, c->apl, c->bitmap_words ? "+bitmap" : "");
+    else snprintf(buf, sizeof(buf), "fused<%d,%d>%s%s", c->lpe, c->apl, c->bitmap_words ? "+bitmap" : "",
+                  c->fused_box.enabled ? "+box" : "");
     c->path_name = buf;
   } else {
     c->path_name = "staged";   // refined after staged_alloc (box-count plan)

@@ -11,6 +11,26 @@
 
 namespace swarm {
 
+// ------------------------------------------------------------------------------------------------
+// Box counts: the sub-quadratic exact path for the reward's threshold counts.
+// After the last collision round the shared bitmap holds exactly the N (distinct) final cells, so
+//   #{j : D_ij < t}  (self included, D = Chebyshev)  =  popcount of the bitmap over the (2t-1)^2 box around i,
+// and for a large threshold the complement is cheaper:
+//   #{j : D_ij >= t} = #{|dx| >= t} + #{|dy| >= t} - #{both}
+// with the first two from prefix sums of the per-column / per-row agent histograms and the last from the (at
+// most four) corner rectangles of side <= S - t.  All integers: results are identical to the pairwise sweep.
+// The host picks a method per threshold (BOX_*) and only enables the path when its cost per agent is far below
+// the pairwise sweep's; otherwise (and for every vf_size step) the tiled pairwise kernel runs.
+// ------------------------------------------------------------------------------------------------
+enum { BOX_ZERO = 0, BOX_ALL = 1, BOX_DIRECT = 2, BOX_COMPLEMENT = 3 };
+struct BoxPlan {
+  int enabled;       // 0: pairwise kernels compute the counts
+  int need_hist;     // some threshold uses BOX_COMPLEMENT
+  int mode[4];       // for t_rep, t_att, t_repf, t_attf
+  int t[4];
+};
+
+
 // ----------------------------------------------------------------------------------------------
 // Kernel parameter block (by-value kernel argument).
 // ----------------------------------------------------------------------------------------------
@@ -27,6 +47,7 @@ struct StepParams {
   int K, PL, KP, R;
   int auto_reset, track_stats;
   int bitmap_words;  // per-env smem occupancy bitmap words (0: not used)
+  BoxPlan box;       // fused kernels: box-count reward path (needs the per-env bitmap, bitmap_words > 0)
   int one;           // runtime 1: `v * one + acc` compiles to IMAD (FMA pipe) instead of IADD3 (ALU pipe)
   // state
   int16_t *x, *y, *px, *py;
@@ -144,5 +165,49 @@ __device__ __forceinline__ AgentTerms agent_terms(const StepParams& p, int cR, i
   t.una = 0.5 * (double)vis - 0.25 * (double)P - 0.35355339059327376220 * (double)Q;
   return t;
 }
+
+// number of set bits in the bit range [lo, hi] (inclusive, lo <= hi) of a word array
+__device__ __forceinline__ int range_popc(const unsigned* __restrict__ bits, int lo, int hi) {
+  const int w0 = lo >> 5, w1 = hi >> 5;
+  const unsigned m0 = 0xFFFFFFFFu << (lo & 31), m1 = 0xFFFFFFFFu >> (31 - (hi & 31));
+  if (w0 == w1) return __popc(bits[w0] & m0 & m1);
+  int c = __popc(bits[w0] & m0) + __popc(bits[w1] & m1);
+  for (int w = w0 + 1; w < w1; ++w) c += __popc(bits[w]);
+  return c;
+}
+// agents in the rectangle [x0,x1] x [y0,y1] (empty when a bound is inverted)
+__device__ __forceinline__ int box_popc(const unsigned* __restrict__ bits, int S, int x0, int x1, int y0, int y1) {
+  if (x0 > x1 || y0 > y1) return 0;
+  int c = 0;
+  for (int y = y0; y <= y1; ++y) c += range_popc(bits, y * S + x0, y * S + x1);
+  return c;
+}
+// inclusive prefix of a histogram with the out-of-range conventions P(a < 0) = 0, P(a >= S-1) = N
+__device__ __forceinline__ int hist_le(const int* __restrict__ pre, int a, int S, int N) {
+  return a < 0 ? 0 : (a >= S - 1 ? N : pre[a]);
+}
+__device__ __forceinline__ int box_count(const BoxPlan& bp, int s, const unsigned* __restrict__ bits, const int* __restrict__ hx,
+                                         const int* __restrict__ hy, int xi, int yi, int S, int N) {
+  const int t = bp.t[s];
+  switch (bp.mode[s]) {
+    case BOX_ZERO: return 0;
+    case BOX_ALL: return N;
+    case BOX_DIRECT: {
+      const int r = t - 1;
+      return box_popc(bits, S, max(0, xi - r), min(S - 1, xi + r), max(0, yi - r), min(S - 1, yi + r));
+    }
+    default: {
+      const int nxs = hist_le(hx, xi - t, S, N) + N - hist_le(hx, xi + t - 1, S, N);
+      const int nys = hist_le(hy, yi - t, S, N) + N - hist_le(hy, yi + t - 1, S, N);
+      int both = 0;
+      if (nxs > 0 && nys > 0) {
+        both = box_popc(bits, S, 0, xi - t, 0, yi - t) + box_popc(bits, S, 0, xi - t, yi + t, S - 1) +
+               box_popc(bits, S, xi + t, S - 1, 0, yi - t) + box_popc(bits, S, xi + t, S - 1, yi + t, S - 1);
+      }
+      return N - (nxs + nys - both);
+    }
+  }
+}
+
 
 }  // namespace swarm

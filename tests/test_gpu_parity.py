@@ -138,6 +138,24 @@ def test_box_count_path_thresholds(att, rep):
     _oracle_lockstep(E=2, N=1500, S=50, T=2, seed=att + rep, n_actions=9, att=att, rep=rep, K=4096, KR=6000)
 
 
+@pytest.mark.parametrize("force", ["0", "1"])
+@pytest.mark.parametrize("N,S", [(16, 32), (24, 12), (33, 64), (64, 64), (100, 48), (128, 128), (255, 64)])
+def test_fused_reward_by_ring_sweep_and_by_box_counts(N, S, force, monkeypatch):
+    """The fused lane-group kernel computes the reward counts either by the symmetric ring sweep or from the env's
+    occupancy bitmap (box counts); SWARM_FUSED_BOX forces one or the other regardless of the cost heuristic."""
+    monkeypatch.setenv("SWARM_FUSED_BOX", force)
+    dense = S * S < 4 * N
+    _oracle_lockstep(E=9, N=N, S=S, T=12, seed=N * 3 + S + int(force), n_actions=9, K=512 if dense else None,
+                     KR=2000 if dense else None, weights=(0.5, 1.0, 0.25))
+
+
+@pytest.mark.parametrize("att,rep", [(5, 2), (2, 5), (0, 0), (1, 1), (9, 3), (3, 12), (10, 200), (40, 3), (70, 70), (5, 60)])
+def test_fused_box_count_thresholds(att, rep, monkeypatch):
+    monkeypatch.setenv("SWARM_FUSED_BOX", "1")
+    _oracle_lockstep(E=6, N=120, S=64, T=4, seed=att * 13 + rep, n_actions=9, att=att, rep=rep, weights=(0.5, 1.0, 0.25))
+    _oracle_lockstep(E=6, N=40, S=21, T=4, seed=att + rep, n_actions=9, att=att, rep=rep)
+
+
 def test_staged_path_names():
     from gym_swarm_b200.envs import BatchedSwarmEnv
     for kw, name in ((dict(path="auto"), "staged+box"), (dict(path="staged_pairwise"), "staged+bitmap")):
