@@ -640,9 +640,22 @@ int swarm_pairwise(int32_t E, int32_t N, int32_t S, int32_t attraction_thresh, i
   StagedScratch sc;
   memset(&sc, 0, sizeof(sc));
   sc.NW = (N + 1) / 2;
-  void* block = nullptr;
+  // scratch of the standalone entry point: one block per device, grown on demand and kept (a stream-ordered
+  // allocation per call made every other launch wait on the pool); calls on the same device must not overlap
+  static void* g_block[64] = {nullptr};
+  static size_t g_bytes[64] = {0};
+  int devi = 0;
+  CUDA_TRY(nullptr, cudaGetDevice(&devi));
+  if (devi < 0 || devi >= 64) return fail(nullptr, SWARM_E_INVALID, "swarm_pairwise: device ordinal out of range");
   const size_t b_pairw = align_up((size_t)E * sc.NW * 16, 256), b_pc = align_up((size_t)E * N * 32 + 64, 256);
-  CUDA_TRY(nullptr, cudaMallocAsync(&block, b_pairw + b_pc + 256, s));
+  if (g_bytes[devi] < b_pairw + b_pc + 256) {
+    CUDA_TRY(nullptr, cudaDeviceSynchronize());
+    if (g_block[devi]) cudaFree(g_block[devi]);
+    g_block[devi] = nullptr; g_bytes[devi] = 0;
+    CUDA_TRY(nullptr, cudaMalloc(&g_block[devi], b_pairw + b_pc + 256));
+    g_bytes[devi] = b_pairw + b_pc + 256;
+  }
+  void* block = g_block[devi];
   sc.pairw = (uint4*)block;
   sc.pcounts = (unsigned*)((char*)block + b_pairw);
   sc.counter = (unsigned*)((char*)block + b_pairw + b_pc);
@@ -656,7 +669,6 @@ int swarm_pairwise(int32_t E, int32_t N, int32_t S, int32_t attraction_thresh, i
   const long long agents = (long long)E * N;
   pair_counts_kernel<<<(int)((agents + 255) / 256), 256, 0, s>>>(p, sc.pcounts, skip, out_counts);
   CUDA_TRY(nullptr, cudaGetLastError());
-  CUDA_TRY(nullptr, cudaFreeAsync(block, s));
   return SWARM_OK;
 }
 
