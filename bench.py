@@ -213,6 +213,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--path", default="auto", choices=["auto", "fused", "group", "staged", "staged_pairwise"])
     ap.add_argument("--vf", type=int, default=None, help="reward_type['vf_size'] (default None)")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="time the HBM-resident loop as CUDA-graph replays of --tape-steps steps (auto: when a step has "
+                         "fewer than 1M agents and the host launch cost would dominate)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
 
@@ -286,6 +289,15 @@ def main():
         step_no[0] = t + 1
         return env.last_launch_count()
 
+    use_graph = args.graph == "on" or (args.graph == "auto" and E * N < (1 << 20) and args.vf is None)
+    roll = None
+    if use_graph:                                        # T steps per graph launch, tapes rotate inside the graph
+        roll = env.capture_rollout(d_actions, d_retarget, d_slab,
+                                   [curriculum_weights(t, cfg["curriculum"]) for t in range(T)])
+        graph_launches_per_step = roll.launches / T
+        n_replays = max(1, -(-args.steps // T))
+        args.steps = n_replays * T
+
     # ---- warm-up + device-resident timed region ---------------------------------------------------------
     for _ in range(max(3, args.warmup)):
         dev_step()
@@ -299,8 +311,14 @@ def main():
     launches = 0
     w0 = time.time()
     ev0.record()
-    for _ in range(args.steps):
-        launches += dev_step()
+    if roll is not None:
+        for _ in range(n_replays):
+            roll.replay()
+        launches = int(round(graph_launches_per_step * args.steps))
+        step_no[0] += args.steps
+    else:
+        for _ in range(args.steps):
+            launches += dev_step()
     ev1.record()
     barrier()
     w1 = time.time()
@@ -430,7 +448,8 @@ def main():
                        "kernel_path": env.path_name, "launches_per_step": env.last_launch_count(),
                        "l2": f"no flush: per-step working set {ws_mb:.0f} MB, {T} rotating tape steps "
                              f"({ws_mb * 1.0 + T * (E * N + E * K) / 1e6:.0f} MB touched per rotation) vs 126 MB L2",
-                       "parallelism": f"env-sharded x{world}" if world > 1 else "single GPU"},
+                       "parallelism": f"env-sharded x{world}" if world > 1 else "single GPU",
+                       "timed_loop": (f"CUDA graph replays of {T} steps" if roll is not None else "eager swarm_step calls")},
             "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline,
             "roofline_int32": roofline_int32, "cpu_baseline": cpu, "episode_stats": stats,
         }

@@ -128,22 +128,25 @@ static int fused_smem_bytes(const StepParams& p, bool vf) {
   return C::WARPS * (C::pair_bytes() + (vf ? C::vf_bytes() : 0) + C::EPW * (p.bitmap_words + hist_words) * 4);
 }
 
+// once per handle (swarm_create): opt in to the dynamic shared memory the two step kernels need.  Nothing but
+// kernel launches happens in swarm_step, so a step can be captured into a CUDA graph.
+template <int LPE, int APL>
+static cudaError_t prepare_fused_step(const StepParams& p) {
+  cudaError_t e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       fused_smem_bytes<LPE, APL>(p, true));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(fused_step_kernel<LPE, APL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              fused_smem_bytes<LPE, APL>(p, false));
+}
+
 template <int LPE, int APL>
 static cudaError_t launch_fused_step(const StepParams& p, bool vf, cudaStream_t s) {
   using C = FusedCfg<LPE, APL>;
   const int envs_per_cta = C::WARPS * C::EPW;
   const int grid = (p.E + envs_per_cta - 1) / envs_per_cta;
   const int smem = fused_smem_bytes<LPE, APL>(p, vf);
-  cudaError_t e;
-  if (vf) {
-    e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    fused_step_kernel<LPE, APL, true><<<grid, C::WARPS * 32, smem, s>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    fused_step_kernel<LPE, APL, false><<<grid, C::WARPS * 32, smem, s>>>(p);
-  }
+  if (vf) fused_step_kernel<LPE, APL, true><<<grid, C::WARPS * 32, smem, s>>>(p);
+  else fused_step_kernel<LPE, APL, false><<<grid, C::WARPS * 32, smem, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -413,6 +416,18 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
     if (rc != SWARM_OK) { std::string m = c->err; delete c; return fail(nullptr, rc, m); }
     if (c->coll_bm_words > 0 && c->box.enabled && !c->force_pairwise) c->path_name = "staged+box (vf: staged pairwise)";
     else if (c->coll_bm_words > 0) c->path_name = "staged+bitmap";
+  }
+  if (c->fused) {
+    const StepParams p0 = base_params(c);
+    cudaError_t pe = cudaSuccess;
+#define CALL(L, A) pe = prepare_fused_step<L, A>(p0)
+    FUSED_DISPATCH(c, CALL);
+#undef CALL
+    if (pe != cudaSuccess) {
+      const std::string m = std::string("swarm_create: shared memory opt-in failed: ") + cudaGetErrorString(pe);
+      delete c;
+      return fail(nullptr, SWARM_E_CUDA, m);
+    }
   }
   cudaError_t e = cudaMalloc(&c->d_stats, 8 * sizeof(double));
   if (e != cudaSuccess) { delete c; return fail(nullptr, SWARM_E_CUDA, "cudaMalloc stats"); }

@@ -245,6 +245,44 @@ class BatchedSwarmEnv:
         _lib.check(self.lib.swarm_stats_allreduce(self._h, buf, self._stream()), self._h)
         return dict(zip(self.STAT_KEYS, [float(v) for v in buf]))
 
+    # ---- checkpoint / resume (the reference's state is its attributes + the global NumPy RNG) ----
+    _STATE_TENSORS = ("x", "y", "px", "py", "target", "pred_orient", "frozen", "err", "reset_count",
+                      "ep_len", "ep_ret", "fin_count", "fin_len", "fin_ret")
+
+    def state_dict(self):
+        """Everything needed to continue bit-identically: device state, statistics, reset tapes, the host tape
+        generator and the unconsumed part of the current tape chunk."""
+        torch.cuda.synchronize(self.device)
+        d = {"shape": (self.E, self.N, self.S), "tensors": {}, "rng": self._rng.bit_generator.state,
+             "chunk_pos": self._chunk_pos}
+        for k in self._STATE_TENSORS:
+            t = getattr(self, k)
+            if t is not None:
+                d["tensors"][k] = t.detach().cpu().clone()
+        d["place"] = None if self._place is None else self._place.cpu().clone()
+        d["ptape"] = None if self._ptape is None else self._ptape.cpu().clone()
+        d["chunk"] = None if self._chunk is None else tuple(t.cpu().clone() for t in self._chunk)
+        return d
+
+    def load_state_dict(self, d):
+        assert tuple(d["shape"]) == (self.E, self.N, self.S), "checkpoint is for another shape"
+        for k, v in d["tensors"].items():
+            getattr(self, k).copy_(v)                   # in place: the bound device pointers stay valid
+        if d["place"] is not None:
+            self.set_reset_tapes(d["place"], d["ptape"])
+        self._rng.bit_generator.state = d["rng"]
+        self._chunk = None if d["chunk"] is None else tuple(t.to(self.device) for t in d["chunk"])
+        self._chunk_pos = d["chunk_pos"]
+
+    # ---- CUDA graph rollouts --------------------------------------------------------------------------
+    def capture_rollout(self, actions, retarget, slab, reward_types=None):
+        """Capture T consecutive steps (actions u8[T,E,N], retarget u8[T,E], slab u8[T,E,K] resident on the device) into
+        one CUDA graph.  ``swarm_step`` only launches kernels, so the whole rollout replays with a single graph launch:
+        this removes the per-step host cost that dominates small batches (cfg2: 4,096 x 16).  Returns a
+        ``GraphedRollout``; refill the three tape tensors in place and call ``replay()``.  Per-step global rewards and
+        done flags are recorded into ``rewards f32[T,E,5]`` / ``dones u8[T,E]``."""
+        return GraphedRollout(self, actions, retarget, slab, reward_types)
+
     # ---- numpy views for tests / the compatibility class ------------------------------------------
     def state_numpy(self):
         torch.cuda.synchronize(self.device)
@@ -273,6 +311,85 @@ class BatchedSwarmEnv:
             o["agent_cnt"] = self.agent_counts.cpu().numpy().astype(np.int64)
             o["eff"] = self.eff_action.cpu().numpy()
         return o
+
+
+class GraphedRollout:
+    """T steps of a ``BatchedSwarmEnv`` as one CUDA graph (see ``BatchedSwarmEnv.capture_rollout``)."""
+
+    def __init__(self, env, actions, retarget, slab, reward_types=None):
+        self.env = env
+        T = actions.shape[0]
+        assert actions.is_cuda and retarget.is_cuda and slab.is_cuda, "graph inputs must live on the device"
+        assert actions.dtype == torch.uint8 and retarget.dtype == torch.uint8 and slab.dtype == torch.uint8
+        assert tuple(actions.shape) == (T, env.E, env.N) and tuple(retarget.shape) == (T, env.E)
+        assert tuple(slab.shape) == (T, env.E, env.K)
+        self.T, self.actions, self.retarget, self.slab = T, actions, retarget, slab
+        self.rewards = torch.zeros((T, env.E, 5), dtype=torch.float32, device=env.device)
+        self.dones = torch.zeros((T, env.E), dtype=torch.uint8, device=env.device)
+        rts = reward_types if isinstance(reward_types, (list, tuple)) else [reward_types] * T
+        env._ensure_reset_tapes()
+        self.launches = 0
+        side = torch.cuda.Stream(device=env.device)
+        side.wait_stream(torch.cuda.current_stream(env.device))
+        with torch.cuda.stream(side):                   # warm-up outside the capture (lazy module loading)
+            snap = env.state_dict()
+            env.step(actions[0], rts[0], retarget=retarget[0], slab=slab[0])
+            env.load_state_dict(snap)
+        torch.cuda.current_stream(env.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            for t in range(T):
+                env.step(actions[t], rts[t], retarget=retarget[t], slab=slab[t])
+                self.launches += env.last_launch_count()
+                self.rewards[t].copy_(env.reward)
+                self.dones[t].copy_(env.done)
+
+    def replay(self):
+        self.graph.replay()
+        return self.rewards, self.dones
+
+
+class SwarmVectorEnv:
+    """Vector-env style adapter (the Gymnasium ``VectorEnv`` call shapes, no gym import needed): E copies of the swarm
+    env stepped together, auto-reset on termination.
+
+    ``reset(seed=None) -> (obs, info)``; ``step(actions) -> (obs, reward, terminated, truncated, info)`` with
+    ``obs`` int16[E,N,2] (x, y of every agent), ``reward`` f32[E] (the global ``sum`` reward, SDE:366) -- the
+    per-component and per-agent rewards are in ``info`` -- ``terminated`` bool[E], ``truncated`` all False (the
+    reference has no time limit).  All tensors stay on the device."""
+
+    def __init__(self, num_envs, num_agents=4, obs_space_size=20, reward_type=None, seed=0, **env_kwargs):
+        env_kwargs.setdefault("auto_reset", True)
+        self.env = BatchedSwarmEnv(num_envs, num_agents, obs_space_size, seed=seed, **env_kwargs)
+        self.num_envs, self.num_agents, self.obs_space_size = self.env.E, self.env.N, self.env.S
+        self.reward_type = dict(DEFAULT_REWARD_TYPE if reward_type is None else reward_type)
+        self.single_action_space = SimpleNamespace(n=8, shape=(self.num_agents,), dtype=np.uint8)
+        self.single_observation_space = SimpleNamespace(shape=(self.num_agents, 2), dtype=np.int16, low=0,
+                                                        high=self.obs_space_size - 1)
+        self._obs = torch.zeros((self.num_envs, self.num_agents, 2), dtype=torch.int16, device=self.env.device)
+
+    def _observe(self):
+        self._obs[:, :, 0].copy_(self.env.x)
+        self._obs[:, :, 1].copy_(self.env.y)
+        return self._obs
+
+    def reset(self, seed=None):
+        if seed is not None:
+            self.env._rng = np.random.default_rng(seed)
+            self.env._place = None
+            self.env._chunk = None
+        self.env.reset()
+        return self._observe(), {"predator": torch.stack([self.env.px, self.env.py], 1)}
+
+    def step(self, actions):
+        _, reward, done, info = self.env.step(actions, self.reward_type)
+        info = dict(info, reward_components=reward["global"], agent_rewards=reward["agents"],
+                    predator=torch.stack([self.env.px, self.env.py], 1))
+        terminated = done.bool()
+        return self._observe(), reward["global"][:, 4], terminated, torch.zeros_like(terminated), info
+
+    def close(self):
+        self.env.close()
 
 
 class SwarmEnv:
