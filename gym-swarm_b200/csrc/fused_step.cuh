@@ -475,13 +475,28 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
         }
         g.sync();
       }
+      if (p.box.fast_rmax >= 0) {
 #pragma unroll
-      for (int k = 0; k < APL; ++k) {
-        if (i0 + k < N) {
-          aR[k] = (unsigned)box_count(p.box, 0, sbit, hx, hy, nx[k], ny[k], S, N);
-          aA[k] = (unsigned)box_count(p.box, 1, sbit, hx, hy, nx[k], ny[k], S, N);
-          aRf[k] = (unsigned)box_count(p.box, 2, sbit, hx, hy, nx[k], ny[k], S, N);
-          aAf[k] = (unsigned)box_count(p.box, 3, sbit, hx, hy, nx[k], ny[k], S, N);
+        for (int k = 0; k < APL; ++k) {
+          // padding agents sweep (clamped, in-range) rows too so that the row loop stays convergent; their counts
+          // are never used
+          const int xi = i0 + k < N ? nx[k] : 0, yi = i0 + k < N ? ny[k] : 0;
+          int cnt[4];
+          box_direct_sweep(p.box, sbit, xi, yi, S, cnt);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (p.box.mode[q] != BOX_DIRECT) cnt[q] = box_count(p.box, q, sbit, hx, hy, xi, yi, S, N);
+          aR[k] = (unsigned)cnt[0]; aA[k] = (unsigned)cnt[1]; aRf[k] = (unsigned)cnt[2]; aAf[k] = (unsigned)cnt[3];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < APL; ++k) {
+          if (i0 + k < N) {
+            aR[k] = (unsigned)box_count(p.box, 0, sbit, hx, hy, nx[k], ny[k], S, N);
+            aA[k] = (unsigned)box_count(p.box, 1, sbit, hx, hy, nx[k], ny[k], S, N);
+            aRf[k] = (unsigned)box_count(p.box, 2, sbit, hx, hy, nx[k], ny[k], S, N);
+            aAf[k] = (unsigned)box_count(p.box, 3, sbit, hx, hy, nx[k], ny[k], S, N);
+          }
         }
       }
     } else {

@@ -83,6 +83,7 @@ static BoxPlan make_box_plan(int N, int S, int att, int rep, double& cost) {
   const int ts[4] = {tp.t_rep, tp.t_att, tp.t_repf, tp.t_attf};
   BoxPlan bp{};
   cost = 0.0;
+  bp.fast_rmax = -1;
   for (int q = 0; q < 4; ++q) {
     const int t = ts[q];
     bp.t[q] = t;
@@ -95,6 +96,12 @@ static BoxPlan make_box_plan(int N, int S, int att, int rep, double& cost) {
       else { bp.mode[q] = BOX_COMPLEMENT; bp.need_hist = 1; cost += comp; }
     }
   }
+  // single-sweep variant for the fused kernel: word-aligned rows and small direct boxes
+  int rmax = -1;
+  bool ok = (S % 32) == 0;
+  for (int q = 0; q < 4; ++q)
+    if (bp.mode[q] == BOX_DIRECT) { rmax = std::max(rmax, bp.t[q] - 1); ok = ok && bp.t[q] - 1 <= 15; }
+  if (ok && rmax >= 0) bp.fast_rmax = rmax;
   return bp;
 }
 
@@ -392,10 +399,11 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
     if (c->bitmap_words > 0 && !c->tiny) {
       double cost = 0.0;
       BoxPlan bp = make_box_plan(cfg->num_agents, cfg->grid_size, cfg->attraction_thresh, cfg->repulsion_thresh, cost);
-      // Measured on B200 at cfg3 (N = 128, S = 128, default thresholds): ring sweep 0.275 ms / step, box counts
-      // 0.422 ms / step (random shared-memory reads, divergent row loops, per-env histograms) -- so for the lane-group
-      // kernels (N <= 256) the box path is OFF unless SWARM_FUSED_BOX=1 asks for it; it pays off from N ~ 1000 up,
-      // which is the staged path.
+      // Measured on B200 at cfg3 (N = 128, S = 128, default thresholds), ms / step: ring sweep 0.275-0.278; box counts
+      // 0.42-0.45 (the far thresholds' corner rectangles are rare per agent but hit some lane of nearly every warp);
+      // even with the far thresholds stubbed out the single-sweep direct boxes alone gave 0.270 -- no better than the
+      // ring.  So for the lane-group kernels (N <= 256) the box path is OFF unless SWARM_FUSED_BOX=1 asks for it; it
+      // pays off from N ~ 1000 up, which is the staged path.
       bp.enabled = 0;
       (void)cost;
       const char* force = getenv("SWARM_FUSED_BOX");          // kernel A/B experiments / tests

@@ -28,6 +28,9 @@ struct BoxPlan {
   int need_hist;     // some threshold uses BOX_COMPLEMENT
   int mode[4];       // for t_rep, t_att, t_repf, t_attf
   int t[4];
+  int fast_rmax;     // >= 0: word-aligned rows (S % 32 == 0) and every BOX_DIRECT radius t-1 <= fast_rmax <= 15:
+                     // the fused kernel counts all direct thresholds in ONE branch-free sweep of 2*fast_rmax+1 rows
+                     // (32-bit window per row by funnel shift); -1: generic box_count per threshold
 };
 
 
@@ -209,5 +212,36 @@ __device__ __forceinline__ int box_count(const BoxPlan& bp, int s, const unsigne
   }
 }
 
+
+// All BOX_DIRECT thresholds of one agent in a single sweep over the rows yi-r .. yi+r (r = bp.fast_rmax, uniform over
+// the warp, so the loop and the per-threshold row tests do not diverge).  Per row: two shared-memory words, one funnel
+// shift to a 32-bit window that starts at the leftmost in-grid column of the widest box, one AND + POPC per threshold.
+__device__ __forceinline__ void box_direct_sweep(const BoxPlan& bp, const unsigned* __restrict__ bits, int xi, int yi, int S,
+                                                 int (&cnt)[4]) {
+  const int r = bp.fast_rmax;
+  const int wpr = S >> 5;                                   // words per row
+  const int lo_c = max(xi - r, 0);
+  const int sh = lo_c & 31, w0 = lo_c >> 5, w1 = min(w0 + 1, wpr - 1);
+  unsigned mq[4];
+  int rq[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    rq[q] = bp.mode[q] == BOX_DIRECT ? bp.t[q] - 1 : -1;
+    const int lq = max(xi - rq[q], 0), hq = min(xi + rq[q], S - 1);
+    mq[q] = rq[q] >= 0 ? ((0xFFFFFFFFu >> (31 - (hq - lq))) << (lq - lo_c)) : 0u;   // box columns inside the window
+    cnt[q] = 0;
+  }
+  for (int dy = -r; dy <= r; ++dy) {
+    const int y = yi + dy;
+    const bool valid = y >= 0 && y < S;
+    const int yb = min(max(y, 0), S - 1) * wpr;
+    const unsigned a = bits[yb + w0], b = bits[yb + w1];
+    const unsigned win = valid ? __funnelshift_r(a, b, sh) : 0u;
+    const int ady = dy < 0 ? -dy : dy;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (ady <= rq[q]) cnt[q] += __popc(win & mq[q]);      // uniform branch: rq and dy are the same for every lane
+  }
+}
 
 }  // namespace swarm

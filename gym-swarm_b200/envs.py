@@ -154,15 +154,32 @@ class BatchedSwarmEnv:
 
     def _ensure_reset_tapes(self):
         if self._place is None:
-            rt = _tapes.make_reset_tapes(self._rng, self.R, self.E, self.N, self.S, KR=self.KR, KP=self.KP)
-            self.set_reset_tapes(rt.place, rt.ptape)
+            if self.R * self.E * self.PL <= (1 << 24):
+                rt = _tapes.make_reset_tapes(self._rng, self.R, self.E, self.N, self.S, KR=self.KR, KP=self.KP)
+                self.set_reset_tapes(rt.place, rt.ptape)
+            else:                                       # large batches: draw the reset tapes on the device
+                g = torch.Generator(device=self.device)
+                g.manual_seed(int(self._rng.integers(0, 2 ** 62)))
+                place = torch.randint(0, self.S, (self.R, self.E, self.PL), dtype=torch.int16, device=self.device, generator=g)
+                ptape = torch.randint(0, self.S, (self.R, self.E, self.KP, 2), dtype=torch.int16, device=self.device,
+                                      generator=g)
+                self.set_reset_tapes(place, ptape)
 
     def _next_step_tapes(self):
+        """Tapes for callers that do not bring their own: drawn in chunks of ``tape_chunk`` steps.  Small batches draw
+        on the host (NumPy generator, reproducible from ``seed`` alone); large ones draw on the device with a torch
+        generator seeded from the same NumPy stream -- a host draw of [T, E, K] bytes costs seconds at a million envs."""
         if self._chunk is None or self._chunk_pos >= self._tape_chunk:
             T = self._tape_chunk
-            roll = self._rng.random(size=(T, self.E))
-            retarget = torch.from_numpy((roll < 0.1).astype(np.uint8)).to(self.device)
-            slab = torch.from_numpy(self._rng.integers(0, 8, size=(T, self.E, self.K), dtype=np.uint8)).to(self.device)
+            if self.E * self.K * T <= (1 << 24):
+                roll = self._rng.random(size=(T, self.E))
+                retarget = torch.from_numpy((roll < 0.1).astype(np.uint8)).to(self.device)
+                slab = torch.from_numpy(self._rng.integers(0, 8, size=(T, self.E, self.K), dtype=np.uint8)).to(self.device)
+            else:
+                g = torch.Generator(device=self.device)
+                g.manual_seed(int(self._rng.integers(0, 2 ** 62)))
+                retarget = (torch.rand((T, self.E), device=self.device, generator=g) < 0.1).to(torch.uint8)
+                slab = torch.randint(0, 8, (T, self.E, self.K), dtype=torch.uint8, device=self.device, generator=g)
             self._chunk, self._chunk_pos = (retarget, slab), 0
         r, s = self._chunk[0][self._chunk_pos], self._chunk[1][self._chunk_pos]
         self._chunk_pos += 1
