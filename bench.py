@@ -43,7 +43,7 @@ CONFIGS = {
                  desc="configs[2]: 65,536 envs x 128 agents, 128x128 grid, per-agent reward dict + curriculum"),
     "cfg4": dict(E=16, N=16384, S=1024, per_agent=True, curriculum=False,
                  desc="configs[3]: 16 envs x 16,384 agents, 1024x1024 grid, pairwise dominated"),
-    "cfg5": dict(E=1048576, N=8, S=16, per_agent=False, curriculum=False,
+    "cfg5": dict(E=1048576, N=8, S=16, per_agent=False, curriculum=False, place_extra=64,
                  desc="configs[4]: 1,048,576 envs x 8 agents, 16x16 grid, auto-reset + episode statistics"),
     # streaming shape for an honest DRAM number: 16 M envs x 8 agents
     "stream": dict(E=16777216, N=8, S=16, per_agent=False, curriculum=False, place_extra=64,

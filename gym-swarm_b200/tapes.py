@@ -33,8 +33,9 @@ def default_slab_len(N: int) -> int:
 
 
 def default_place_extra(N: int) -> int:
-    """Extra (x,y) pairs per reset for placement re-draw rounds."""
-    return int(max(16, N // 4))
+    """Extra (x,y) pairs per reset for placement re-draw rounds (a 16-pair tape was exhausted by one env in
+    8 M x 100 steps at N = 8 on 16 x 16; 32 pairs leaves orders of magnitude of margin, benches at >= 1 M envs use 64)."""
+    return int(max(32, N // 4))
 
 
 @dataclass
