@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(_HERE, "libswarm_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "swarm_abi.h")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 PATH_AUTO, PATH_STAGED, PATH_FUSED, PATH_GROUP, PATH_STAGED_PAIRWISE = 0, 1, 2, 3, 4
 
 ERR_SLAB_OVERFLOW = 1
@@ -49,7 +49,7 @@ class State(C.Structure):
 class StepIn(C.Structure):
     _fields_ = [("actions", C.c_void_p), ("retarget", C.c_void_p), ("slab", C.c_void_p),
                 ("w_attraction", C.c_double), ("w_repulsion", C.c_double), ("w_alignment", C.c_double),
-                ("vf_size", C.c_int32)]
+                ("vf_size", C.c_int32), ("rng_step", C.c_uint32), ("rng_seed", C.c_uint64)]
 
 
 class StepOut(C.Structure):
@@ -67,6 +67,7 @@ EXPORTS = {
     "swarm_abi_version": (C.c_int, []),
     "swarm_bind_state": (C.c_int, [_VP, C.POINTER(State)]),
     "swarm_bind_reset_tapes": (C.c_int, [_VP, _VP, _VP]),
+    "swarm_set_device_reset_tapes": (C.c_int, [_VP, C.c_uint64]),
     "swarm_reset": (C.c_int, [_VP, _VP]),
     "swarm_step": (C.c_int, [_VP, C.POINTER(StepIn), C.POINTER(StepOut), _VP]),
     "swarm_path_name": (C.c_char_p, [_VP]),

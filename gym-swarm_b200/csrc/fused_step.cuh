@@ -268,13 +268,12 @@ __device__ __noinline__ void reset_group(const StepParams& p, const Seg<LPE>& g,
   unsigned rc = p.reset_count[env];
   g.sync();   // every lane has read reset_count before lane 0 bumps it
   if (g.li == 0) p.reset_count[env] = rc + 1u;
-  const size_t slot = (size_t)(rc % (unsigned)p.R) * (size_t)p.E + (size_t)env;
-  const int16_t* __restrict__ tape = p.place + slot * (size_t)p.PL;
+  const int16_t* __restrict__ tape = place_row(p, env, rc);
 #pragma unroll
   for (int k = 0; k < APL; ++k) {
     const bool v = i0 + k < N;
-    x[k] = v ? (int)tape[i0 + k] : 0;          // SDE:202-203: all x's then all y's
-    y[k] = v ? (int)tape[N + i0 + k] : 0;
+    x[k] = v ? tape_place(p, tape, env, rc, i0 + k) : 0;          // SDE:202-203: all x's then all y's
+    y[k] = v ? tape_place(p, tape, env, rc, N + i0 + k) : 0;
   }
   int cur = 2 * N;
   for (;;) {
@@ -292,19 +291,19 @@ __device__ __noinline__ void reset_group(const StepParams& p, const Seg<LPE>& g,
       const int e = c[k] - 1;
       if (e > 0) {                                // SDE:208-209: (2,L) block, last duplicate wins
         const int s = off + e - 1;
-        x[k] = tape[cur + s];
-        y[k] = tape[cur + L + s];
+        x[k] = tape_place(p, tape, env, rc, cur + s);
+        y[k] = tape_place(p, tape, env, rc, cur + L + s);
       }
       off += e;
     }
     cur += 2 * L;
   }
-  const int16_t* __restrict__ pt = p.ptape + slot * (size_t)p.KP * 2;
+  const int16_t* __restrict__ pt = ptape_row(p, env, rc);
   int a = 0;
   px = 0; py = 0;
   for (;;) {                                      // SDE:92-105
     if (a >= p.KP) { err |= SWARM_ERR_PRED_OVERFLOW; break; }
-    px = pt[2 * a]; py = pt[2 * a + 1];
+    tape_pred(p, pt, env, rc, a, px, py);
     ++a;
     bool hit = false;
 #pragma unroll
@@ -375,7 +374,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
   load_u8<APL>(p.actions + base, i0, N, vec, act);
   int px = p.px[env], py = p.py[env];
   int target = p.target[env];
-  const int retarget = p.retarget[env];
+  const int retarget = tape_retarget(p, env);
   unsigned err = 0;
 
   // ---- move + collision re-draw rounds (SDE:237-255) --------------------------------------------
@@ -412,7 +411,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
     for (int k = 0; k < APL; ++k) {
       const int e = c[k] - 1;
-      if (e > 0) eff[k] = slab[cur + off + e - 1] & 7;   // SDE:250-252: last of its c-1 draws wins
+      if (e > 0) eff[k] = tape_slab(p, slab, env, cur + off + e - 1);   // SDE:250-252: last of its c-1 draws wins
       off += e;
     }
     cur += L;

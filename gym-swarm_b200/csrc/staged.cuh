@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(1024) collide_kernel(const StepParams p, const
         for (int i = lo; i < hi; ++i) {
           const int e = hash_c(h, i) - 1;
           if (e > 0) {                                       // SDE:250-255
-            const int a = slab[cur + off + e - 1] & 7;
+            const int a = tape_slab(p, slab, env, cur + off + e - 1);
             eff[i] = (uint8_t)a;
             nx[i] = (int16_t)wrap1((int)p.x[base + i] + move_dx(a), S);
             ny[i] = (int16_t)wrap1((int)p.y[base + i] + move_dy(a), S);
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p
         for (int i = lo; i < hi; ++i) {
           const int e = (int)((cpack >> (4 * (i - lo))) & 15ull);
           if (e > 0) {                                       // SDE:250-255
-            const int a = slab[cur + off + e - 1] & 7;
+            const int a = tape_slab(p, slab, env, cur + off + e - 1);
             eff[i] = (uint8_t)a;
             nx[i] = (int16_t)wrap1((int)p.x[base + i] + move_dx(a), S);
             ny[i] = (int16_t)wrap1((int)p.y[base + i] + move_dy(a), S);
@@ -454,7 +454,8 @@ __global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p
 struct PredIO {
   int E, N, S;
   const int16_t *xo, *yo, *xn, *yn;
-  const uint8_t *retarget, *frozen;
+  const uint8_t *retarget, *frozen;   // retarget == NULL: Philox stream 1 (rng_* below)
+  unsigned rng_seed_lo, rng_seed_hi, rng_step;
   int16_t *px, *py;
   int32_t* target;
   uint8_t* orient;
@@ -470,6 +471,11 @@ __device__ __forceinline__ unsigned warp_umin(unsigned v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
   return v;
+}
+
+__device__ __forceinline__ int pred_retarget(const PredIO& io, int env) {
+  if (io.retarget) return io.retarget[env];
+  return philox4x32_10(make_uint4((unsigned)env, io.rng_step, 0u, 1u), io.rng_seed_lo, io.rng_seed_hi).x < 429496730u;
 }
 
 // 8 packed agents (one uint4 of x, one of y) against the predator cell: nearest-neighbour keys
@@ -545,7 +551,7 @@ __global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
   const uint4* __restrict__ yo4 = reinterpret_cast<const uint4*>(io.yo) + vbase;
   int px = io.px[env], py = io.py[env];
   int target = io.target[env];
-  const int retarget = io.retarget[env];
+  const int retarget = pred_retarget(io, env);
   target = min(max(target, 0), N - 1);
   uint4 xn[PRED_VPL], yn[PRED_VPL];
 #pragma unroll
@@ -608,7 +614,7 @@ __global__ void __launch_bounds__(256) predator_block_kernel(const PredIO io) {
     int px = io.px[env], py = io.py[env];
     int target = io.target[env];
     const int ppx = px, ppy = py;
-    if (io.retarget[env]) {
+    if (pred_retarget(io, env)) {
       unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;
 #pragma unroll 4
       for (int v = threadIdx.x; v < NV; v += blockDim.x) nn_keys8(__ldg(xo4 + v), __ldg(yo4 + v), px, py, v * 8, klo, khi);
@@ -647,7 +653,7 @@ __global__ void __launch_bounds__(256) predator_kernel(const PredIO io) {
   int px = io.px[env], py = io.py[env];
   int target = io.target[env];
   const int ppx = px, ppy = py;
-  if (io.retarget[env]) {                                      // SDE:138-140
+  if (pred_retarget(io, env)) {                                      // SDE:138-140
     unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;
     for (int i = lane; i < N; i += 32) {
       const int d = max(iabs(px - (int)io.xo[base + i]), iabs(py - (int)io.yo[base + i]));
@@ -1238,10 +1244,12 @@ __global__ void __launch_bounds__(1024) reset_kernel(const StepParams p, const S
     unsigned rc = mode == 0 ? 0u : p.reset_count[env];
     __syncthreads();
     if (threadIdx.x == 0) p.reset_count[env] = rc + 1u;
-    const size_t slot = (size_t)(rc % (unsigned)p.R) * (size_t)p.E + (size_t)env;
-    const int16_t* __restrict__ tape = p.place + slot * (size_t)p.PL;
+    const int16_t* __restrict__ tape = place_row(p, env, rc);
     unsigned err = 0;
-    for (int i = lo; i < hi; ++i) { x[i] = tape[i]; y[i] = tape[N + i]; }   // SDE:202-203
+    for (int i = lo; i < hi; ++i) {                                         // SDE:202-203
+      x[i] = (int16_t)tape_place(p, tape, env, rc, i);
+      y[i] = (int16_t)tape_place(p, tape, env, rc, N + i);
+    }
     int cur = 2 * N;
     for (;;) {
       const int extra = hash_count_extra(h, lo, hi, [&](int i) { return pack2(x[i], y[i]); });
@@ -1253,8 +1261,8 @@ __global__ void __launch_bounds__(1024) reset_kernel(const StepParams p, const S
           const int e = hash_c(h, i) - 1;
           if (e > 0) {                                // SDE:208-209
             const int s = off + e - 1;
-            x[i] = tape[cur + s];
-            y[i] = tape[cur + L + s];
+            x[i] = (int16_t)tape_place(p, tape, env, rc, cur + s);
+            y[i] = (int16_t)tape_place(p, tape, env, rc, cur + L + s);
           }
           off += e;
         }
@@ -1264,11 +1272,11 @@ __global__ void __launch_bounds__(1024) reset_kernel(const StepParams p, const S
       if (overflow) { err |= SWARM_ERR_PLACE_OVERFLOW; break; }
       cur += 2 * L;
     }
-    const int16_t* __restrict__ pt = p.ptape + slot * (size_t)p.KP * 2;
+    const int16_t* __restrict__ pt = ptape_row(p, env, rc);
     int a = 0, px = 0, py = 0;
     for (;;) {                                        // SDE:92-105
       if (a >= p.KP) { err |= SWARM_ERR_PRED_OVERFLOW; break; }
-      px = pt[2 * a]; py = pt[2 * a + 1];
+      tape_pred(p, pt, env, rc, a, px, py);
       ++a;
       int hit = 0;
       for (int i = lo; i < hi; ++i) hit |= ((int)x[i] == px && (int)y[i] == py);

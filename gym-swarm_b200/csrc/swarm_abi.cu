@@ -22,6 +22,8 @@ struct Ctx {
   bool has_state = false;
   const int16_t* place = nullptr;
   const int16_t* ptape = nullptr;
+  bool dev_reset = false;     // reset tapes drawn in-kernel (swarm_set_device_reset_tapes)
+  uint64_t rst_seed = 0;
   std::string err;
   std::string path_name;
   bool fused = false;
@@ -124,6 +126,7 @@ static StepParams base_params(const Ctx* c) {
   p.frozen = s.frozen; p.err = s.err; p.reset_count = s.reset_count;
   p.ep_len = s.ep_len; p.ep_ret = s.ep_ret; p.fin_count = s.fin_count; p.fin_len = s.fin_len; p.fin_ret = s.fin_ret;
   p.place = c->place; p.ptape = c->ptape;
+  p.rst_seed_lo = (unsigned)(c->rst_seed & 0xFFFFFFFFull); p.rst_seed_hi = (unsigned)(c->rst_seed >> 32);
   return p;
 }
 
@@ -478,6 +481,17 @@ int swarm_bind_reset_tapes(swarm_handle h, const int16_t* place, const int16_t* 
   if (!c || !place || !ptape) return fail(c, SWARM_E_INVALID, "swarm_bind_reset_tapes: null argument");
   c->place = place;
   c->ptape = ptape;
+  c->dev_reset = false;
+  return SWARM_OK;
+}
+
+int swarm_set_device_reset_tapes(swarm_handle h, uint64_t seed) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c) return fail(c, SWARM_E_INVALID, "swarm_set_device_reset_tapes: null handle");
+  c->place = nullptr;
+  c->ptape = nullptr;
+  c->dev_reset = true;
+  c->rst_seed = seed;
   return SWARM_OK;
 }
 
@@ -492,7 +506,8 @@ int swarm_last_launch_count(swarm_handle h) {
 }
 
 static int do_reset(Ctx* c, const uint8_t* mask, int mode, cudaStream_t s) {
-  if (!c->has_state || !c->place || !c->ptape) return fail(c, SWARM_E_STATE, "reset: bind state and reset tapes first");
+  if (!c->has_state || (!c->dev_reset && (!c->place || !c->ptape)))
+    return fail(c, SWARM_E_STATE, "reset: bind state and reset tapes first");
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   StepParams p = base_params(c);
   c->launches = 0;
@@ -524,10 +539,11 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
   Ctx* c = reinterpret_cast<Ctx*>(h);
   if (!c || !in || !out) return fail(c, SWARM_E_INVALID, "swarm_step: null argument");
   if (!c->has_state) return fail(c, SWARM_E_STATE, "swarm_step: bind state first");
-  if (c->cfg.auto_reset && (!c->place || !c->ptape))
+  if (c->cfg.auto_reset && !c->dev_reset && (!c->place || !c->ptape))
     return fail(c, SWARM_E_STATE, "swarm_step: auto_reset needs bound reset tapes");
-  if (!in->actions || !in->retarget || (!in->slab && c->cfg.slab_len > 0))
-    return fail(c, SWARM_E_INVALID, "swarm_step: null input tape");
+  const bool dev_tapes = !in->retarget && !in->slab;          // both step tapes drawn in-kernel (Philox)
+  if (!in->actions || (!dev_tapes && (!in->retarget || (!in->slab && c->cfg.slab_len > 0))))
+    return fail(c, SWARM_E_INVALID, "swarm_step: null input tape (pass retarget and slab, or neither for device tapes)");
   if (!out->done || !out->eaten || !out->reward || !out->counts || !out->pred_prev || !out->pred_next ||
       !out->step_orient || !out->step_target || !out->consumed)
     return fail(c, SWARM_E_INVALID, "swarm_step: a required output pointer is null");
@@ -537,6 +553,8 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   StepParams p = base_params(c);
   p.actions = in->actions; p.retarget = in->retarget; p.slab = in->slab;
+  p.rng_seed_lo = (unsigned)(in->rng_seed & 0xFFFFFFFFull); p.rng_seed_hi = (unsigned)(in->rng_seed >> 32);
+  p.rng_step = in->rng_step;
   p.w_att = in->w_attraction; p.w_rep = in->w_repulsion; p.w_ali = in->w_alignment;
   p.t_vf = in->vf_size < 0 ? -1 : clampi(in->vf_size >= p.S ? p.S : in->vf_size + 1, 0, p.S);
   p.done = out->done; p.eaten = out->eaten; p.reward = out->reward; p.counts = out->counts;
@@ -586,6 +604,7 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     PredIO io;
     io.E = p.E; io.N = p.N; io.S = p.S; io.xo = p.x; io.yo = p.y; io.xn = sc.nx; io.yn = sc.ny;
     io.retarget = p.retarget; io.frozen = p.frozen; io.px = p.px; io.py = p.py; io.target = p.target;
+    io.rng_seed_lo = p.rng_seed_lo; io.rng_seed_hi = p.rng_seed_hi; io.rng_step = p.rng_step;
     io.orient = p.orient; io.pred_prev = p.pred_prev; io.pred_next = p.pred_next; io.step_orient = p.step_orient;
     io.step_target = p.step_target; io.done = p.done; io.eaten = p.eaten; io.err = p.err;
     launch_predator(io, c->num_sms, s);

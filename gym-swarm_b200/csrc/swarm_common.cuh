@@ -50,6 +50,11 @@ struct StepParams {
   int K, PL, KP, R;
   int auto_reset, track_stats;
   int bitmap_words;  // per-env smem occupancy bitmap words (0: not used)
+  // counter-based tapes: when a tape pointer is NULL the draw is computed in the kernel by
+  // Philox4x32-10 keyed with rng_seed; the host can materialise the identical tapes (tapes.philox_*).
+  unsigned rng_seed_lo, rng_seed_hi;   // step streams (retarget, slab): counter (env, rng_step, block, 1)
+  unsigned rng_step;
+  unsigned rst_seed_lo, rst_seed_hi;   // reset streams (place: stream 2, ptape: stream 3): counter (env, reset index, block, stream)
   BoxPlan box;       // fused kernels: box-count reward path (needs the per-env bitmap, bitmap_words > 0)
   int one;           // runtime 1: `v * one + acc` compiles to IMAD (FMA pipe) instead of IADD3 (ALU pipe)
   // state
@@ -75,6 +80,34 @@ struct StepParams {
   int32_t* agent_counts;
   uint8_t* eff_action;
 };
+
+// ----------------------------------------------------------------------------------------------
+// Counter-based tapes: Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11).
+// A draw is a pure function of (seed, stream, env, index), so the kernels need no tape memory and no RNG state;
+// gym-swarm_b200/tapes.py holds the NumPy twin that materialises the same values for the oracle.
+//   stream 1 (step n):    block 0 word 0 -> retarget flag (w < 0.1 * 2^32);  block 1 + k/16, byte k%16 -> slab[k] & 7
+//   stream 2 (reset r):   value i of the placement tape = (w * S) >> 32 with w = word i%4 of block i/4
+//   stream 3 (reset r):   predator attempt a = (x, y) from words 2(a%2), 2(a%2)+1 of block a/2
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, unsigned k0, unsigned k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ unsigned word_of(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+struct StepParams;
+__device__ __forceinline__ int tape_retarget(const StepParams& p, int env);
+__device__ __forceinline__ int tape_slab(const StepParams& p, const uint8_t* __restrict__ row, int env, int d);
+__device__ __forceinline__ int tape_place(const StepParams& p, const int16_t* __restrict__ row, int env, unsigned rc, int i);
+__device__ __forceinline__ void tape_pred(const StepParams& p, const int16_t* __restrict__ row, int env, unsigned rc, int a,
+                                          int& px, int& py);
 
 // ----------------------------------------------------------------------------------------------
 // Action table SDE:467-475 as 2-bit LUTs: (d+1) for action a sits at bits [2a, 2a+2).
@@ -242,6 +275,35 @@ __device__ __forceinline__ void box_direct_sweep(const BoxPlan& bp, const unsign
     for (int q = 0; q < 4; ++q)
       if (ady <= rq[q]) cnt[q] += __popc(win & mq[q]);      // uniform branch: rq and dy are the same for every lane
   }
+}
+
+// ---- tape accessors: a bound tape (row pointer) or the in-kernel Philox stream -----------------------------------
+__device__ __forceinline__ int tape_retarget(const StepParams& p, int env) {
+  if (p.retarget) return p.retarget[env];
+  return philox4x32_10(make_uint4((unsigned)env, p.rng_step, 0u, 1u), p.rng_seed_lo, p.rng_seed_hi).x < 429496730u;
+}
+__device__ __forceinline__ int tape_slab(const StepParams& p, const uint8_t* __restrict__ row, int env, int d) {
+  if (p.slab) return row[d] & 7;
+  const uint4 v = philox4x32_10(make_uint4((unsigned)env, p.rng_step, 1u + (unsigned)(d >> 4), 1u), p.rng_seed_lo, p.rng_seed_hi);
+  return (int)((word_of(v, (d >> 2) & 3) >> (8 * (d & 3))) & 7u);
+}
+__device__ __forceinline__ const int16_t* place_row(const StepParams& p, int env, unsigned rc) {
+  return p.place ? p.place + ((size_t)(rc % (unsigned)p.R) * (size_t)p.E + (size_t)env) * (size_t)p.PL : nullptr;
+}
+__device__ __forceinline__ const int16_t* ptape_row(const StepParams& p, int env, unsigned rc) {
+  return p.ptape ? p.ptape + ((size_t)(rc % (unsigned)p.R) * (size_t)p.E + (size_t)env) * (size_t)p.KP * 2 : nullptr;
+}
+__device__ __forceinline__ int tape_place(const StepParams& p, const int16_t* __restrict__ row, int env, unsigned rc, int i) {
+  if (row) return row[i];
+  const uint4 v = philox4x32_10(make_uint4((unsigned)env, rc, (unsigned)(i >> 2), 2u), p.rst_seed_lo, p.rst_seed_hi);
+  return (int)__umulhi(word_of(v, i & 3), (unsigned)p.S);
+}
+__device__ __forceinline__ void tape_pred(const StepParams& p, const int16_t* __restrict__ row, int env, unsigned rc, int a,
+                                          int& px, int& py) {
+  if (row) { px = row[2 * a]; py = row[2 * a + 1]; return; }
+  const uint4 v = philox4x32_10(make_uint4((unsigned)env, rc, (unsigned)(a >> 1), 3u), p.rst_seed_lo, p.rst_seed_hi);
+  px = (int)__umulhi((a & 1) ? v.z : v.x, (unsigned)p.S);
+  py = (int)__umulhi((a & 1) ? v.w : v.y, (unsigned)p.S);
 }
 
 }  // namespace swarm

@@ -59,12 +59,11 @@ __device__ __forceinline__ int tiny_closest(int N, int S, int qx, int qy, const 
 __device__ __forceinline__ void tiny_reset(const StepParams& p, int env, unsigned rc, int (&x)[TINY_N], int (&y)[TINY_N],
                                            int& px, int& py, int& target, unsigned& err) {
   const int N = p.N, S = p.S;
-  const size_t slot = (size_t)(rc % (unsigned)p.R) * (size_t)p.E + (size_t)env;
-  const int16_t* __restrict__ tape = p.place + slot * (size_t)p.PL;
+  const int16_t* __restrict__ tape = place_row(p, env, rc);
 #pragma unroll
   for (int k = 0; k < TINY_N; ++k) {
-    x[k] = k < N ? (int)tape[k] : 0;                 // SDE:202-203: all x's then all y's
-    y[k] = k < N ? (int)tape[N + k] : 0;
+    x[k] = k < N ? tape_place(p, tape, env, rc, k) : 0;       // SDE:202-203: all x's then all y's
+    y[k] = k < N ? tape_place(p, tape, env, rc, N + k) : 0;
   }
   int cur = 2 * N;
   for (;;) {
@@ -81,19 +80,19 @@ __device__ __forceinline__ void tiny_reset(const StepParams& p, int env, unsigne
       const int e = c[k] - 1;
       if (e > 0) {                                    // SDE:208-209: (2,L) block, last duplicate wins
         const int s = off + e - 1;
-        x[k] = tape[cur + s];
-        y[k] = tape[cur + L + s];
+        x[k] = tape_place(p, tape, env, rc, cur + s);
+        y[k] = tape_place(p, tape, env, rc, cur + L + s);
       }
       off += e;
     }
     cur += 2 * L;
   }
-  const int16_t* __restrict__ pt = p.ptape + slot * (size_t)p.KP * 2;
+  const int16_t* __restrict__ pt = ptape_row(p, env, rc);
   int a = 0;
   px = 0; py = 0;
   for (;;) {                                          // SDE:92-105
     if (a >= p.KP) { err |= SWARM_ERR_PRED_OVERFLOW; break; }
-    px = pt[2 * a]; py = pt[2 * a + 1];
+    tape_pred(p, pt, env, rc, a, px, py);
     ++a;
     bool hit = false;
 #pragma unroll
@@ -146,7 +145,7 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   }
   int px = p.px[env], py = p.py[env];
   int target = p.target[env];
-  const int retarget = p.retarget[env];
+  const int retarget = tape_retarget(p, env);
   // everything else the step will read, issued now so that one DRAM round trip covers all of it
   unsigned ep_len0 = 0u;
   float4 ep_ret0 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -173,7 +172,7 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   // predator has been computed, so the load's latency is hidden
   const uint8_t* __restrict__ slab = p.slab + (size_t)env * (size_t)p.K;
   unsigned long long slab8 = 0ull;
-  const bool slab_vec = p.K >= 8 && (((uintptr_t)slab) & 7) == 0;
+  const bool slab_vec = p.slab != nullptr && p.K >= 8 && (((uintptr_t)slab) & 7) == 0;
   if (L > 0 && slab_vec) {
     const uint2 v = *reinterpret_cast<const uint2*>(slab);
     slab8 = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
@@ -203,7 +202,7 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
       const int e = c[k] - 1;
       if (e > 0) {                                        // SDE:250-252: last of its c-1 draws wins
         const int d = cur + off + e - 1;
-        const int a = (slab_vec && d < 8) ? (int)((slab8 >> (8 * d)) & 7ull) : (int)(slab[d] & 7);
+        const int a = (slab_vec && d < 8) ? (int)((slab8 >> (8 * d)) & 7ull) : tape_slab(p, slab, env, d);
         eff[k] = a;
         nx[k] = wrap1(x[k] + move_dx(a), S);
         ny[k] = wrap1(y[k] + move_dy(a), S);

@@ -58,7 +58,7 @@ class BatchedSwarmEnv:
     def __init__(self, num_envs, num_agents=4, obs_space_size=20, attraction_thresh=5, repulsion_thresh=2,
                  predator_eat_rew=-10, device="cuda:0", auto_reset=True, track_stats=False, slab_len=None,
                  place_extra=None, pred_attempts=8, reset_slots=4, per_agent=True, debug_outputs=False,
-                 path="auto", seed=0, tape_chunk=16):
+                 path="auto", seed=0, tape_chunk=16, device_tapes=False):
         self.lib = _lib.load()                      # raises when the CUDA library is missing
         if not torch.cuda.is_available():
             raise _lib.SwarmLibraryError("no CUDA device: the swarm transition has no CPU fallback")
@@ -73,6 +73,11 @@ class BatchedSwarmEnv:
         self.KP, self.R = int(pred_attempts), int(reset_slots)
         self.per_agent, self.debug_outputs = bool(per_agent), bool(debug_outputs)
         self._rng = np.random.default_rng(seed)
+        # device_tapes: every random draw of the transition is computed inside the kernels by Philox4x32-10 keyed with
+        # ``seed`` (no tape memory, no host draws); tapes.philox_* materialise the identical values on the host
+        self.device_tapes = bool(device_tapes)
+        self.seed = int(seed)
+        self.step_index = 0
         self._tape_chunk = int(tape_chunk)
         self._chunk = None
         self._chunk_pos = 0
@@ -153,6 +158,11 @@ class BatchedSwarmEnv:
         _lib.check(self.lib.swarm_bind_reset_tapes(self._h, _ptr(place), _ptr(ptape)), self._h)
 
     def _ensure_reset_tapes(self):
+        if self.device_tapes and self._place is None:
+            if not getattr(self, "_dev_reset_bound", False):
+                _lib.check(self.lib.swarm_set_device_reset_tapes(self._h, C.c_uint64(self.reset_seed)), self._h)
+                self._dev_reset_bound = True
+            return
         if self._place is None:
             if self.R * self.E * self.PL <= (1 << 24):
                 rt = _tapes.make_reset_tapes(self._rng, self.R, self.E, self.N, self.S, KR=self.KR, KP=self.KP)
@@ -185,6 +195,11 @@ class BatchedSwarmEnv:
         self._chunk_pos += 1
         return r, s
 
+    @property
+    def reset_seed(self):
+        """Key of the in-kernel reset streams (placement, predator attempts) in device_tapes mode."""
+        return (self.seed * 0x9E3779B97F4A7C15 + 1) & 0xFFFFFFFFFFFFFFFF
+
     # ---- Gym-style surface (tensor I/O) ----------------------------------------------------------
     def reset(self):
         """SDE:197-221 for every env. Returns the observation (x, y): int16[E,N] views of the state."""
@@ -207,16 +222,21 @@ class BatchedSwarmEnv:
         vf = rt.get("vf_size", None)
         actions = _as_dev(actions, torch.uint8, self.device)
         assert tuple(actions.shape) == (self.E, self.N), tuple(actions.shape)
-        if retarget is None or slab is None:
-            r2, s2 = self._next_step_tapes()
-            retarget = r2 if retarget is None else retarget
-            slab = s2 if slab is None else slab
-        retarget = _as_dev(retarget, torch.uint8, self.device)
-        slab = _as_dev(slab, torch.uint8, self.device)
-        assert tuple(retarget.shape) == (self.E,) and tuple(slab.shape) == (self.E, self.K), (retarget.shape, slab.shape)
+        if self.device_tapes and retarget is None and slab is None:
+            retarget = slab = None                      # drawn in the kernels: Philox(seed, step_index)
+        else:
+            if retarget is None or slab is None:
+                r2, s2 = self._next_step_tapes()
+                retarget = r2 if retarget is None else retarget
+                slab = s2 if slab is None else slab
+            retarget = _as_dev(retarget, torch.uint8, self.device)
+            slab = _as_dev(slab, torch.uint8, self.device)
+            assert tuple(retarget.shape) == (self.E,) and tuple(slab.shape) == (self.E, self.K), (retarget.shape, slab.shape)
         sin = _lib.StepIn(actions=_ptr(actions), retarget=_ptr(retarget), slab=_ptr(slab),
                           w_attraction=float(rt["attraction"]), w_repulsion=float(rt["repulsion"]),
-                          w_alignment=float(rt["alignment"]), vf_size=-1 if vf is None else int(math.floor(vf)))
+                          w_alignment=float(rt["alignment"]), vf_size=-1 if vf is None else int(math.floor(vf)),
+                          rng_step=self.step_index & 0xFFFFFFFF, rng_seed=self.seed & 0xFFFFFFFFFFFFFFFF)
+        self.step_index += 1
         self._keep = (actions, retarget, slab)      # keep inputs alive until the kernels ran
         _lib.check(self.lib.swarm_step(self._h, C.byref(sin), C.byref(self._out), self._stream()), self._h)
         reward = {"global": self.reward, "agents": self.agent_reward, "counts": self.counts}
@@ -271,7 +291,7 @@ class BatchedSwarmEnv:
         generator and the unconsumed part of the current tape chunk."""
         torch.cuda.synchronize(self.device)
         d = {"shape": (self.E, self.N, self.S), "tensors": {}, "rng": self._rng.bit_generator.state,
-             "chunk_pos": self._chunk_pos}
+             "chunk_pos": self._chunk_pos, "seed": self.seed, "step_index": self.step_index}
         for k in self._STATE_TENSORS:
             t = getattr(self, k)
             if t is not None:
@@ -288,6 +308,8 @@ class BatchedSwarmEnv:
         if d["place"] is not None:
             self.set_reset_tapes(d["place"], d["ptape"])
         self._rng.bit_generator.state = d["rng"]
+        self.seed, self.step_index = d.get("seed", self.seed), d.get("step_index", self.step_index)
+        self._dev_reset_bound = False
         self._chunk = None if d["chunk"] is None else tuple(t.to(self.device) for t in d["chunk"])
         self._chunk_pos = d["chunk_pos"]
 

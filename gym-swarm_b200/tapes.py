@@ -70,3 +70,65 @@ def make_step_tapes(rng: np.random.Generator, T: int, E: int, N: int, K: int | N
     retarget = (roll < p_retarget).astype(np.uint8)
     slab = rng.integers(0, 8, size=(T, E, K), dtype=np.uint8)
     return StepTapes(actions, retarget, slab, roll)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Counter-based tapes: the NumPy twin of the in-kernel Philox4x32-10 streams of
+# gym-swarm_b200/csrc/swarm_common.cuh.  A draw is a pure function of (seed, stream, env, index); these functions
+# materialise exactly the values the kernels compute when no tape is bound, so the oracle can be fed the same draws.
+# ------------------------------------------------------------------------------------------------------
+_M32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al., SC'11) on uint32 arrays (broadcast); returns the four output words."""
+    c0, c1, c2, c3 = (np.asarray(v, dtype=np.uint64) & _M32 for v in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0) & _M32, np.uint64(k1) & _M32
+    c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c0
+        p1 = np.uint64(0xCD9E8D57) * c2
+        c0, c1, c2, c3 = (p1 >> np.uint64(32)) ^ c1 ^ k0, p1 & _M32, (p0 >> np.uint64(32)) ^ c3 ^ k1, p0 & _M32
+        k0 = (k0 + np.uint64(0x9E3779B9)) & _M32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & _M32
+    return tuple(v.astype(np.uint32) for v in (c0, c1, c2, c3))
+
+
+def _key(seed):
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return seed & 0xFFFFFFFF, seed >> 32
+
+
+def philox_step_tapes(seed, step, E, K):
+    """(retarget u8[E], slab u8[E,K]) of step ``step``: stream 1, counter (env, step, block, 1)."""
+    k0, k1 = _key(seed)
+    env = np.arange(E, dtype=np.uint64)
+    retarget = (philox4x32_10(env, step, 0, 1, k0, k1)[0] < np.uint32(429496730)).astype(np.uint8)
+    slab = np.zeros((E, K), dtype=np.uint8)
+    for blk in range((K + 15) // 16):
+        w = philox4x32_10(env, step, 1 + blk, 1, k0, k1)
+        for d in range(16 * blk, min(K, 16 * blk + 16)):
+            slab[:, d] = ((w[(d >> 2) & 3] >> np.uint32(8 * (d & 3))) & np.uint32(7)).astype(np.uint8)
+    return retarget, slab
+
+
+def philox_reset_tapes(seed, R, E, N, S, KR=None, KP=8):
+    """ResetTapes for reset indices 0..R-1: stream 2 (placement) and stream 3 (predator attempts).  The device uses the
+    reset index itself as the stream counter, so these equal its draws as long as no env resets more than R times."""
+    KR = default_place_extra(N) if KR is None else KR
+    PL = 2 * N + 2 * KR
+    k0, k1 = _key(seed)
+    env = np.arange(E, dtype=np.uint64)
+    place = np.zeros((R, E, PL), dtype=np.int16)
+    ptape = np.zeros((R, E, KP, 2), dtype=np.int16)
+    for r in range(R):
+        for blk in range((PL + 3) // 4):
+            w = philox4x32_10(env, r, blk, 2, k0, k1)
+            for i in range(4 * blk, min(PL, 4 * blk + 4)):
+                place[r, :, i] = ((w[i & 3].astype(np.uint64) * np.uint64(S)) >> np.uint64(32)).astype(np.int16)
+        for blk in range((KP + 1) // 2):
+            w = philox4x32_10(env, r, blk, 3, k0, k1)
+            for a in range(2 * blk, min(KP, 2 * blk + 2)):
+                ptape[r, :, a, 0] = ((w[2 * (a & 1)].astype(np.uint64) * np.uint64(S)) >> np.uint64(32)).astype(np.int16)
+                ptape[r, :, a, 1] = ((w[2 * (a & 1) + 1].astype(np.uint64) * np.uint64(S)) >> np.uint64(32)).astype(np.int16)
+    return ResetTapes(place, ptape, np.zeros((R, E, N), dtype=np.uint8))

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SWARM_ABI_VERSION 1
+#define SWARM_ABI_VERSION 2
 
 /* return codes */
 #define SWARM_OK 0
@@ -104,10 +104,14 @@ typedef struct swarm_step_in {
   const uint8_t* actions;  /* [E,N] action ids 0..8 (SDE:467-475) */
   const uint8_t* retarget; /* [E]   1 iff the reference's np.random.random() < 0.1 (SDE:138-139) */
   const uint8_t* slab;     /* [E,K] re-draw actions 0..7 in consumption order (SDE:250) */
+                           /* retarget == slab == NULL: both tapes are drawn in the kernels by Philox4x32-10 from
+                              (rng_seed, rng_step): counter-based, no tape memory (DESIGN.md "Tapes") */
   double w_attraction;     /* reward_type["attraction"] (bool or float: the reward curriculum) */
   double w_repulsion;      /* reward_type["repulsion"] */
   double w_alignment;      /* reward_type["alignment"] */
   int32_t vf_size;         /* floor(reward_type["vf_size"]) or -1 for None (SDE:349-355) */
+  uint32_t rng_step;       /* device tapes: index of this step (the caller increments it) */
+  uint64_t rng_seed;       /* device tapes: key of the step streams */
 } swarm_step_in;
 
 /* Per-step outputs; pointers marked (opt) may be NULL. */
@@ -139,6 +143,10 @@ int swarm_abi_version(void);
 int swarm_bind_state(swarm_handle h, const swarm_state* st);
 /* place: int16[R,E,PL]  ptape: int16[R,E,KP,2] */
 int swarm_bind_reset_tapes(swarm_handle h, const int16_t* place, const int16_t* ptape);
+
+/* Reset tapes drawn in the kernels instead (Philox4x32-10 keyed by seed, counter = (env, reset index, ...)): unbinds
+ * any bound reset tapes; the n-th reset of an env then uses stream index n (no wrap-around at reset_slots). */
+int swarm_set_device_reset_tapes(swarm_handle h, uint64_t seed);
 
 /* SDE:197-221 for every env (reset_count := 0, slot 0). */
 int swarm_reset(swarm_handle h, void* stream);

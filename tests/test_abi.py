@@ -41,7 +41,7 @@ def test_struct_layout_matches_header():
     # field counts / sizes of the ctypes mirrors (all pointers 8 bytes, int32/float 4, double 8)
     assert ctypes.sizeof(_lib.Config) == 15 * 4
     assert ctypes.sizeof(_lib.State) == 14 * 8
-    assert ctypes.sizeof(_lib.StepIn) == 3 * 8 + 3 * 8 + 8
+    assert ctypes.sizeof(_lib.StepIn) == 3 * 8 + 3 * 8 + 4 + 4 + 8
     assert ctypes.sizeof(_lib.StepOut) == 14 * 8
 
 

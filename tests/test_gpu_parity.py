@@ -156,6 +156,47 @@ def test_fused_box_count_thresholds(att, rep, monkeypatch):
     _oracle_lockstep(E=6, N=40, S=21, T=4, seed=att + rep, n_actions=9, att=att, rep=rep)
 
 
+@pytest.mark.parametrize("E,N,S,path", [(300, 8, 6, "auto"), (64, 5, 9, "group"), (40, 16, 8, "auto"), (9, 128, 40, "auto"),
+                                        (6, 200, 300, "auto"), (3, 300, 40, "auto"), (3, 300, 40, "staged_pairwise"),
+                                        (20, 12, 5, "staged")])
+def test_device_tapes_equal_host_materialised_tapes(E, N, S, path):
+    """Counter-based tapes: with no tape bound the kernels draw retarget flags, re-draw actions, placements and predator
+    attempts from Philox4x32-10; the NumPy twin materialises the same values, and the oracle fed with them reproduces
+    the trajectory (resets included: dense grids finish episodes quickly)."""
+    from gym_swarm_b200 import tapes
+    from gym_swarm_b200.envs import BatchedSwarmEnv
+    from oracle import swarm_oracle as so
+    T, R, seed = 25, 40, 1234 + N
+    dense = S * S < 6 * N
+    env = BatchedSwarmEnv(E, N, S, auto_reset=True, per_agent=True, debug_outputs=True, path=path, seed=seed,
+                          device_tapes=True, reset_slots=R, slab_len=512 if dense else None,
+                          place_extra=600 if dense else None, pred_attempts=32)
+    rt = tapes.philox_reset_tapes(env.reset_seed, R, E, N, S, KR=env.KR, KP=env.KP)
+    ora = so.OracleBatch(E, N, S, 5, 2, -10.0, True)
+    ora.set_reset_tapes(rt.place, rt.ptape)
+    env.reset()
+    a, b = env.state_numpy(), ora.reset()
+    for k in ("x", "y", "px", "py", "target"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=f"reset {k}")
+    act_rng = np.random.default_rng(seed)
+    for t in range(T):
+        actions = act_rng.integers(0, 9, size=(E, N), dtype=np.uint8)
+        retarget, slab = tapes.philox_step_tapes(seed, t, E, env.K)
+        env.step(actions, {"attraction": 1.0, "repulsion": 0.5, "alignment": 0.25, "vf_size": None})
+        a = env.state_numpy()
+        b = ora.step(actions, slab, retarget, (1.0, 0.5, 0.25), None, True)
+        for k in ("x", "y", "px", "py", "target"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg=f"step {t} {k}")
+        np.testing.assert_array_equal(env.done.cpu().numpy(), b["done"], err_msg=f"step {t} done")
+        np.testing.assert_array_equal(env.counts.cpu().numpy(), b["cnt"], err_msg=f"step {t} counts")
+        np.testing.assert_array_equal(env.consumed.cpu().numpy(), b["consumed"], err_msg=f"step {t} consumed")
+    assert int(ora.reset_count.max()) <= R, "raise R: the host twin only holds R reset slots"
+    if S <= 10:
+        assert int(ora.reset_count.sum()) > E, "no episode ended: the reset streams were not exercised"
+    assert not np.any(a["err"])
+    env.close()
+
+
 def test_staged_path_names():
     from gym_swarm_b200.envs import BatchedSwarmEnv
     for kw, name in ((dict(path="auto"), "staged+box"), (dict(path="staged_pairwise"), "staged+bitmap")):

@@ -87,3 +87,18 @@ def test_c_oracle_equals_numpy_oracle_on_fresh_tapes():
             np.testing.assert_allclose(oa["glob"], ob["glob"], rtol=1e-12, atol=1e-13)
             np.testing.assert_allclose(oa["agent"], ob["agent"], rtol=1e-12, atol=1e-13)
         b.close()
+
+
+def test_philox_known_answers():
+    """The NumPy twin of the in-kernel tape generator against Random123's published Philox4x32-10 vectors."""
+    from gym_swarm_b200 import tapes
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, out in kat:
+        assert tuple(int(v) for v in tapes.philox4x32_10(*ctr, *key)) == out
+    r, s = tapes.philox_step_tapes(5, 3, 4000, 40)
+    assert 0.07 < r.mean() < 0.13 and s.max() <= 7
+    rt = tapes.philox_reset_tapes(7, 2, 50, 8, 16)
+    assert rt.place.min() >= 0 and rt.place.max() < 16 and rt.ptape.shape == (2, 50, 8, 2)
