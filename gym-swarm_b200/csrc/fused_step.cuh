@@ -261,8 +261,8 @@ __device__ __forceinline__ int closest_target(const Seg<LPE>& g, int N, int S, i
 
 // ---- reference reset (SDE:197-221 + Predator.__init__ SDE:90-109) for one env group ---------------
 template <int LPE, int APL>
-__device__ __noinline__ void reset_group(const StepParams& p, const Seg<LPE>& g, int env, unsigned* skey, int i0,
-                                         int (&x)[APL], int (&y)[APL], int& px, int& py, int& target,
+__device__ __noinline__ void reset_group(const StepParams& p, const Seg<LPE>& g, int env, unsigned* skey, unsigned* sbit,
+                                         int i0, int (&x)[APL], int (&y)[APL], int& px, int& py, int& target,
                                          unsigned& err) {
   const int N = p.N, S = p.S;
   unsigned rc = p.reset_count[env];
@@ -278,7 +278,11 @@ __device__ __noinline__ void reset_group(const StepParams& p, const Seg<LPE>& g,
   int cur = 2 * N;
   for (;;) {
     int c[APL];
-    occupancy_counts<LPE, APL>(g, skey, N, i0, x, y, c);
+    if (sbit) {                                   // (clean) per-env bitmap of the step kernel: O(hits) instead of O(N)
+      if (!bitmap_counts<LPE, APL>(g, sbit, N, S, i0, x, y, c, false)) break;
+    } else {
+      occupancy_counts<LPE, APL>(g, skey, N, i0, x, y, c);
+    }
     int extra = 0;
 #pragma unroll
     for (int k = 0; k < APL; ++k) extra += c[k] - 1;
@@ -782,7 +786,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
       store_i16<APL>(p.term_y + base, i0, N, vec, ny);
     }
     if (p.auto_reset) {
-      reset_group<LPE, APL>(p, g, env, skey, i0, nx, ny, px, py, target, err);
+      reset_group<LPE, APL>(p, g, env, skey, p.bitmap_words ? sbit : nullptr, i0, nx, ny, px, py, target, err);
       orient = 0;                                           // SDE:107
     } else if (g.li == 0) {
       p.frozen[env] = 1;
@@ -821,7 +825,7 @@ fused_reset_kernel(const __grid_constant__ StepParams p, const uint8_t* __restri
   }
   int x[APL], y[APL], px, py, target;
   unsigned err = 0;
-  reset_group<LPE, APL>(p, g, env, skey, i0, x, y, px, py, target, err);
+  reset_group<LPE, APL>(p, g, env, skey, nullptr, i0, x, y, px, py, target, err);
   store_i16<APL>(p.x + base, i0, N, vec, x);
   store_i16<APL>(p.y + base, i0, N, vec, y);
   if (g.li == 0) {
