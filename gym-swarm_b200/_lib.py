@@ -76,6 +76,7 @@ EXPORTS = {
     "swarm_predator": (C.c_int, [_I32, _I32, _I32] + [_VP] * 13),
     "swarm_pairwise": (C.c_int, [_I32, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP]),
     "swarm_autoreset": (C.c_int, [_VP, _VP, _VP]),
+    "swarm_observe_vf": (C.c_int, [_I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP]),
     "swarm_stats_read": (C.c_int, [_VP, _DP, _VP]),
     "swarm_nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "swarm_nccl_init": (C.c_int, [_VP, C.POINTER(C.c_uint8), _I32, _I32]),

@@ -1327,4 +1327,46 @@ __global__ void __launch_bounds__(256) pair_counts_kernel(const StepParams p, co
   reinterpret_cast<int2*>(out)[i] = make_int2(t.rep_i, t.att_i);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Visual-field observations (README figure "SwarmEnv - 9 Agents - Visual Field 5x5",
+// gym_swarm/images/env_illustration.png -- the generating notebook is not in the reference tree, so the cell
+// codes below are this repo's definition): for every agent the egocentric (2 vf + 1)^2 window of the grid,
+//   0 = empty (or outside the grid: the distance is the plain, non-periodic Chebyshev one, as in SDE:349-355),
+//   1 = the agent itself (centre), 2 = another agent, 3 = the predator;  out[e, i, dy + vf, dx + vf].
+// One CTA per (env, 128-agent chunk): the env's positions and the chunk's windows live in shared memory, the
+// windows leave as one contiguous, coalesced store.  O(N) cell tests per agent, N <= OBS_MAX_AGENTS.
+// ------------------------------------------------------------------------------------------------
+constexpr int OBS_MAX_AGENTS = 4096;
+constexpr int OBS_CHUNK = 128;
+
+__global__ void __launch_bounds__(OBS_CHUNK) observe_vf_kernel(int E, int N, int vf, const int16_t* __restrict__ x,
+                                                               const int16_t* __restrict__ y, const int16_t* __restrict__ px,
+                                                               const int16_t* __restrict__ py, uint8_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char obs_smem[];
+  const int W = 2 * vf + 1, WW = W * W;
+  int* spos = reinterpret_cast<int*>(obs_smem);                   // [N] packed (x | y << 16)
+  unsigned char* swin = obs_smem + (size_t)N * 4;                 // [OBS_CHUNK][WW]
+  const int chunks = (N + OBS_CHUNK - 1) / OBS_CHUNK;
+  const int env = blockIdx.x / chunks, i0 = (blockIdx.x % chunks) * OBS_CHUNK;
+  const size_t base = (size_t)env * (size_t)N;
+  for (int j = threadIdx.x; j < N; j += OBS_CHUNK) spos[j] = (int)pack2(x[base + j], y[base + j]);
+  const int nwin = min(OBS_CHUNK, N - i0) * WW;
+  for (int q = threadIdx.x; q < nwin; q += OBS_CHUNK) swin[q] = 0;
+  __syncthreads();
+  const int i = i0 + threadIdx.x;
+  if (i < N) {
+    unsigned char* w = swin + (size_t)threadIdx.x * WW;
+    const int xi = (int)(int16_t)(spos[i] & 0xFFFF), yi = (int)(int16_t)((unsigned)spos[i] >> 16);
+    for (int j = 0; j < N; ++j) {
+      const int dx = (int)(int16_t)(spos[j] & 0xFFFF) - xi, dy = (int)(int16_t)((unsigned)spos[j] >> 16) - yi;
+      if (iabs(dx) <= vf && iabs(dy) <= vf) w[(dy + vf) * W + dx + vf] = (j == i) ? 1 : 2;
+    }
+    const int dx = (int)px[env] - xi, dy = (int)py[env] - yi;
+    if (iabs(dx) <= vf && iabs(dy) <= vf) w[(dy + vf) * W + dx + vf] = 3;
+  }
+  __syncthreads();
+  uint8_t* __restrict__ o = out + (base + i0) * (size_t)WW;
+  for (int q = threadIdx.x; q < nwin; q += OBS_CHUNK) o[q] = swin[q];
+}
+
 }  // namespace swarm

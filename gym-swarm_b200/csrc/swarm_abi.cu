@@ -714,6 +714,24 @@ int swarm_pairwise(int32_t E, int32_t N, int32_t S, int32_t attraction_thresh, i
   return SWARM_OK;
 }
 
+int swarm_observe_vf(int32_t E, int32_t N, int32_t S, int32_t vf, const int16_t* x, const int16_t* y, const int16_t* px,
+                     const int16_t* py, uint8_t* out, void* stream) {
+  if (E < 1 || N < 1 || N > OBS_MAX_AGENTS || S < 2 || vf < 0 || vf > 7 || !x || !y || !px || !py || !out)
+    return fail(nullptr, SWARM_E_INVALID, "swarm_observe_vf: bad argument (N <= 4096, 0 <= vf <= 7)");
+  const int W = 2 * vf + 1;
+  const int smem = N * 4 + OBS_CHUNK * W * W;
+  static int opted = 0;
+  if (smem > 48 * 1024 && opted < smem) {
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(observe_vf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    opted = smem;
+  }
+  const long long grid = (long long)E * ((N + OBS_CHUNK - 1) / OBS_CHUNK);
+  if (grid > 0x7FFFFFFFLL) return fail(nullptr, SWARM_E_INVALID, "swarm_observe_vf: too many agent chunks");
+  observe_vf_kernel<<<(int)grid, OBS_CHUNK, smem, (cudaStream_t)stream>>>(E, N, vf, x, y, px, py, out);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  return SWARM_OK;
+}
+
 // ---- statistics -----------------------------------------------------------------------------------------
 
 int swarm_stats_read(swarm_handle h, double out[8], void* stream) {

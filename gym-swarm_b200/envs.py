@@ -245,6 +245,17 @@ class BatchedSwarmEnv:
                 "terminal_state": (self.term_x, self.term_y), "redraws": self.consumed, "errors": self.err}
         return (self.x, self.y), reward, self.done, info
 
+    def observe_visual_field(self, vf_size=2, out=None):
+        """Egocentric occupancy windows of the current state: uint8[E,N,2vf+1,2vf+1], [dy+vf][dx+vf]; 0 empty / outside
+        the grid, 1 self, 2 other agent, 3 predator (README figure "Visual Field 5x5"; include/swarm_abi.h)."""
+        W = 2 * int(vf_size) + 1
+        if out is None:
+            out = torch.empty((self.E, self.N, W, W), dtype=torch.uint8, device=self.device)
+        assert tuple(out.shape) == (self.E, self.N, W, W) and out.dtype == torch.uint8 and out.is_contiguous()
+        _lib.check(self.lib.swarm_observe_vf(self.E, self.N, self.S, int(vf_size), _ptr(self.x), _ptr(self.y), _ptr(self.px),
+                                             _ptr(self.py), _ptr(out), self._stream()))
+        return out
+
     def last_launch_count(self):
         return int(self.lib.swarm_last_launch_count(self._h))
 

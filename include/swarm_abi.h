@@ -175,6 +175,13 @@ int swarm_pairwise(int32_t E, int32_t N, int32_t S, int32_t attraction_thresh, i
 /* SDE:197-221: reset the envs whose mask byte is non-zero (all if mask == NULL) from their next reset slot. */
 int swarm_autoreset(swarm_handle h, const uint8_t* mask, void* stream);
 
+/* Visual-field observations (the policy-side output after a step; README figure "Visual Field 5x5"): for every agent
+ * the egocentric (2*vf+1)^2 window, out uint8[E,N,2*vf+1,2*vf+1] indexed [dy+vf][dx+vf]: 0 empty / outside the grid
+ * (plain Chebyshev distance, as the vf gate of SDE:349-355), 1 the agent itself, 2 another agent, 3 the predator.
+ * N <= 4096, 0 <= vf <= 7.  The generating code is not in the reference tree: the codes are this library's definition. */
+int swarm_observe_vf(int32_t E, int32_t N, int32_t S, int32_t vf, const int16_t* x, const int16_t* y, const int16_t* px,
+                     const int16_t* py, uint8_t* out, void* stream);
+
 /* ---- episode statistics ---- */
 /* out[8] = episodes, sum length, sum return, sum survival, sum attraction, sum repulsion, sum alignment,
  * env-steps of running episodes.  Deterministic reduction; synchronises the stream. */

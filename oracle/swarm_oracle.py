@@ -366,3 +366,21 @@ class OracleBatch:
                 env.err |= keep
         o.update(self.state())
         return o
+
+
+def visual_field(x, y, px, py, S, vf):
+    """Egocentric (2vf+1)^2 windows, uint8[N, 2vf+1, 2vf+1] indexed [dy+vf][dx+vf]: 0 empty / outside the grid, 1 self,
+    2 other agent, 3 predator.  PARITY UNPINNED: the reference tree holds no code for this (only the README figure
+    gym_swarm/images/env_illustration.png, "Visual Field 5x5"; its ``vf_size`` gate at SDE:349-355 fixes the metric:
+    plain, non-periodic Chebyshev distance).  This function is the definition the CUDA kernel is tested against."""
+    N, W = len(x), 2 * vf + 1
+    out = np.zeros((N, W, W), dtype=np.uint8)
+    for i in range(N):
+        for j in range(N):
+            dx, dy = int(x[j]) - int(x[i]), int(y[j]) - int(y[i])
+            if abs(dx) <= vf and abs(dy) <= vf:
+                out[i, dy + vf, dx + vf] = 1 if j == i else 2
+        dx, dy = int(px) - int(x[i]), int(py) - int(y[i])
+        if abs(dx) <= vf and abs(dy) <= vf:
+            out[i, dy + vf, dx + vf] = 3
+    return out

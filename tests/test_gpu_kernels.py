@@ -114,3 +114,28 @@ def test_swarm_pairwise_matches_oracle(E, N, S, att, rep):
         r = so.swarm_reward(x[e].astype(np.int64), y[e].astype(np.int64), eff, -5, -5, N, S, att, rep, -10.0,
                             (1.0, 1.0, 1.0), None)
         np.testing.assert_array_equal(got[e], r["agent_cnt"], err_msg=f"env {e}")
+
+
+@pytest.mark.parametrize("E,N,S,vf", [(5, 9, 12, 2), (3, 4, 20, 0), (7, 8, 6, 1), (4, 128, 40, 2), (2, 300, 30, 3), (2, 130, 16, 7),
+                                      (1, 2048, 128, 2)])
+def test_visual_field_observation(E, N, S, vf):
+    """swarm_observe_vf / BatchedSwarmEnv.observe_visual_field against the oracle's definition (parity unpinned: the
+    reference tree has only the README figure for this output)."""
+    from gym_swarm_b200 import tapes
+    from gym_swarm_b200.envs import BatchedSwarmEnv
+    from oracle import swarm_oracle as so
+    rng = np.random.default_rng(N + vf)
+    env = BatchedSwarmEnv(E, N, S, reset_slots=2, place_extra=max(64, 4 * N), pred_attempts=32)
+    rt = tapes.make_reset_tapes(rng, 2, E, N, S, KR=env.KR, KP=env.KP)
+    env.set_reset_tapes(rt.place, rt.ptape)
+    env.reset()
+    for t in range(3):
+        if t:
+            env.step(rng.integers(0, 8, size=(E, N), dtype=np.uint8))
+        obs = env.observe_visual_field(vf).cpu().numpy()
+        st = env.state_numpy()
+        for e in range(E):
+            ref = so.visual_field(st["x"][e], st["y"][e], st["px"][e], st["py"][e], S, vf)
+            np.testing.assert_array_equal(obs[e], ref, err_msg=f"t={t} env {e}")
+        assert (obs[:, :, vf, vf] >= 1).all()          # the centre is the agent itself (or the predator on top of it)
+    env.close()

@@ -92,6 +92,22 @@ def run_predator(lib, dev, N=128, E=1 << 20, S=128):
             "achieved": alg / (mean * 1e-3) / 1e9, "peak": HBM, "unit": "GB/s", "frac": alg / (mean * 1e-3) / 1e9 / HBM}
 
 
+def run_observe(lib, dev, E=1 << 18, N=128, S=128, vf=2):
+    g = torch.Generator(device=dev).manual_seed(4)
+    x = torch.randint(0, S, (E, N), dtype=torch.int16, device=dev, generator=g)
+    y = torch.randint(0, S, (E, N), dtype=torch.int16, device=dev, generator=g)
+    px = torch.randint(0, S, (E,), dtype=torch.int16, device=dev, generator=g)
+    py = torch.randint(0, S, (E,), dtype=torch.int16, device=dev, generator=g)
+    W = 2 * vf + 1
+    out = torch.empty((E, N, W, W), dtype=torch.uint8, device=dev)
+    fn = lambda: _lib.check(lib.swarm_observe_vf(E, N, S, vf, ptr(x), ptr(y), ptr(px), ptr(py), ptr(out), stream()))
+    mean, best = timeit(fn)
+    alg = E * N * (4 + W * W) + E * 4                 # positions in, windows out
+    return {"kernel": "swarm_observe_vf (observe_vf_kernel)", "shape": f"{E} envs x {N} agents, S={S}, vf={vf}", "bound": "hbm",
+            "algorithmic_bytes": alg, "ms_mean": mean, "ms_best": best, "achieved": alg / (mean * 1e-3) / 1e9, "peak": HBM,
+            "unit": "GB/s", "frac": alg / (mean * 1e-3) / 1e9 / HBM}
+
+
 def int32_peaks(lib):
     out = {}
     for kind, name in ((0, "iadd3"), (1, "imnmx"), (2, "iadd3+imad"), (3, "viaddmnmx_s16x2"), (4, "viaddmnmx_s16x2+imad")):
@@ -126,7 +142,7 @@ def run_pairwise(lib, dev, peaks):
 
 
 def main():
-    which = sys.argv[1:] or ["peaks", "move", "predator", "pairwise"]
+    which = sys.argv[1:] or ["peaks", "move", "predator", "pairwise", "observe"]
     assert torch.cuda.is_available()
     dev = torch.device("cuda:0")
     lib = _lib.load()
@@ -146,6 +162,9 @@ def main():
         torch.cuda.empty_cache()
     if "pairwise" in which:
         print(json.dumps(run_pairwise(lib, dev, peaks)), flush=True)
+        torch.cuda.empty_cache()
+    if "observe" in which:
+        print(json.dumps(run_observe(lib, dev)), flush=True)
 
 
 if __name__ == "__main__":
