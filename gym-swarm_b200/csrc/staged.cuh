@@ -1339,27 +1339,58 @@ __global__ void __launch_bounds__(256) pair_counts_kernel(const StepParams p, co
 constexpr int OBS_MAX_AGENTS = 4096;
 constexpr int OBS_CHUNK = 128;
 
-__global__ void __launch_bounds__(OBS_CHUNK) observe_vf_kernel(int E, int N, int vf, const int16_t* __restrict__ x,
-                                                               const int16_t* __restrict__ y, const int16_t* __restrict__ px,
-                                                               const int16_t* __restrict__ py, uint8_t* __restrict__ out) {
+// BITMAP variant (S*S bits fit in shared memory): the CTA builds the env's occupancy bitmap once, every agent then
+// reads only the 2 vf + 1 rows of its window -- O(vf) instead of O(N) per agent, which makes the kernel HBM bound.
+template <bool BITMAP>
+__global__ void __launch_bounds__(OBS_CHUNK) observe_vf_kernel(int E, int N, int S, int vf, int bm_words,
+                                                               const int16_t* __restrict__ x, const int16_t* __restrict__ y,
+                                                               const int16_t* __restrict__ px, const int16_t* __restrict__ py,
+                                                               uint8_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char obs_smem[];
   const int W = 2 * vf + 1, WW = W * W;
   int* spos = reinterpret_cast<int*>(obs_smem);                   // [N] packed (x | y << 16)
-  unsigned char* swin = obs_smem + (size_t)N * 4;                 // [OBS_CHUNK][WW]
+  unsigned* sbit = reinterpret_cast<unsigned*>(spos + N);         // [bm_words] (BITMAP)
+  unsigned char* swin = reinterpret_cast<unsigned char*>(sbit + bm_words);   // [OBS_CHUNK][WW]
   const int chunks = (N + OBS_CHUNK - 1) / OBS_CHUNK;
   const int env = blockIdx.x / chunks, i0 = (blockIdx.x % chunks) * OBS_CHUNK;
   const size_t base = (size_t)env * (size_t)N;
-  for (int j = threadIdx.x; j < N; j += OBS_CHUNK) spos[j] = (int)pack2(x[base + j], y[base + j]);
+  if (BITMAP)
+    for (int w = threadIdx.x; w < bm_words; w += OBS_CHUNK) sbit[w] = 0u;
   const int nwin = min(OBS_CHUNK, N - i0) * WW;
   for (int q = threadIdx.x; q < nwin; q += OBS_CHUNK) swin[q] = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; j < N; j += OBS_CHUNK) {
+    const int xj = x[base + j], yj = y[base + j];
+    spos[j] = (int)pack2(xj, yj);
+    if (BITMAP) { const int cell = yj * S + xj; atomicOr(&sbit[cell >> 5], 1u << (cell & 31)); }
+  }
   __syncthreads();
   const int i = i0 + threadIdx.x;
   if (i < N) {
     unsigned char* w = swin + (size_t)threadIdx.x * WW;
     const int xi = (int)(int16_t)(spos[i] & 0xFFFF), yi = (int)(int16_t)((unsigned)spos[i] >> 16);
-    for (int j = 0; j < N; ++j) {
-      const int dx = (int)(int16_t)(spos[j] & 0xFFFF) - xi, dy = (int)(int16_t)((unsigned)spos[j] >> 16) - yi;
-      if (iabs(dx) <= vf && iabs(dy) <= vf) w[(dy + vf) * W + dx + vf] = (j == i) ? 1 : 2;
+    if (BITMAP) {
+      const int x0 = max(xi - vf, 0), x1 = min(xi + vf, S - 1);
+      for (int dy = -vf; dy <= vf; ++dy) {
+        const int yy = yi + dy;
+        if (yy < 0 || yy >= S) continue;
+        const int lo = yy * S + x0, hi = yy * S + x1;           // bit range of this window row (<= 15 bits)
+        const unsigned a = sbit[lo >> 5], b = sbit[hi >> 5];
+        unsigned bits = __funnelshift_r(a, b, lo & 31) & (0xFFFFFFFFu >> (31 - (x1 - x0)));
+        unsigned char* row = w + (dy + vf) * W + (x0 - xi + vf);
+        while (bits) {
+          const int c = __ffs(bits) - 1;
+          bits &= bits - 1u;
+          row[c] = 2;
+        }
+      }
+      w[vf * W + vf] = 1;
+    } else {
+      for (int j = 0; j < N; ++j) {
+        const int dx = (int)(int16_t)(spos[j] & 0xFFFF) - xi, dy = (int)(int16_t)((unsigned)spos[j] >> 16) - yi;
+        if (iabs(dx) <= vf && iabs(dy) <= vf) w[(dy + vf) * W + dx + vf] = 2;
+      }
+      w[vf * W + vf] = 1;                                       // the centre is the agent itself
     }
     const int dx = (int)px[env] - xi, dy = (int)py[env] - yi;
     if (iabs(dx) <= vf && iabs(dy) <= vf) w[(dy + vf) * W + dx + vf] = 3;

@@ -719,15 +719,21 @@ int swarm_observe_vf(int32_t E, int32_t N, int32_t S, int32_t vf, const int16_t*
   if (E < 1 || N < 1 || N > OBS_MAX_AGENTS || S < 2 || vf < 0 || vf > 7 || !x || !y || !px || !py || !out)
     return fail(nullptr, SWARM_E_INVALID, "swarm_observe_vf: bad argument (N <= 4096, 0 <= vf <= 7)");
   const int W = 2 * vf + 1;
-  const int smem = N * 4 + OBS_CHUNK * W * W;
-  static int opted = 0;
-  if (smem > 48 * 1024 && opted < smem) {
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(observe_vf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    opted = smem;
+  const long long cells = (long long)S * S;
+  const long long words = (cells + 31) / 32 + 1;
+  const bool bitmap = words * 4 <= 160 * 1024;                       // the env's occupancy bitmap fits in shared memory
+  const int bm_words = bitmap ? (int)words : 0;
+  const int smem = N * 4 + bm_words * 4 + OBS_CHUNK * W * W;
+  static int opted[2] = {0, 0};
+  if (smem > 48 * 1024 && opted[bitmap] < smem) {
+    if (bitmap) CUDA_TRY(nullptr, cudaFuncSetAttribute(observe_vf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else CUDA_TRY(nullptr, cudaFuncSetAttribute(observe_vf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    opted[bitmap] = smem;
   }
   const long long grid = (long long)E * ((N + OBS_CHUNK - 1) / OBS_CHUNK);
   if (grid > 0x7FFFFFFFLL) return fail(nullptr, SWARM_E_INVALID, "swarm_observe_vf: too many agent chunks");
-  observe_vf_kernel<<<(int)grid, OBS_CHUNK, smem, (cudaStream_t)stream>>>(E, N, vf, x, y, px, py, out);
+  if (bitmap) observe_vf_kernel<true><<<(int)grid, OBS_CHUNK, smem, (cudaStream_t)stream>>>(E, N, S, vf, bm_words, x, y, px, py, out);
+  else observe_vf_kernel<false><<<(int)grid, OBS_CHUNK, smem, (cudaStream_t)stream>>>(E, N, S, vf, 0, x, y, px, py, out);
   CUDA_TRY(nullptr, cudaGetLastError());
   return SWARM_OK;
 }

@@ -379,7 +379,8 @@ def visual_field(x, y, px, py, S, vf):
         for j in range(N):
             dx, dy = int(x[j]) - int(x[i]), int(y[j]) - int(y[i])
             if abs(dx) <= vf and abs(dy) <= vf:
-                out[i, dy + vf, dx + vf] = 1 if j == i else 2
+                out[i, dy + vf, dx + vf] = 2
+        out[i, vf, vf] = 1                               # the centre is the agent itself
         dx, dy = int(px) - int(x[i]), int(py) - int(y[i])
         if abs(dx) <= vf and abs(dy) <= vf:
             out[i, dy + vf, dx + vf] = 3
