@@ -346,11 +346,12 @@ __global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p
         int ax = 0, ay = 0, dx = 0, dy = 0;
         for (int i = lo; i < hi; ++i) {
           const int xi = nx[i], yi = ny[i];
-          uint4 c4;
-          c4.x = (unsigned)box_count(bp, 0, sbit, hx, hy, xi, yi, S, N);
-          c4.y = (unsigned)box_count(bp, 1, sbit, hx, hy, xi, yi, S, N);
-          c4.z = (unsigned)box_count(bp, 2, sbit, hx, hy, xi, yi, S, N);
-          c4.w = (unsigned)box_count(bp, 3, sbit, hx, hy, xi, yi, S, N);
+          int cnt[4] = {0, 0, 0, 0};
+          if (bp.fast_rmax >= 0) box_direct_sweep(bp, sbit, xi, yi, S, cnt);     // all direct boxes in one row sweep
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (bp.fast_rmax < 0 || bp.mode[q] != BOX_DIRECT) cnt[q] = box_count(bp, q, sbit, hx, hy, xi, yi, S, N);
+          const uint4 c4 = make_uint4((unsigned)cnt[0], (unsigned)cnt[1], (unsigned)cnt[2], (unsigned)cnt[3]);
           reinterpret_cast<uint4*>(sc.pcounts + (base + i) * 8)[0] = c4;
           const int a = eff[i];
           if (a < 8) {                                   // summed axis / diagonal move vectors (SDE:346-347)

@@ -46,6 +46,10 @@ struct Ctx {
   // nccl
   void* nccl_lib = nullptr;
   void* nccl_comm = nullptr;
+  ~Ctx() {                     // owns only the library scratch; state / tapes / outputs belong to the caller
+    if (scratch_block) cudaFree(scratch_block);
+    if (d_stats) cudaFree(d_stats);
+  }
 };
 
 static int fail(Ctx* c, int code, const std::string& msg) {
@@ -384,12 +388,16 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
     return fail(nullptr, SWARM_E_CUDA, "swarm_create: no CUDA device (this library has no CPU fallback)");
   if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SWARM_E_INVALID, "swarm_create: bad device ordinal");
-  Ctx* c = new Ctx();
+  {
+    cudaError_t de = cudaSetDevice(cfg->device);
+    if (de != cudaSuccess) return fail(nullptr, SWARM_E_CUDA, std::string("swarm_create: cudaSetDevice: ") + cudaGetErrorString(de));
+  }
+  int num_sms = 148;
+  if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess)
+    return fail(nullptr, SWARM_E_CUDA, "swarm_create: cannot query the device");
+  Ctx* c = new Ctx();          // every failure path below deletes it
   c->cfg = *cfg;
-  CUDA_TRY(c, cudaSetDevice(cfg->device));
-  cudaDeviceProp prop;
-  CUDA_TRY(c, cudaGetDeviceProperties(&prop, cfg->device));
-  c->num_sms = prop.multiProcessorCount;
+  c->num_sms = num_sms;
   c->force_pairwise = cfg->path == SWARM_PATH_STAGED_PAIRWISE;
   c->fused = cfg->path == SWARM_PATH_FUSED || cfg->path == SWARM_PATH_GROUP ||
              (cfg->path == SWARM_PATH_AUTO && cfg->num_agents <= SWARM_FUSED_MAX_AGENTS);
@@ -455,8 +463,6 @@ int swarm_destroy(swarm_handle h) {
     destroy_t f = (destroy_t)dlsym(c->nccl_lib, "ncclCommDestroy");
     if (f) f(c->nccl_comm);
   }
-  if (c->scratch_block) cudaFree(c->scratch_block);
-  if (c->d_stats) cudaFree(c->d_stats);
   delete c;
   return SWARM_OK;
 }
