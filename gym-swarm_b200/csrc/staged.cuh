@@ -476,7 +476,7 @@ __device__ __forceinline__ unsigned warp_umin(unsigned v) {
 
 __device__ __forceinline__ int pred_retarget(const PredIO& io, int env) {
   if (io.retarget) return io.retarget[env];
-  return philox4x32_10(make_uint4((unsigned)env, io.rng_step, 0u, 1u), io.rng_seed_lo, io.rng_seed_hi).x < 429496730u;
+  return philox_retarget(io.rng_seed_lo, io.rng_seed_hi, io.rng_step, env);
 }
 
 // 8 packed agents (one uint4 of x, one of y) against the predator cell: nearest-neighbour keys

@@ -278,14 +278,31 @@ __device__ __forceinline__ void box_direct_sweep(const BoxPlan& bp, const unsign
 }
 
 // ---- tape accessors: a bound tape (row pointer) or the in-kernel Philox stream -----------------------------------
+// The Philox paths are separate NON-INLINED functions: inlined, their ~60 instructions and live registers were paid by
+// every kernel even with bound tapes (tiny_step_kernel 96 -> 112 registers, 87 -> 99 us at cfg5).
+__device__ __noinline__ int philox_retarget(unsigned k0, unsigned k1, unsigned step, int env) {
+  return philox4x32_10(make_uint4((unsigned)env, step, 0u, 1u), k0, k1).x < 429496730u;
+}
+__device__ __noinline__ int philox_slab(unsigned k0, unsigned k1, unsigned step, int env, int d) {
+  const uint4 v = philox4x32_10(make_uint4((unsigned)env, step, 1u + (unsigned)(d >> 4), 1u), k0, k1);
+  return (int)((word_of(v, (d >> 2) & 3) >> (8 * (d & 3))) & 7u);
+}
+__device__ __noinline__ int philox_place(unsigned k0, unsigned k1, int S, int env, unsigned rc, int i) {
+  const uint4 v = philox4x32_10(make_uint4((unsigned)env, rc, (unsigned)(i >> 2), 2u), k0, k1);
+  return (int)__umulhi(word_of(v, i & 3), (unsigned)S);
+}
+__device__ __noinline__ unsigned philox_pred(unsigned k0, unsigned k1, int S, int env, unsigned rc, int a) {
+  const uint4 v = philox4x32_10(make_uint4((unsigned)env, rc, (unsigned)(a >> 1), 3u), k0, k1);
+  return pack2((int)__umulhi((a & 1) ? v.z : v.x, (unsigned)S), (int)__umulhi((a & 1) ? v.w : v.y, (unsigned)S));
+}
+
 __device__ __forceinline__ int tape_retarget(const StepParams& p, int env) {
   if (p.retarget) return p.retarget[env];
-  return philox4x32_10(make_uint4((unsigned)env, p.rng_step, 0u, 1u), p.rng_seed_lo, p.rng_seed_hi).x < 429496730u;
+  return philox_retarget(p.rng_seed_lo, p.rng_seed_hi, p.rng_step, env);
 }
 __device__ __forceinline__ int tape_slab(const StepParams& p, const uint8_t* __restrict__ row, int env, int d) {
   if (p.slab) return row[d] & 7;
-  const uint4 v = philox4x32_10(make_uint4((unsigned)env, p.rng_step, 1u + (unsigned)(d >> 4), 1u), p.rng_seed_lo, p.rng_seed_hi);
-  return (int)((word_of(v, (d >> 2) & 3) >> (8 * (d & 3))) & 7u);
+  return philox_slab(p.rng_seed_lo, p.rng_seed_hi, p.rng_step, env, d);
 }
 __device__ __forceinline__ const int16_t* place_row(const StepParams& p, int env, unsigned rc) {
   return p.place ? p.place + ((size_t)(rc % (unsigned)p.R) * (size_t)p.E + (size_t)env) * (size_t)p.PL : nullptr;
@@ -295,15 +312,13 @@ __device__ __forceinline__ const int16_t* ptape_row(const StepParams& p, int env
 }
 __device__ __forceinline__ int tape_place(const StepParams& p, const int16_t* __restrict__ row, int env, unsigned rc, int i) {
   if (row) return row[i];
-  const uint4 v = philox4x32_10(make_uint4((unsigned)env, rc, (unsigned)(i >> 2), 2u), p.rst_seed_lo, p.rst_seed_hi);
-  return (int)__umulhi(word_of(v, i & 3), (unsigned)p.S);
+  return philox_place(p.rst_seed_lo, p.rst_seed_hi, p.S, env, rc, i);
 }
 __device__ __forceinline__ void tape_pred(const StepParams& p, const int16_t* __restrict__ row, int env, unsigned rc, int a,
                                           int& px, int& py) {
   if (row) { px = row[2 * a]; py = row[2 * a + 1]; return; }
-  const uint4 v = philox4x32_10(make_uint4((unsigned)env, rc, (unsigned)(a >> 1), 3u), p.rst_seed_lo, p.rst_seed_hi);
-  px = (int)__umulhi((a & 1) ? v.z : v.x, (unsigned)p.S);
-  py = (int)__umulhi((a & 1) ? v.w : v.y, (unsigned)p.S);
+  const unsigned v = philox_pred(p.rst_seed_lo, p.rst_seed_hi, p.S, env, rc, a);
+  px = (int)(v & 0xFFFFu); py = (int)(v >> 16);
 }
 
 }  // namespace swarm

@@ -20,3 +20,11 @@ KR="python tools/kernel_roofline.py move predator"
 $KR > gpurun_out/plainkr.log 2>&1 && ncu --set full --clock-control none --import-source on -k "regex:move_kernel|predator_group|predator_block" -s 5 -c 1 -f -o gpurun_out/${R}_move $KR > gpurun_out/ncu_kr.log 2>&1; echo rc=$?
 ncu --set full --clock-control none --import-source on -k "regex:predator_group" -s 5 -c 1 -f -o gpurun_out/${R}_predator_n128 $KR > gpurun_out/ncu_kr2.log 2>&1; echo rc=$?
 ncu --set full --clock-control none --import-source on -k "regex:predator_block" -s 5 -c 1 -f -o gpurun_out/${R}_predator_n16384 $KR > gpurun_out/ncu_kr3.log 2>&1; echo rc=$?
+
+# summarise on the box (ncu is installed there too) and drop the bulky reports: gpurun_out/ may not exceed 64 MiB
+for n in cfg3_fused cfg5_tiny cfg4_staged move predator_n128 predator_n16384; do
+  if [ -s gpurun_out/${R}_$n.ncu-rep ]; then python tools/ncu_summary.py full gpurun_out/${R}_$n.ncu-rep > gpurun_out/${R}_${n}_full.txt; fi
+done
+[ -s gpurun_out/${R}_cfg3_fused.ncu-rep ] && python tools/ncu_regions.py gpurun_out/${R}_cfg3_fused.ncu-rep > gpurun_out/${R}_cfg3_fused_regions.txt
+for n in cfg5_tiny cfg4_staged move predator_n128 predator_n16384; do rm -f gpurun_out/${R}_$n.ncu-rep; done
+du -sh gpurun_out
