@@ -60,10 +60,21 @@ __device__ __forceinline__ void tiny_reset(const StepParams& p, int env, unsigne
                                            int& px, int& py, int& target, unsigned& err) {
   const int N = p.N, S = p.S;
   const int16_t* __restrict__ tape = place_row(p, env, rc);
+  if (tape && N == TINY_N && (((uintptr_t)tape) & 15) == 0) {   // the first placement as two 128-bit loads
+    const uint4 xv = *reinterpret_cast<const uint4*>(tape);
+    const uint4 yv = *reinterpret_cast<const uint4*>(tape + TINY_N);
+    const unsigned xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
-  for (int k = 0; k < TINY_N; ++k) {
-    x[k] = k < N ? tape_place(p, tape, env, rc, k) : 0;       // SDE:202-203: all x's then all y's
-    y[k] = k < N ? tape_place(p, tape, env, rc, N + k) : 0;
+    for (int k = 0; k < TINY_N; ++k) {
+      x[k] = (int)(int16_t)((xs[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
+      y[k] = (int)(int16_t)((ys[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < TINY_N; ++k) {
+      x[k] = k < N ? tape_place(p, tape, env, rc, k) : 0;       // SDE:202-203: all x's then all y's
+      y[k] = k < N ? tape_place(p, tape, env, rc, N + k) : 0;
+    }
   }
   int cur = 2 * N;
   for (;;) {
@@ -417,11 +428,22 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   if (err) p.err[env] |= err;
 }
 
-// Masked reset of finished envs (auto-reset after tiny_step_kernel): thread per env.
+// Masked reset of finished envs (auto-reset after tiny_step_kernel).  Finished envs are rare (a few per cent) and
+// scattered, so each CTA first compacts its finished envs into a shared list and then resets them with consecutive
+// threads: one or two warps run the (long, divergent) reset code instead of every warp running it for one lane.
 __global__ void __launch_bounds__(TINY_THREADS) tiny_reset_kernel(const __grid_constant__ StepParams p,
                                                                    const uint8_t* __restrict__ mask) {
-  const int env = blockIdx.x * TINY_THREADS + threadIdx.x;
-  if (env >= p.E || !mask[env]) return;
+  __shared__ int s_list[TINY_THREADS];
+  __shared__ int s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  {
+    const int e = blockIdx.x * TINY_THREADS + threadIdx.x;
+    if (e < p.E && mask[e]) s_list[atomicAdd(&s_count, 1)] = e;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x >= s_count) return;
+  const int env = s_list[threadIdx.x];
   const int N = p.N;
   const size_t base = (size_t)env * (size_t)N;
   const unsigned rc = p.reset_count[env];
