@@ -314,13 +314,22 @@ __global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p
     const uint8_t* __restrict__ slab = p.slab + (size_t)env * (size_t)p.K;
     int cur = 0;
     unsigned err = 0;
+    // the thread's (<= 16) candidate positions live in registers for all rounds: re-reading them from global in every
+    // phase (scalar int16 loads at a 32 B stride) made the L1 sector rate, not the shared-memory work, the limit
+    unsigned pos[16];
+    const int nown = hi - lo;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) pos[k] = k < nown ? pack2(nx[lo + k], ny[lo + k]) : 0u;
     for (;;) {
       // phase A: bitmap insert, hit flags
       unsigned hitmask = 0u;
-      for (int i = lo; i < hi; ++i) {
-        const int cell = (int)ny[i] * S + (int)nx[i];
-        const unsigned bit = 1u << (cell & 31);
-        if (atomicOr(&sbit[cell >> 5], bit) & bit) hitmask |= 1u << (i - lo);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (k < nown) {
+          const int cell = (int)(pos[k] >> 16) * S + (int)(pos[k] & 0xFFFFu);
+          const unsigned bit = 1u << (cell & 31);
+          if (atomicOr(&sbit[cell >> 5], bit) & bit) hitmask |= 1u << k;
+        }
       }
       const int H = block_sum(__popc(hitmask), bs);     // (syncs: all bits are set)
       if (H == 0 && bp.enabled) {
@@ -328,7 +337,9 @@ __global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p
         if (bp.need_hist) {
           for (int a = threadIdx.x; a < 2 * S; a += blockDim.x) hx[a] = 0;
           __syncthreads();
-          for (int i = lo; i < hi; ++i) { atomicAdd(&hx[nx[i]], 1); atomicAdd(&hy[ny[i]], 1); }
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (k < nown) { atomicAdd(&hx[pos[k] & 0xFFFFu], 1); atomicAdd(&hy[pos[k] >> 16], 1); }
           __syncthreads();
           // inclusive prefix sums over the S columns / S rows (thread t owns a contiguous chunk of each)
           const int hper = (S + blockDim.x - 1) / blockDim.x;
@@ -344,8 +355,14 @@ __global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p
           __syncthreads();
         }
         int ax = 0, ay = 0, dx = 0, dy = 0;
-        for (int i = lo; i < hi; ++i) {
-          const int xi = nx[i], yi = ny[i];
+#pragma unroll 1
+        for (int k = 0; k < nown; ++k) {
+          unsigned pk = 0u;
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (q == k) pk = pos[q];
+          const int i = lo + k;
+          const int xi = (int)(pk & 0xFFFFu), yi = (int)(pk >> 16);
           int cnt[4] = {0, 0, 0, 0};
           if (bp.fast_rmax >= 0) box_direct_sweep(bp, sbit, xi, yi, S, cnt);     // all direct boxes in one row sweep
 #pragma unroll
@@ -365,28 +382,34 @@ __global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p
           ea[0] = ax; ea[1] = ay; ea[2] = dx; ea[3] = dy;
         }
       }
-      for (int i = lo; i < hi; ++i) sbit[((int)ny[i] * S + (int)nx[i]) >> 5] = 0u;   // leave the bitmap clean
+#pragma unroll
+      for (int k = 0; k < 16; ++k)                      // leave the bitmap clean
+        if (k < nown) sbit[((int)(pos[k] >> 16) * S + (int)(pos[k] & 0xFFFFu)) >> 5] = 0u;
       if (H == 0) { __syncthreads(); break; }                                       // change_position_id -> None
       unsigned long long cpack = 0ull;                  // (c_i - 1) in 4 bits per owned agent
       int extra = 0;
       const bool small = H <= COLL_HC / 2;
       if (small) {
-        for (int i = lo; i < hi; ++i)
-          if (hitmask & (1u << (i - lo))) hash_insert(hkeys, hcnt, COLL_HC - 1, 12, pack2(nx[i], ny[i]));
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (hitmask & (1u << k)) hash_insert(hkeys, hcnt, COLL_HC - 1, 12, pos[k]);
         __syncthreads();
-        for (int i = lo; i < hi; ++i) {
-          const unsigned key = pack2(nx[i], ny[i]);
-          unsigned sl = hash_slot(key, 12);
-          unsigned cnt = 0u;
-          for (;;) {
-            const unsigned k = hkeys[sl];
-            if (k == key) { cnt = hcnt[sl]; break; }
-            if (k == HASH_EMPTY) break;
-            sl = (sl + 1u) & (COLL_HC - 1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (k < nown) {
+            const unsigned key = pos[k];
+            unsigned sl = hash_slot(key, 12);
+            unsigned cnt = 0u;
+            for (;;) {
+              const unsigned kk = hkeys[sl];
+              if (kk == key) { cnt = hcnt[sl]; break; }
+              if (kk == HASH_EMPTY) break;
+              sl = (sl + 1u) & (COLL_HC - 1);
+            }
+            cnt = min(cnt, 15u);
+            cpack |= (unsigned long long)cnt << (4 * k);
+            extra += (int)cnt;
           }
-          cnt = min(cnt, 15u);
-          cpack |= (unsigned long long)cnt << (4 * (i - lo));
-          extra += (int)cnt;
         }
       } else {
         extra = hash_count_extra(gh, lo, hi, [&](int i) { return pack2(nx[i], ny[i]); });
@@ -396,13 +419,17 @@ __global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p
       int off = block_excl_scan(extra, L, bs);           // (syncs: all lookups are done)
       const bool overflow = cur + L > p.K;
       if (!overflow) {
-        for (int i = lo; i < hi; ++i) {
-          const int e = (int)((cpack >> (4 * (i - lo))) & 15ull);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int e = (int)((cpack >> (4 * k)) & 15ull);
           if (e > 0) {                                       // SDE:250-255
+            const int i = lo + k;
             const int a = tape_slab(p, slab, env, cur + off + e - 1);
+            const int vx = wrap1((int)p.x[base + i] + move_dx(a), S), vy = wrap1((int)p.y[base + i] + move_dy(a), S);
             eff[i] = (uint8_t)a;
-            nx[i] = (int16_t)wrap1((int)p.x[base + i] + move_dx(a), S);
-            ny[i] = (int16_t)wrap1((int)p.y[base + i] + move_dy(a), S);
+            nx[i] = (int16_t)vx;
+            ny[i] = (int16_t)vy;
+            pos[k] = pack2(vx, vy);
           }
           off += e;
         }
