@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p
         }
       }
       const int H = block_sum(__popc(hitmask), bs);     // (syncs: all bits are set)
-      if (H == 0 && bp.enabled) {
+      if (H == 0 && bp.enabled == 1) {
         // no shared cell: the bitmap is the exact occupancy of the final positions -> reward counts (SDE:330-343)
         if (bp.need_hist) {
           for (int a = threadIdx.x; a < 2 * S; a += blockDim.x) hx[a] = 0;
@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p
       if (overflow) { err |= SWARM_ERR_SLAB_OVERFLOW; break; }
       cur += L;
     }
+    if (err && bp.enabled && threadIdx.x == 0) sc.envacc[(size_t)env * 12 + 9] = 1;   // boxcount_kernel skips this env
     if (err && bp.enabled) {
       // Slab exhausted: cells are still shared, which a bitmap cannot represent.  The reference semantics go on
       // with those positions, so this (exceptional, flagged) env gets its counts from a plain all-pairs loop.
@@ -472,6 +473,76 @@ __global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p
       p.consumed[env] = cur;
       if (err) p.err[env] |= err;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2c: box counts as their own kernel when there are fewer envs than SMs (cfg4: 16 envs): `parts` CTAs per env
+// each rebuild the env's occupancy bitmap (+ histograms) in their shared memory -- cheap next to the counting --
+// and count 1/parts of the agents, so the reward phase runs on parts x E SMs instead of E.
+// Envs whose re-draw slab overflowed (flag at envacc[9]) were counted by collide_bitmap_kernel's all-pairs loop.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) boxcount_kernel(const StepParams p, const StagedScratch sc, int bm_words,
+                                                        const BoxPlan bp, int parts) {
+  extern __shared__ __align__(16) unsigned coll_smem[];
+  __shared__ BlockScratch bs;
+  unsigned* sbit = coll_smem;                                  // [bm_words]
+  int* hx = reinterpret_cast<int*>(coll_smem + bm_words);      // [S]
+  int* hy = hx + p.S;                                          // [S]
+  const int N = p.N, S = p.S;
+  const int env = blockIdx.x / parts, part = blockIdx.x % parts;
+  if (p.frozen[env] || sc.envacc[(size_t)env * 12 + 9]) return;
+  const size_t base = (size_t)env * (size_t)N;
+  const int16_t* __restrict__ nx = sc.nx + base;
+  const int16_t* __restrict__ ny = sc.ny + base;
+  for (int w = threadIdx.x; w < bm_words; w += blockDim.x) sbit[w] = 0u;
+  if (bp.need_hist)
+    for (int a = threadIdx.x; a < 2 * S; a += blockDim.x) hx[a] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int xi = nx[i], yi = ny[i];
+    const int cell = yi * S + xi;
+    atomicOr(&sbit[cell >> 5], 1u << (cell & 31));
+    if (bp.need_hist) { atomicAdd(&hx[xi], 1); atomicAdd(&hy[yi], 1); }
+  }
+  __syncthreads();
+  if (bp.need_hist) {
+    const int hper = (S + blockDim.x - 1) / blockDim.x;
+    const int h0 = min(S, (int)threadIdx.x * hper), h1 = min(S, h0 + hper);
+    for (int q = 0; q < 2; ++q) {
+      int* h = q ? hy : hx;
+      int run = 0;
+      for (int a = h0; a < h1; ++a) run += h[a];
+      int tot;
+      int carry = block_excl_scan(run, tot, bs);
+      for (int a = h0; a < h1; ++a) { carry += h[a]; h[a] = carry; }
+    }
+    __syncthreads();
+  }
+  const int begin = (int)(((long long)N * part) / parts), end = (int)(((long long)N * (part + 1)) / parts);
+  int ax = 0, ay = 0, dx = 0, dy = 0;
+  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    const int xi = nx[i], yi = ny[i];
+    int cnt[4] = {0, 0, 0, 0};
+    if (bp.fast_rmax >= 0) box_direct_sweep(bp, sbit, xi, yi, S, cnt);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (bp.fast_rmax < 0 || bp.mode[q] != BOX_DIRECT) cnt[q] = box_count(bp, q, sbit, hx, hy, xi, yi, S, N);
+    reinterpret_cast<uint4*>(sc.pcounts + (base + i) * 8)[0] =
+        make_uint4((unsigned)cnt[0], (unsigned)cnt[1], (unsigned)cnt[2], (unsigned)cnt[3]);
+    const int a = sc.eff[base + i];
+    if (a < 8) {                                     // summed axis / diagonal move vectors (SDE:346-347)
+      const int mx = move_dx(a), my = move_dy(a);
+      if (a & 1) { dx += mx; dy += my; } else { ax += mx; ay += my; }
+    }
+  }
+  ax = block_sum(ax, bs); ay = block_sum(ay, bs); dx = block_sum(dx, bs); dy = block_sum(dy, bs);
+  if (threadIdx.x == 0) {
+    int* ea = sc.envacc + (size_t)env * 12;
+    if (ax) atomicAdd(ea + 0, ax);
+    if (ay) atomicAdd(ea + 1, ay);
+    if (dx) atomicAdd(ea + 2, dx);
+    if (dy) atomicAdd(ea + 3, dy);
   }
 }
 

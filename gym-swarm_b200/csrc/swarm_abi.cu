@@ -231,6 +231,8 @@ static int staged_alloc(Ctx* c) {
       c->box = bp;
       CUDA_TRY(c, cudaFuncSetAttribute(collide_bitmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        c->coll_smem_bytes));
+      CUDA_TRY(c, cudaFuncSetAttribute(boxcount_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(words * 4 + 2LL * S * 4)));
     }
   }
   const size_t hs = (size_t)1 << log2hs;
@@ -599,10 +601,18 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     move_kernel<<<grid, 256, 0, s>>>(total, p.N, p.S, p.x, p.y, p.actions, sc.nx, sc.ny, sc.eff, p.err);
   }
   const bool box = c->coll_bm_words > 0 && c->box.enabled && !vf && !c->force_pairwise;
+  int box_parts = 1;                           // CTAs per env for the box counts: spread few big envs over the SMs
+  if (box) box_parts = std::max(1, std::min(8, c->num_sms / std::max(1, p.E)));
+  int extra_launches = 0;
   if (c->coll_bm_words > 0) {
     BoxPlan bp = c->box;
-    bp.enabled = box ? 1 : 0;
+    bp.enabled = box ? (box_parts > 1 ? 2 : 1) : 0;
     collide_bitmap_kernel<<<sc.env_grid, c->per_env_threads, c->coll_smem_bytes, s>>>(p, sc, c->coll_bm_words, bp);
+    if (box && box_parts > 1) {
+      const int smem = c->coll_bm_words * 4 + (bp.need_hist ? 2 * p.S * 4 : 0);
+      boxcount_kernel<<<p.E * box_parts, 1024, smem, s>>>(p, sc, c->coll_bm_words, bp, box_parts);
+      extra_launches = 1;
+    }
   } else {
     collide_kernel<<<sc.env_grid, c->per_env_threads, 0, s>>>(p, sc);
   }
@@ -615,7 +625,7 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     io.step_target = p.step_target; io.done = p.done; io.eaten = p.eaten; io.err = p.err;
     launch_predator(io, c->num_sms, s);
   }
-  c->launches = 5;
+  c->launches = 5 + extra_launches;
   if (!box) {                                  // tiled pairwise kernels compute the threshold counts
     const long long words = (long long)p.E * sc.NW;
     pairprep_kernel<<<(int)((words + 255) / 256), 256, 0, s>>>(p.E, p.N, p.S, sc.NW, sc.nx, sc.ny, sc.eff, sc.pairw,
