@@ -34,16 +34,9 @@ struct Seg {
     li = lane % LPE;
     mask = (LPE == 32) ? 0xFFFFFFFFu : (((1u << LPE) - 1u) << (seg * LPE));
   }
-  __device__ __forceinline__ int sum(int v) const {
-#pragma unroll
-    for (int d = LPE / 2; d > 0; d >>= 1) v += __shfl_xor_sync(mask, v, d, LPE);
-    return v;
-  }
-  __device__ __forceinline__ unsigned umin(unsigned v) const {
-#pragma unroll
-    for (int d = LPE / 2; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(mask, v, d, LPE));
-    return v;
-  }
+  // group reductions: one REDUX instruction (works for any lane mask) instead of a log2(LPE)-step shuffle butterfly
+  __device__ __forceinline__ int sum(int v) const { return __reduce_add_sync(mask, v); }
+  __device__ __forceinline__ unsigned umin(unsigned v) const { return __reduce_min_sync(mask, v); }
   // exclusive prefix sum over the group's lanes; total = group sum
   __device__ __forceinline__ int excl_scan(int v, int& total) const {
     int inc = v;
@@ -317,6 +310,142 @@ __device__ __noinline__ void reset_group(const StepParams& p, const Seg<LPE>& g,
   target = closest_target<LPE, APL>(g, N, S, i0, px, py, x, y);   // SDE:109
 }
 
+// ---- symmetric ring sweep (see the comment at its call site) ---------------------------------------------------
+// FAR = false: the two far thresholds were already counted by the border pass (far_border_counts), the sweep carries
+// only the {rep, att} counter pair.
+template <int LPE, int APL, bool FAR>
+__device__ __forceinline__ void ring_sweep(const Seg<LPE>& g, const uint4* __restrict__ spw, const unsigned (&XI)[APL],
+                                           const unsigned (&YI)[APL], const unsigned (&NXI)[APL], const unsigned (&NYI)[APL],
+                                           unsigned TR, unsigned TA, unsigned TRf, unsigned TAf, unsigned one, unsigned c256,
+                                           unsigned (&aR)[APL], unsigned (&aA)[APL], unsigned (&aRf)[APL], unsigned (&aAf)[APL]) {
+  constexpr int W = APL / 2;
+  constexpr int HALF = LPE / 2;
+  // Counters are BYTE packed: a 16x2 indicator word holds 0/1 in bytes 0 and 2, so ind(t0) + 256 * ind(t1)
+  // carries two thresholds for two agents in one register ({t0,t1} = {rep,att} and {rep_far,att_far}); it is
+  // built once (IMAD) and added to the row and to the column counter.  No byte can overflow: a row byte
+  // meets at most NMAX / 2 <= 64 pair words, a column byte at most (LPE / 2 - 1) * APL <= 60 rows.
+  unsigned row[APL][2], col[W][2];
+#pragma unroll
+  for (int k = 0; k < APL; ++k) row[k][0] = row[k][1] = 0u;
+#pragma unroll
+  for (int w = 0; w < W; ++w) col[w][0] = col[w][1] = 0u;
+  auto rows_only = [&](int src) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const uint4 vw = spw[w * LPE + src];
+#pragma unroll
+      for (int k = 0; k < APL; ++k) {
+        const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
+        row[k][0] = lt2(TR, m) * one + row[k][0];
+        row[k][0] = lt2(TA, m) * c256 + row[k][0];
+        if constexpr (FAR) {
+          row[k][1] = lt2(TRf, m) * one + row[k][1];
+          row[k][1] = lt2(TAf, m) * c256 + row[k][1];
+        }
+      }
+    }
+  };
+  rows_only(g.li);                                       // round 0: own block
+  const int nxt = (g.li + 1) & (LPE - 1);
+#pragma unroll 1
+  for (int r = 1; r < HALF; ++r) {
+    const int src = (g.li + r) & (LPE - 1);
+    if (r > 1) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        col[w][0] = __shfl_sync(g.mask, col[w][0], nxt, LPE);
+        if constexpr (FAR) col[w][1] = __shfl_sync(g.mask, col[w][1], nxt, LPE);
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const uint4 vw = spw[w * LPE + src];
+#pragma unroll
+      for (int k = 0; k < APL; ++k) {
+        const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
+        const unsigned n0 = lt2(TA, m) * c256 + lt2(TR, m);
+        row[k][0] = n0 * one + row[k][0];
+        col[w][0] = n0 * one + col[w][0];
+        if constexpr (FAR) {
+          const unsigned n1 = lt2(TAf, m) * c256 + lt2(TRf, m);
+          row[k][1] = n1 * one + row[k][1];
+          col[w][1] = n1 * one + col[w][1];
+        }
+      }
+    }
+  }
+  // send the column counters home: lane l holds those of block l + HALF - 1
+  if constexpr (HALF > 1) {
+    const int from = (g.li - (HALF - 1)) & (LPE - 1);
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      col[w][0] = __shfl_sync(g.mask, col[w][0], from, LPE);
+      if constexpr (FAR) col[w][1] = __shfl_sync(g.mask, col[w][1], from, LPE);
+    }
+  }
+  rows_only((g.li + HALF) & (LPE - 1));                  // round LPE/2: met from both sides
+  // fold: total = both agents' bytes of the row counter + this agent's bytes of the column counter
+#pragma unroll
+  for (int k = 0; k < APL; ++k) {
+    const int sh = 16 * (k & 1);
+    aR[k] = __dp4a(row[k][0], 0x00010001u, 0u) + ((col[k >> 1][0] >> sh) & 0xFFu);
+    aA[k] = __dp4a(row[k][0], 0x01000100u, 0u) + ((col[k >> 1][0] >> (sh + 8)) & 0xFFu);
+    if constexpr (FAR) {
+      aRf[k] = __dp4a(row[k][1], 0x00010001u, 0u) + ((col[k >> 1][1] >> sh) & 0xFFu);
+      aAf[k] = __dp4a(row[k][1], 0x01000100u, 0u) + ((col[k >> 1][1] >> (sh + 8)) & 0xFFu);
+    }
+  }
+}
+
+// ---- far thresholds from the border agents only ------------------------------------------------------------------
+// For a threshold t > S/2 a pair with D >= t needs one agent within b = S - t cells of a border and the other within
+// b cells of the OPPOSITE border, so #{j : D_ij < t} = N-1 for every agent outside the border band and only the
+// (few) band agents have to be paired with each other.  They are compacted into shared memory (positions in
+// slist[0, nb), counters in slist[NMAX, NMAX + nb)) and every (i, j) pair among them is evaluated once by some lane.
+// Outputs aRf / aAf in the sweep's convention (self included): N - #{j != i : D_ij >= t}.
+template <int LPE, int APL>
+__device__ __forceinline__ void far_border_counts(const StepParams& p, const Seg<LPE>& g, unsigned* slist, int N, int S, int i0,
+                                                  const int (&cx)[APL], const int (&cy)[APL], unsigned (&aRf)[APL],
+                                                  unsigned (&aAf)[APL]) {
+  constexpr int NMAX = LPE * APL;
+  const int b = p.far_band;
+  const unsigned lt_mask = (1u << (threadIdx.x & 31)) - 1u;
+  int slot[APL];
+  int nb = 0;
+#pragma unroll
+  for (int k = 0; k < APL; ++k) {
+    const bool f = (i0 + k < N) && (cx[k] < b || cx[k] >= S - b || cy[k] < b || cy[k] >= S - b);
+    const unsigned ball = __ballot_sync(g.mask, f) & g.mask;
+    slot[k] = f ? nb + __popc(ball & lt_mask) : -1;
+    if (f) slist[slot[k]] = pack2(cx[k], cy[k]);
+    nb += __popc(ball);
+  }
+  g.sync();
+  // lane j owns band agent j (one chunk of LPE at a time) and sweeps all band agents i: independent broadcast loads,
+  // the count stays in a register (no atomics)
+  for (int j0 = 0; j0 < nb; j0 += LPE) {
+    const int j = j0 + g.li;
+    const unsigned pj = j < nb ? slist[j] : 0u;
+    const int xj = (int)(pj & 0xFFFFu), yj = (int)(pj >> 16);
+    unsigned acc = 0u;
+#pragma unroll 4
+    for (int i = 0; i < nb; ++i) {
+      const unsigned pi = slist[i];
+      const int d = max(iabs(xj - (int)(pi & 0xFFFFu)), iabs(yj - (int)(pi >> 16)));
+      acc += (i != j) ? ((unsigned)(d >= p.t_repf) | ((unsigned)(d >= p.t_attf) << 16)) : 0u;
+    }
+    if (j < nb) slist[NMAX + j] = acc;
+  }
+  g.sync();
+#pragma unroll
+  for (int k = 0; k < APL; ++k) {
+    const unsigned v = slot[k] >= 0 ? slist[NMAX + slot[k]] : 0u;
+    aRf[k] = (unsigned)N - (v & 0xFFFFu);
+    aAf[k] = (unsigned)N - (v >> 16);
+  }
+  g.sync();                                                       // the list region is the pair-word staging area next
+}
+
 // ---- the fused step kernel ------------------------------------------------------------------------
 template <int LPE, int APL>
 struct FusedCfg {
@@ -359,7 +488,20 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
   const size_t base = (size_t)env * (size_t)N;
   const bool vec = (N % APL) == 0;
 
-  if (p.frozen[env]) {                      // SDE:233-234: finished episode, auto-reset off
+  // every load the step needs is issued here, before the first dependent branch, so that one DRAM round trip covers
+  // all of it (the frozen flag, the state and -- for lane 0 -- the running episode statistics)
+  const int is_frozen = p.frozen[env];
+  int x[APL], y[APL], act[APL];
+  load_i16<APL>(p.x + base, i0, N, vec, x);
+  load_i16<APL>(p.y + base, i0, N, vec, y);
+  load_u8<APL>(p.actions + base, i0, N, vec, act);
+  int px = p.px[env], py = p.py[env];
+  int target = p.target[env];
+  unsigned ep_len0 = 0u;
+  float4 ep_ret0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.track_stats && g.li == 0) { ep_len0 = p.ep_len[env]; ep_ret0 = reinterpret_cast<const float4*>(p.ep_ret)[env]; }
+
+  if (is_frozen) {                          // SDE:233-234: finished episode, auto-reset off
     if (g.li == 0) {
       p.err[env] |= SWARM_ERR_STEP_WHEN_DONE;
       p.done[env] = 1;
@@ -372,12 +514,6 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
     return;
   }
 
-  int x[APL], y[APL], act[APL];
-  load_i16<APL>(p.x + base, i0, N, vec, x);
-  load_i16<APL>(p.y + base, i0, N, vec, y);
-  load_u8<APL>(p.actions + base, i0, N, vec, act);
-  int px = p.px[env], py = p.py[env];
-  int target = p.target[env];
   const int retarget = tape_retarget(p, env);
   unsigned err = 0;
 
@@ -503,6 +639,13 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
         }
       }
     } else {
+      bool far_done = false;
+      if constexpr (!HAS_VF && (APL == 2 || APL == 4) && LPE >= 4) {
+        if (p.far_border) {                              // both far thresholds > S/2: only border agents can be far apart
+          far_border_counts<LPE, APL>(p, g, skey, N, S, i0, nx, ny, aRf, aAf);
+          far_done = true;
+        }
+      }
       // stage the env's positions as packed pair words {x2, y2, -x2, -y2}; padding agents sit at x=-S
       int sx[APL], sy[APL];
   #pragma unroll
@@ -555,78 +698,9 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
         // sent home after the last symmetric round.  Rounds 0 (own block) and LPE/2 (met from both sides) only
         // count rows.  The accumulations are IMADs by a runtime 1 so that they issue on the FMA pipe and leave the
         // ALU pipe to the DPX ops.
-        constexpr int W = APL / 2;
-        constexpr int HALF = LPE / 2;
         const unsigned one = (unsigned)p.one, c256 = (unsigned)p.one << 8;
-        // Counters are BYTE packed: a 16x2 indicator word holds 0/1 in bytes 0 and 2, so ind(t0) + 256 * ind(t1)
-        // carries two thresholds for two agents in one register ({t0,t1} = {rep,att} and {rep_far,att_far}); it is
-        // built once (IMAD) and added to the row and to the column counter.  No byte can overflow: a row byte
-        // meets at most NMAX / 2 <= 64 pair words, a column byte at most (LPE / 2 - 1) * APL <= 60 rows.
-        unsigned row[APL][2], col[W][2];
-  #pragma unroll
-        for (int k = 0; k < APL; ++k) row[k][0] = row[k][1] = 0u;
-  #pragma unroll
-        for (int w = 0; w < W; ++w) col[w][0] = col[w][1] = 0u;
-        auto rows_only = [&](int src) {
-  #pragma unroll
-          for (int w = 0; w < W; ++w) {
-            const uint4 vw = spw[w * LPE + src];
-  #pragma unroll
-            for (int k = 0; k < APL; ++k) {
-              const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
-              row[k][0] = lt2(TR, m) * one + row[k][0];
-              row[k][0] = lt2(TA, m) * c256 + row[k][0];
-              row[k][1] = lt2(TRf, m) * one + row[k][1];
-              row[k][1] = lt2(TAf, m) * c256 + row[k][1];
-            }
-          }
-        };
-        rows_only(g.li);                                       // round 0: own block
-        const int nxt = (g.li + 1) & (LPE - 1);
-  #pragma unroll 1
-        for (int r = 1; r < HALF; ++r) {
-          const int src = (g.li + r) & (LPE - 1);
-          if (r > 1) {
-  #pragma unroll
-            for (int w = 0; w < W; ++w) {
-              col[w][0] = __shfl_sync(g.mask, col[w][0], nxt, LPE);
-              col[w][1] = __shfl_sync(g.mask, col[w][1], nxt, LPE);
-            }
-          }
-  #pragma unroll
-          for (int w = 0; w < W; ++w) {
-            const uint4 vw = spw[w * LPE + src];
-  #pragma unroll
-            for (int k = 0; k < APL; ++k) {
-              const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], vw);
-              const unsigned n0 = lt2(TA, m) * c256 + lt2(TR, m);
-              const unsigned n1 = lt2(TAf, m) * c256 + lt2(TRf, m);
-              row[k][0] = n0 * one + row[k][0];
-              row[k][1] = n1 * one + row[k][1];
-              col[w][0] = n0 * one + col[w][0];
-              col[w][1] = n1 * one + col[w][1];
-            }
-          }
-        }
-        // send the column counters home: lane l holds those of block l + HALF - 1
-        if constexpr (HALF > 1) {
-          const int from = (g.li - (HALF - 1)) & (LPE - 1);
-  #pragma unroll
-          for (int w = 0; w < W; ++w) {
-            col[w][0] = __shfl_sync(g.mask, col[w][0], from, LPE);
-            col[w][1] = __shfl_sync(g.mask, col[w][1], from, LPE);
-          }
-        }
-        rows_only((g.li + HALF) & (LPE - 1));                  // round LPE/2: met from both sides
-        // fold: total = both agents' bytes of the row counter + this agent's bytes of the column counter
-  #pragma unroll
-        for (int k = 0; k < APL; ++k) {
-          const int sh = 16 * (k & 1);
-          aR[k] = __dp4a(row[k][0], 0x00010001u, 0u) + ((col[k >> 1][0] >> sh) & 0xFFu);
-          aA[k] = __dp4a(row[k][0], 0x01000100u, 0u) + ((col[k >> 1][0] >> (sh + 8)) & 0xFFu);
-          aRf[k] = __dp4a(row[k][1], 0x00010001u, 0u) + ((col[k >> 1][1] >> sh) & 0xFFu);
-          aAf[k] = __dp4a(row[k][1], 0x01000100u, 0u) + ((col[k >> 1][1] >> (sh + 8)) & 0xFFu);
-        }
+        if (far_done) ring_sweep<LPE, APL, false>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf);
+        else ring_sweep<LPE, APL, true>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf);
       } else {
         const int NW = (N + 1) >> 1;
   #pragma unroll 2
@@ -761,15 +835,16 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
     p.step_target[env] = step_target;
     p.consumed[env] = cur;
     if (p.track_stats) {
-      const unsigned len = p.ep_len[env] + 1u;
-      float4 ret = reinterpret_cast<float4*>(p.ep_ret)[env];
+      const unsigned len = ep_len0 + 1u;
+      float4 ret = ep_ret0;
       ret.x += (float)r_surv; ret.y += (float)r_att; ret.z += (float)r_rep; ret.w += (float)r_ali;
-      if (done) {
-        p.fin_count[env] += 1u;
-        p.fin_len[env] += len;
-        float4 f = reinterpret_cast<float4*>(p.fin_ret)[env];
-        f.x += ret.x; f.y += ret.y; f.z += ret.z; f.w += ret.w;
-        reinterpret_cast<float4*>(p.fin_ret)[env] = f;
+      if (done) {                                  // single writer per env: fire-and-forget reductions, no read round trip
+        atomicAdd(&p.fin_count[env], 1u);
+        atomicAdd(&p.fin_len[env], len);
+        atomicAdd(&p.fin_ret[4 * env + 0], ret.x);
+        atomicAdd(&p.fin_ret[4 * env + 1], ret.y);
+        atomicAdd(&p.fin_ret[4 * env + 2], ret.z);
+        atomicAdd(&p.fin_ret[4 * env + 3], ret.w);
         p.ep_len[env] = 0u;
         reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
       } else {

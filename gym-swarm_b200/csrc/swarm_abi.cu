@@ -78,6 +78,10 @@ static void fill_thresholds(StepParams& p, int N, int S, int att, int rep) {
   p.diag_rep = (0 < rep ? 1 : 0) + (S < rep ? 1 : 0);
   p.diag_att = (((0 < att) == (0 >= rep)) ? 1 : 0) + (((S < att) == (S >= rep)) ? 1 : 0);
   p.inv_nn = 1.0 / ((double)N * (double)(N - 1));
+  // far thresholds beyond half the grid: a pair at distance >= t needs both agents in opposite border bands
+  p.far_border = (2 * p.t_repf > S && 2 * p.t_attf > S) ? 1 : 0;
+  p.far_band = S - std::min(p.t_repf, p.t_attf);
+  if (getenv("SWARM_NO_FAR_BORDER")) p.far_border = 0;     // kernel A/B experiments / tests of the 4-threshold sweep
 }
 
 // Box-count plan: per threshold the cheaper of the direct box and the complement (cost in bitmap word reads per

@@ -45,6 +45,7 @@ struct StepParams {
   int t_rep, t_att, t_repf, t_attf;
   int diag_rep, diag_att;  // contribution of the diagonal (D=0, S-D=S) to the literal N x N sums
   int t_vf;                // D <= vf  <=>  D < t_vf ; -1: no visual-field gate
+  int far_border, far_band;  // both far thresholds > S/2: far pairs only among agents within far_band of a border
   double w_att, w_rep, w_ali, inv_nn;  // reward_type weights, 1/(N(N-1))
   float eat;
   int K, PL, KP, R;

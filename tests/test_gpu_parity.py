@@ -149,6 +149,24 @@ def test_fused_reward_by_ring_sweep_and_by_box_counts(N, S, force, monkeypatch):
                      KR=2000 if dense else None, weights=(0.5, 1.0, 0.25))
 
 
+@pytest.mark.parametrize("N,S", [(16, 32), (24, 12), (64, 64), (60, 11), (128, 128)])
+def test_fused_four_threshold_sweep(N, S, monkeypatch):
+    """Default thresholds normally take the border pass for the two far thresholds + a 2-threshold ring sweep;
+    SWARM_NO_FAR_BORDER keeps all four thresholds in the sweep (the path other threshold combinations use)."""
+    monkeypatch.setenv("SWARM_NO_FAR_BORDER", "1")
+    dense = S * S < 4 * N
+    _oracle_lockstep(E=9, N=N, S=S, T=10, seed=N + S, n_actions=9, K=512 if dense else None, KR=2000 if dense else None)
+
+
+@pytest.mark.parametrize("att,rep", [(5, 2), (2, 5), (1, 1), (9, 3), (3, 12), (12, 12), (20, 3), (31, 31), (32, 5)])
+def test_fused_far_border_pass_thresholds(att, rep):
+    """Far thresholds S-att+1, S-rep+1 on both sides of S/2 (S = 64, 21): the border pass is taken iff both exceed S/2;
+    small grids put most agents into the border band."""
+    _oracle_lockstep(E=6, N=120, S=64, T=4, seed=att * 17 + rep, n_actions=9, att=att, rep=rep, weights=(0.5, 1.0, 0.25))
+    _oracle_lockstep(E=6, N=40, S=21, T=4, seed=att + rep + 1, n_actions=9, att=min(att, 21), rep=min(rep, 21))
+    _oracle_lockstep(E=6, N=16, S=7, T=6, seed=att + rep + 2, n_actions=9, att=min(att, 7), rep=min(rep, 7), K=256, KR=500)
+
+
 @pytest.mark.parametrize("att,rep", [(5, 2), (2, 5), (0, 0), (1, 1), (9, 3), (3, 12), (10, 200), (40, 3), (70, 70), (5, 60)])
 def test_fused_box_count_thresholds(att, rep, monkeypatch):
     monkeypatch.setenv("SWARM_FUSED_BOX", "1")
