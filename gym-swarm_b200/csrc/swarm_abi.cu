@@ -27,7 +27,8 @@ struct Ctx {
   std::string err;
   std::string path_name;
   bool fused = false;
-  bool tiny = false;          // N <= 8: thread-per-env kernel (steps without a visual-field gate)
+  bool tiny = false;          // thread-per-env kernel (steps without a visual-field gate)
+  int tiny_n = 8;             // its register capacity: 8 or 16 agents
   bool force_pairwise = false;  // SWARM_PATH_STAGED_PAIRWISE: never use the box-count reward path
   int lpe = 0, apl = 0;
   int bitmap_words = 0;
@@ -407,7 +408,13 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
   c->force_pairwise = cfg->path == SWARM_PATH_STAGED_PAIRWISE;
   c->fused = cfg->path == SWARM_PATH_FUSED || cfg->path == SWARM_PATH_GROUP ||
              (cfg->path == SWARM_PATH_AUTO && cfg->num_agents <= SWARM_FUSED_MAX_AGENTS);
-  c->tiny = c->fused && cfg->path != SWARM_PATH_GROUP && cfg->num_agents <= TINY_N;
+  // thread per env: always for N <= 8; for 9..16 agents only when the batch is large enough to fill the GPU with one
+  // thread per env (the lane-group kernel spreads a small batch over 8x more threads and has the shorter latency)
+  int big_min_envs = 65536;
+  if (const char* ev = getenv("SWARM_TINY16_MIN_ENVS")) big_min_envs = atoi(ev);   // tests / experiments
+  c->tiny = c->fused && cfg->path != SWARM_PATH_GROUP &&
+            (cfg->num_agents <= TINY_N || (cfg->num_agents <= TINY_N_BIG && cfg->num_envs >= big_min_envs));
+  c->tiny_n = cfg->num_agents <= TINY_N ? TINY_N : TINY_N_BIG;
   if (c->fused) {
     choose_fused_shape(cfg->num_agents, c->lpe, c->apl);
     const long long cells = (long long)cfg->grid_size * cfg->grid_size;
@@ -428,7 +435,7 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
       c->fused_box = bp;
     }
     char buf[64];
-    if (c->tiny) snprintf(buf, sizeof(buf), "tiny<%d> (vf: fused<%d,%d>)", TINY_N, c->lpe, c->apl);
+    if (c->tiny) snprintf(buf, sizeof(buf), "tiny<%d> (vf: fused<%d,%d>)", c->tiny_n, c->lpe, c->apl);
     else snprintf(buf, sizeof(buf), "fused<%d,%d>%s%s", c->lpe, c->apl, c->bitmap_words ? "+bitmap" : "",
                   c->fused_box.enabled ? "+box" : "");
     c->path_name = buf;
@@ -576,14 +583,21 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
   const bool vf = p.t_vf >= 0;
   c->launches = 0;
   if (c->tiny && !vf) {
-    if (p.N == TINY_N && ((uintptr_t)in->actions & 7))
+    if (p.N == c->tiny_n && ((uintptr_t)in->actions & 7))
       return fail(c, SWARM_E_INVALID, "swarm_step: actions must be 8-byte aligned");
     const int grid = (p.E + TINY_THREADS - 1) / TINY_THREADS;
-    if (p.agent_reward || p.agent_counts) tiny_step_kernel<true><<<grid, TINY_THREADS, 0, s>>>(p);
-    else tiny_step_kernel<false><<<grid, TINY_THREADS, 0, s>>>(p);
+    const bool agent_out = p.agent_reward || p.agent_counts;
+    if (c->tiny_n == TINY_N) {
+      if (agent_out) tiny_step_kernel<TINY_N, true><<<grid, TINY_THREADS, 0, s>>>(p);
+      else tiny_step_kernel<TINY_N, false><<<grid, TINY_THREADS, 0, s>>>(p);
+    } else {
+      if (agent_out) tiny_step_kernel<TINY_N_BIG, true><<<grid, TINY_THREADS, 0, s>>>(p);
+      else tiny_step_kernel<TINY_N_BIG, false><<<grid, TINY_THREADS, 0, s>>>(p);
+    }
     c->launches = 1;
     if (p.auto_reset) {
-      tiny_reset_kernel<<<grid, TINY_THREADS, 0, s>>>(p, p.done);
+      if (c->tiny_n == TINY_N) tiny_reset_kernel<TINY_N><<<grid, TINY_THREADS, 0, s>>>(p, p.done);
+      else tiny_reset_kernel<TINY_N_BIG><<<grid, TINY_THREADS, 0, s>>>(p, p.done);
       c->launches = 2;
     }
     CUDA_TRY(c, cudaGetLastError());

@@ -21,31 +21,34 @@
 
 namespace swarm {
 
-constexpr int TINY_N = 8;
+constexpr int TINY_N = 8;        // largest N of the default thread-per-env kernel
+constexpr int TINY_N_BIG = 16;   // second instantiation (9..16 agents), used for large batches only
 constexpr int TINY_THREADS = 128;
 
 // c[k] = number of agents on agent k's cell (SDE:269-292); keys of padding agents are unique. Returns sum(c-1).
-__device__ __forceinline__ int tiny_counts(const unsigned (&key)[TINY_N], int (&c)[TINY_N]) {
+template <int TN>
+__device__ __forceinline__ int tiny_counts(const unsigned (&key)[TN], int (&c)[TN]) {
 #pragma unroll
-  for (int k = 0; k < TINY_N; ++k) c[k] = 1;
+  for (int k = 0; k < TN; ++k) c[k] = 1;
 #pragma unroll
-  for (int i = 0; i < TINY_N; ++i)
+  for (int i = 0; i < TN; ++i)
 #pragma unroll
-    for (int j = i + 1; j < TINY_N; ++j) {
+    for (int j = i + 1; j < TN; ++j) {
       const int eq = key[i] == key[j];
       c[i] += eq;
       c[j] += eq;
     }
   int L = 0;
 #pragma unroll
-  for (int k = 0; k < TINY_N; ++k) L += c[k] - 1;
+  for (int k = 0; k < TN; ++k) L += c[k] - 1;
   return L;
 }
 
-__device__ __forceinline__ int tiny_closest(int N, int S, int qx, int qy, const int (&ax)[TINY_N], const int (&ay)[TINY_N]) {
+template <int TN>
+__device__ __forceinline__ int tiny_closest(int N, int S, int qx, int qy, const int (&ax)[TN], const int (&ay)[TN]) {
   unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;
 #pragma unroll
-  for (int k = 0; k < TINY_N; ++k) {
+  for (int k = 0; k < TN; ++k) {
     if (k < N) {
       const int d = max(iabs(qx - ax[k]), iabs(qy - ay[k]));
       klo = min(klo, nn_key_lo(d, k));
@@ -56,38 +59,44 @@ __device__ __forceinline__ int tiny_closest(int N, int S, int qx, int qy, const 
 }
 
 // reference reset (SDE:197-221 + SDE:90-109) of one env by one thread
-__device__ __forceinline__ void tiny_reset(const StepParams& p, int env, unsigned rc, int (&x)[TINY_N], int (&y)[TINY_N],
+template <int TN>
+__device__ __forceinline__ void tiny_reset(const StepParams& p, int env, unsigned rc, int (&x)[TN], int (&y)[TN],
                                            int& px, int& py, int& target, unsigned& err) {
   const int N = p.N, S = p.S;
   const int16_t* __restrict__ tape = place_row(p, env, rc);
-  if (tape && N == TINY_N && (((uintptr_t)tape) & 15) == 0) {   // the first placement as two 128-bit loads
-    const uint4 xv = *reinterpret_cast<const uint4*>(tape);
-    const uint4 yv = *reinterpret_cast<const uint4*>(tape + TINY_N);
-    const unsigned xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+  if (tape && N == TN && (((uintptr_t)tape) & 15) == 0) {   // the first placement as 128-bit loads
+    unsigned xs[TN / 2], ys[TN / 2];
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k) {
+    for (int v = 0; v < TN / 8; ++v) {
+      const uint4 xv = *reinterpret_cast<const uint4*>(tape + 8 * v);
+      const uint4 yv = *reinterpret_cast<const uint4*>(tape + TN + 8 * v);
+      xs[4 * v] = xv.x; xs[4 * v + 1] = xv.y; xs[4 * v + 2] = xv.z; xs[4 * v + 3] = xv.w;
+      ys[4 * v] = yv.x; ys[4 * v + 1] = yv.y; ys[4 * v + 2] = yv.z; ys[4 * v + 3] = yv.w;
+    }
+#pragma unroll
+    for (int k = 0; k < TN; ++k) {
       x[k] = (int)(int16_t)((xs[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
       y[k] = (int)(int16_t)((ys[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k) {
+    for (int k = 0; k < TN; ++k) {
       x[k] = k < N ? tape_place(p, tape, env, rc, k) : 0;       // SDE:202-203: all x's then all y's
       y[k] = k < N ? tape_place(p, tape, env, rc, N + k) : 0;
     }
   }
   int cur = 2 * N;
   for (;;) {
-    unsigned key[TINY_N];
-    int c[TINY_N];
+    unsigned key[TN];
+    int c[TN];
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k) key[k] = k < N ? pack2(x[k], y[k]) : (0xFFFF0000u | (unsigned)k);
-    const int L = tiny_counts(key, c);
+    for (int k = 0; k < TN; ++k) key[k] = k < N ? pack2(x[k], y[k]) : (0xFFFF0000u | (unsigned)k);
+    const int L = tiny_counts<TN>(key, c);
     if (L == 0) break;
     if (cur + 2 * L > p.PL) { err |= SWARM_ERR_PLACE_OVERFLOW; break; }
     int off = 0;
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k) {
+    for (int k = 0; k < TN; ++k) {
       const int e = c[k] - 1;
       if (e > 0) {                                    // SDE:208-209: (2,L) block, last duplicate wins
         const int s = off + e - 1;
@@ -107,15 +116,15 @@ __device__ __forceinline__ void tiny_reset(const StepParams& p, int env, unsigne
     ++a;
     bool hit = false;
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k) hit |= (k < N) && x[k] == px && y[k] == py;
+    for (int k = 0; k < TN; ++k) hit |= (k < N) && x[k] == px && y[k] == py;
     if (!hit) break;
   }
-  target = tiny_closest(N, S, px, py, x, y);          // SDE:109
+  target = tiny_closest<TN>(N, S, px, py, x, y);          // SDE:109
 }
 
 // AGENT_OUT: per-agent rewards / counts are written (otherwise only the env totals are formed, from the packed
 // counters, without ever unpacking a per-agent value).
-template <bool AGENT_OUT>
+template <int TN, bool AGENT_OUT>
 __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_constant__ StepParams p) {
   const int env = blockIdx.x * TINY_THREADS + threadIdx.x;
   if (env >= p.E) return;
@@ -134,21 +143,27 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   }
 
   // ---- load ---------------------------------------------------------------------------------------
-  int x[TINY_N], y[TINY_N], eff[TINY_N];
-  if (N == TINY_N) {
-    const uint4 xv = *reinterpret_cast<const uint4*>(p.x + base);
-    const uint4 yv = *reinterpret_cast<const uint4*>(p.y + base);
-    const uint2 av = *reinterpret_cast<const uint2*>(p.actions + base);
-    const unsigned xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+  int x[TN], y[TN], eff[TN];
+  if (N == TN) {
+    unsigned xs[TN / 2], ys[TN / 2], as[TN / 4];
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k) {
+    for (int v = 0; v < TN / 8; ++v) {
+      const uint4 xv = *reinterpret_cast<const uint4*>(p.x + base + 8 * v);
+      const uint4 yv = *reinterpret_cast<const uint4*>(p.y + base + 8 * v);
+      const uint2 av = *reinterpret_cast<const uint2*>(p.actions + base + 8 * v);
+      xs[4 * v] = xv.x; xs[4 * v + 1] = xv.y; xs[4 * v + 2] = xv.z; xs[4 * v + 3] = xv.w;
+      ys[4 * v] = yv.x; ys[4 * v + 1] = yv.y; ys[4 * v + 2] = yv.z; ys[4 * v + 3] = yv.w;
+      as[2 * v] = av.x; as[2 * v + 1] = av.y;
+    }
+#pragma unroll
+    for (int k = 0; k < TN; ++k) {
       x[k] = (int)(int16_t)((xs[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
       y[k] = (int)(int16_t)((ys[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
-      eff[k] = (int)(((k < 4 ? av.x : av.y) >> (8 * (k & 3))) & 0xFFu);
+      eff[k] = (int)((as[k >> 2] >> (8 * (k & 3))) & 0xFFu);
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k) {
+    for (int k = 0; k < TN; ++k) {
       x[k] = k < N ? (int)p.x[base + k] : 0;
       y[k] = k < N ? (int)p.y[base + k] : 0;
       eff[k] = k < N ? (int)p.actions[base + k] : 8;
@@ -165,20 +180,20 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   {
     bool bad = false;
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k) { bad |= eff[k] > 8; eff[k] = min(eff[k], 8); }
+    for (int k = 0; k < TN; ++k) { bad |= eff[k] > 8; eff[k] = min(eff[k], 8); }
     if (bad) err |= SWARM_ERR_BAD_ACTION;
   }
 
   // ---- move (SDE:237-244, 60-80) + first collision count (SDE:246, 269-292) ---------------------------
-  int nx[TINY_N], ny[TINY_N], c[TINY_N];
-  unsigned key[TINY_N];
+  int nx[TN], ny[TN], c[TN];
+  unsigned key[TN];
 #pragma unroll
-  for (int k = 0; k < TINY_N; ++k) {
+  for (int k = 0; k < TN; ++k) {
     nx[k] = wrap1(x[k] + move_dx(eff[k]), S);
     ny[k] = wrap1(y[k] + move_dy(eff[k]), S);
     key[k] = k < N ? pack2(nx[k], ny[k]) : (0xFFFF0000u | (unsigned)k);
   }
-  int L = tiny_counts(key, c);
+  int L = tiny_counts<TN>(key, c);
   // the first 8 re-draw actions of this env are fetched now (only by envs that collided) and consumed after the
   // predator has been computed, so the load's latency is hidden
   const uint8_t* __restrict__ slab = p.slab + (size_t)env * (size_t)p.K;
@@ -191,13 +206,13 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
 
   // ---- predator (SDE:258-259, 133-165) on the OLD agent positions ------------------------------
   const int prev_px = px, prev_py = py;
-  if (retarget) target = tiny_closest(N, S, px, py, x, y);
+  if (retarget) target = tiny_closest<TN>(N, S, px, py, x, y);
   target = min(max(target, 0), N - 1);
   int orient;
   {
     int tx = 0, ty = 0;
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k)
+    for (int k = 0; k < TN; ++k)
       if (k == target) { tx = x[k]; ty = y[k]; }
     pursue(px, py, tx, ty, S, px, py, orient);
   }
@@ -209,7 +224,7 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
     if (cur + L > p.K) { err |= SWARM_ERR_SLAB_OVERFLOW; break; }
     int off = 0;
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k) {
+    for (int k = 0; k < TN; ++k) {
       const int e = c[k] - 1;
       if (e > 0) {                                        // SDE:250-252: last of its c-1 draws wins
         const int d = cur + off + e - 1;
@@ -222,13 +237,13 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
       off += e;
     }
     cur += L;
-    L = tiny_counts(key, c);                              // change_position_id again
+    L = tiny_counts<TN>(key, c);                              // change_position_id again
   }
 
   // ---- termination (SDE:307-309, 321-327) on the NEW positions ---------------------------------
   int eaten = -1;
 #pragma unroll
-  for (int k = TINY_N - 1; k >= 0; --k)
+  for (int k = TN - 1; k >= 0; --k)
     if (k < N && nx[k] == px && ny[k] == py) eaten = k;
   const bool done = eaten >= 0;
 
@@ -236,29 +251,29 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   double r_surv = 0.0, r_att = 0.0, r_rep = 0.0, r_ali = 0.0, r_sum = 0.0;
   int g_rep = 0, g_att = 0;
   if (!done) {
-    int sx[TINY_N], sy[TINY_N];
+    int sx[TN], sy[TN];
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k) { sx[k] = k < N ? nx[k] : -S; sy[k] = k < N ? ny[k] : 0; }
-    uint4 pw[TINY_N / 2];
+    for (int k = 0; k < TN; ++k) { sx[k] = k < N ? nx[k] : -S; sy[k] = k < N ? ny[k] : 0; }
+    uint4 pw[TN / 2];
 #pragma unroll
-    for (int w = 0; w < TINY_N / 2; ++w)
+    for (int w = 0; w < TN / 2; ++w)
       pw[w] = make_uint4(pack2(sx[2 * w], sx[2 * w + 1]), pack2(sy[2 * w], sy[2 * w + 1]),
                          pack2(-sx[2 * w], -sx[2 * w + 1]), pack2(-sy[2 * w], -sy[2 * w + 1]));
     const unsigned TR = rep2(p.t_rep), TA = rep2(p.t_att), TRf = rep2(p.t_repf), TAf = rep2(p.t_attf);
     const unsigned one = (unsigned)p.one, c256 = (unsigned)p.one << 8;
     // byte-packed counters: [.][0] = {rep, att}, [.][1] = {rep_far, att_far}; a byte meets at most 8 pairs
-    unsigned row[TINY_N][2], col[TINY_N / 2][2];
+    unsigned row[TN][2], col[TN / 2][2];
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k) row[k][0] = row[k][1] = 0u;
+    for (int k = 0; k < TN; ++k) row[k][0] = row[k][1] = 0u;
 #pragma unroll
-    for (int w = 0; w < TINY_N / 2; ++w) col[w][0] = col[w][1] = 0u;
+    for (int w = 0; w < TN / 2; ++w) col[w][0] = col[w][1] = 0u;
 #pragma unroll
-    for (int i = 0; i < TINY_N; ++i) {
+    for (int i = 0; i < TN; ++i) {
       const unsigned XI = rep2(sx[i]), YI = rep2(sy[i]), NXI = rep2(-sx[i]), NYI = rep2(-sy[i]);
       // even i: its own word holds (i, i+1): low half = the self pair (row only), high half = pair (i, i+1);
       // odd i: its own word holds only pairs already met; the self pair is added analytically below
 #pragma unroll
-      for (int w = (i + 1) / 2; w < TINY_N / 2; ++w) {
+      for (int w = (i + 1) / 2; w < TN / 2; ++w) {
         const unsigned m = neg_cheb2(XI, YI, NXI, NYI, pw[w]);
         const unsigned n0 = lt2(TA, m) * c256 + lt2(TR, m);
         const unsigned n1 = lt2(TAf, m) * c256 + lt2(TRf, m);
@@ -276,7 +291,7 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
     // alignment sums (SDE:346-359), vf_size == None
     int Ax = 0, Ay = 0, Dx = 0, Dy = 0, n_axis = 0, n_diag = 0;
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k) {
+    for (int k = 0; k < TN; ++k) {
       const int a = eff[k];
       if (k < N && a < 8) {
         const int mx = move_dx(a), my = move_dy(a);
@@ -290,7 +305,7 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
       float4* __restrict__ ar = p.agent_reward ? reinterpret_cast<float4*>(p.agent_reward) + base : nullptr;
       int2* __restrict__ ac = p.agent_counts ? reinterpret_cast<int2*>(p.agent_counts) + base : nullptr;
 #pragma unroll
-      for (int k = 0; k < TINY_N; ++k) {
+      for (int k = 0; k < TN; ++k) {
         if (k < N) {
           const int sh = 16 * (k & 1);
           // counts over j != k: row (pairs met as the row agent; includes the self pair for even k) + column
@@ -319,7 +334,7 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
       unsigned sR = 0u, sRf = 0u, sAbsN = 0u, sAbsF = 0u;
       const unsigned selfN = (unsigned)(selfR | (selfA << 8)), selfF = (unsigned)(selfRf | (selfAf << 8));
 #pragma unroll
-      for (int w = 0; w < TINY_N / 2; ++w) {
+      for (int w = 0; w < TN / 2; ++w) {
         const unsigned vm = (2 * w < N ? 0x0000FFFFu : 0u) | (2 * w + 1 < N ? 0xFFFF0000u : 0u);
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
@@ -347,24 +362,26 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
     if (AGENT_OUT && p.agent_reward) {
       float4* __restrict__ ar = reinterpret_cast<float4*>(p.agent_reward) + base;
 #pragma unroll
-      for (int k = 0; k < TINY_N; ++k)
+      for (int k = 0; k < TN; ++k)
         if (k < N) ar[k] = make_float4(0.f, 0.f, 0.f, k == eaten ? p.eat : 0.f);
     }
     if (AGENT_OUT && p.agent_counts) {
       int2* __restrict__ ac = reinterpret_cast<int2*>(p.agent_counts) + base;
 #pragma unroll
-      for (int k = 0; k < TINY_N; ++k)
+      for (int k = 0; k < TN; ++k)
         if (k < N) ac[k] = make_int2(0, 0);
     }
   }
   if (p.eff_action) {
-    if (N == TINY_N) {
-      *reinterpret_cast<uint2*>(p.eff_action + base) =
-          make_uint2((unsigned)(eff[0] | (eff[1] << 8) | (eff[2] << 16) | (eff[3] << 24)),
-                     (unsigned)(eff[4] | (eff[5] << 8) | (eff[6] << 16) | (eff[7] << 24)));
+    if (N == TN) {
+#pragma unroll
+      for (int v = 0; v < TN / 8; ++v)
+        *reinterpret_cast<uint2*>(p.eff_action + base + 8 * v) =
+            make_uint2((unsigned)(eff[8 * v] | (eff[8 * v + 1] << 8) | (eff[8 * v + 2] << 16) | (eff[8 * v + 3] << 24)),
+                       (unsigned)(eff[8 * v + 4] | (eff[8 * v + 5] << 8) | (eff[8 * v + 6] << 16) | (eff[8 * v + 7] << 24)));
     } else {
 #pragma unroll
-      for (int k = 0; k < TINY_N; ++k)
+      for (int k = 0; k < TN; ++k)
         if (k < N) p.eff_action[base + k] = (uint8_t)eff[k];
     }
   }
@@ -406,19 +423,22 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   if (done) {
     if (p.term_x) {
 #pragma unroll
-      for (int k = 0; k < TINY_N; ++k)
+      for (int k = 0; k < TN; ++k)
         if (k < N) { p.term_x[base + k] = (int16_t)nx[k]; p.term_y[base + k] = (int16_t)ny[k]; }
     }
     if (!p.auto_reset) p.frozen[env] = 1;               // auto-reset: tiny_reset_kernel follows, masked by done
   }
-  if (N == TINY_N) {
-    *reinterpret_cast<uint4*>(p.x + base) =
-        make_uint4(pack2(nx[0], nx[1]), pack2(nx[2], nx[3]), pack2(nx[4], nx[5]), pack2(nx[6], nx[7]));
-    *reinterpret_cast<uint4*>(p.y + base) =
-        make_uint4(pack2(ny[0], ny[1]), pack2(ny[2], ny[3]), pack2(ny[4], ny[5]), pack2(ny[6], ny[7]));
+  if (N == TN) {
+#pragma unroll
+    for (int v = 0; v < TN / 8; ++v) {
+      *reinterpret_cast<uint4*>(p.x + base + 8 * v) = make_uint4(pack2(nx[8 * v], nx[8 * v + 1]), pack2(nx[8 * v + 2], nx[8 * v + 3]),
+                                                                 pack2(nx[8 * v + 4], nx[8 * v + 5]), pack2(nx[8 * v + 6], nx[8 * v + 7]));
+      *reinterpret_cast<uint4*>(p.y + base + 8 * v) = make_uint4(pack2(ny[8 * v], ny[8 * v + 1]), pack2(ny[8 * v + 2], ny[8 * v + 3]),
+                                                                 pack2(ny[8 * v + 4], ny[8 * v + 5]), pack2(ny[8 * v + 6], ny[8 * v + 7]));
+    }
   } else {
 #pragma unroll
-    for (int k = 0; k < TINY_N; ++k)
+    for (int k = 0; k < TN; ++k)
       if (k < N) { p.x[base + k] = (int16_t)nx[k]; p.y[base + k] = (int16_t)ny[k]; }
   }
   p.px[env] = (int16_t)px;
@@ -431,6 +451,7 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
 // Masked reset of finished envs (auto-reset after tiny_step_kernel).  Finished envs are rare (a few per cent) and
 // scattered, so each CTA first compacts its finished envs into a shared list and then resets them with consecutive
 // threads: one or two warps run the (long, divergent) reset code instead of every warp running it for one lane.
+template <int TN>
 __global__ void __launch_bounds__(TINY_THREADS) tiny_reset_kernel(const __grid_constant__ StepParams p,
                                                                    const uint8_t* __restrict__ mask) {
   __shared__ int s_list[TINY_THREADS];
@@ -448,11 +469,11 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_reset_kernel(const __grid_c
   const size_t base = (size_t)env * (size_t)N;
   const unsigned rc = p.reset_count[env];
   p.reset_count[env] = rc + 1u;
-  int x[TINY_N], y[TINY_N], px, py, target;
+  int x[TN], y[TN], px, py, target;
   unsigned err = 0;
-  tiny_reset(p, env, rc, x, y, px, py, target, err);
+  tiny_reset<TN>(p, env, rc, x, y, px, py, target, err);
 #pragma unroll
-  for (int k = 0; k < TINY_N; ++k)
+  for (int k = 0; k < TN; ++k)
     if (k < N) { p.x[base + k] = (int16_t)x[k]; p.y[base + k] = (int16_t)y[k]; }
   p.px[env] = (int16_t)px;
   p.py[env] = (int16_t)py;

@@ -51,8 +51,8 @@ extern "C" {
 /* limits */
 #define SWARM_MAX_AGENTS 16384
 #define SWARM_MAX_GRID 16384
-#define SWARM_FUSED_MAX_AGENTS 256   /* N <= this: fused kernels (thread per env for N <= 8, lane group per env
-                                        above); larger N: staged kernels */
+#define SWARM_FUSED_MAX_AGENTS 256   /* N <= this: fused kernels (thread per env for N <= 8 -- N <= 16 in batches of
+                                        >= 65,536 envs --, lane group per env above); larger N: staged kernels */
 
 /* swarm_config.path */
 #define SWARM_PATH_AUTO 0

@@ -110,6 +110,23 @@ def test_oracle_lockstep_tiny_and_group_kernels(N, S):
                          K=512 if dense else None, KR=2000 if dense else None, weights=(0.5, 1.0, 0.25))
 
 
+@pytest.mark.parametrize("N,S", [(9, 16), (12, 7), (13, 40), (16, 32), (16, 8)])
+def test_oracle_lockstep_tiny16_kernel(N, S, monkeypatch):
+    """9..16 agents: the 16-agent instantiation of the thread-per-env kernel (normally chosen only for batches of
+    >= 65,536 envs; SWARM_TINY16_MIN_ENVS lowers the bar so that the oracle can follow)."""
+    from gym_swarm_b200.envs import BatchedSwarmEnv
+    monkeypatch.setenv("SWARM_TINY16_MIN_ENVS", "1")
+    env = BatchedSwarmEnv(4, N, S)
+    assert env.path_name.startswith("tiny<16>"), env.path_name
+    env.close()
+    dense = S * S < 4 * N
+    _oracle_lockstep(E=70, N=N, S=S, T=25, seed=N * 7 + S, n_actions=9, K=512 if dense else None,
+                     KR=2000 if dense else None, weights=(0.5, 1.0, 0.25))
+    for (att, rep) in ((5, 2), (2, 5), (0, 0), (30, 3), (10, 200)):
+        _oracle_lockstep(E=70, N=N, S=S, T=8, seed=N * 3 + S + att, n_actions=9, att=att, rep=rep, agent_out=False,
+                         K=512 if dense else None, KR=2000 if dense else None)
+
+
 def test_tiny_kernel_is_the_default_for_small_n():
     from gym_swarm_b200.envs import BatchedSwarmEnv
     for N, name in ((8, "tiny<8>"), (4, "tiny<8>"), (9, "fused<8,2>"), (16, "fused<8,2>")):

@@ -126,6 +126,8 @@ def test_properties_cfg2_full_size():
     (1 << 18, 8, 16, ("auto", "group", "staged")),                # cfg5 shape: thread per env == lane group == staged
     (16, 16384, 1024, ("auto", "staged_pairwise")),               # cfg4: box counts == symmetric tiled pairwise
     (4096, 16, 32, ("auto", "staged")),                           # cfg2
+    (1 << 17, 16, 32, ("auto", "group")),                         # big batch of 16-agent envs: tiny<16> == lane group
+    (1 << 16, 11, 20, ("auto", "group")),
 ])
 def test_kernel_paths_agree_at_full_size(E, N, S, paths):
     """Same seeds through different kernel paths: every integer state / output tensor identical; float rewards (the same

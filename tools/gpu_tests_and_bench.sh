@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1; echo tests rc=$?; tail -4 gpurun_out/gpu_tests.log
-for c in cfg5 cfg3 cfg4; do timeout 300 python bench.py --config $c --steps 96 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; python - <<PY
+for c in ${CFGS:-cfg5 cfg3 cfg4}; do timeout 300 python bench.py --config $c --steps 96 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; python - <<PY
 import json
 try:
     d=json.loads(open('gpurun_out/bench_$c.json').read().strip().splitlines()[-1])
@@ -8,4 +8,3 @@ try:
 except Exception as e: print("fail", e)
 PY
 done
-python tools/kernel_roofline.py predator | cut -c1-330
