@@ -1413,6 +1413,180 @@ __global__ void __launch_bounds__(1024) reset_kernel(const StepParams p, const S
 }
 
 // ------------------------------------------------------------------------------------------------
+// K7b: reference reset with the env's occupancy bitmap in shared memory (same machinery as collide_bitmap_kernel:
+// bitmap hits -> per-cell hit counts in a shared hash -> block scan for the re-draw slots; the thread's <= 16
+// positions stay in registers).  The global-hash reset_kernel above took ~0.3 ms per finished 16,384-agent env --
+// longer than the whole step.  A round with more hits than the shared hash can take falls back to the global hash.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) reset_bitmap_kernel(const StepParams p, const StagedScratch sc, int bm_words,
+                                                            const uint8_t* __restrict__ mask, int mode) {
+  extern __shared__ __align__(16) unsigned coll_smem[];
+  __shared__ BlockScratch bs;
+  unsigned* sbit = coll_smem;                    // [bm_words]
+  unsigned* hkeys = coll_smem + bm_words;        // [COLL_HC]
+  unsigned* hcnt = hkeys + COLL_HC;              // [COLL_HC]
+  const int N = p.N, S = p.S;
+  const EnvHash gh = env_hash(sc, N);
+  const int per = (N + blockDim.x - 1) / blockDim.x;
+  const int lo = min(N, (int)threadIdx.x * per), hi = min(N, lo + per);
+  const int nown = hi - lo;
+  bool smem_ready = false;
+  for (int env = blockIdx.x; env < p.E; env += gridDim.x) {
+    if (mode == 1 && mask && !mask[env]) continue;
+    if (mode == 1 && p.frozen[env]) continue;      // frozen envs report done=1 but are never reset
+    if (!smem_ready) {                             // (uniform per CTA) zero the bitmap / hash only when there is work
+      for (int w = threadIdx.x; w < bm_words; w += blockDim.x) sbit[w] = 0u;
+      for (int w = threadIdx.x; w < COLL_HC; w += blockDim.x) { hkeys[w] = HASH_EMPTY; hcnt[w] = 0u; }
+      smem_ready = true;
+    }
+    const size_t base = (size_t)env * (size_t)N;
+    int16_t* __restrict__ x = p.x + base;
+    int16_t* __restrict__ y = p.y + base;
+    unsigned rc = mode == 0 ? 0u : p.reset_count[env];
+    __syncthreads();
+    if (threadIdx.x == 0) p.reset_count[env] = rc + 1u;
+    const int16_t* __restrict__ tape = place_row(p, env, rc);
+    unsigned err = 0;
+    unsigned pos[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k)                   // SDE:202-203
+      pos[k] = k < nown ? pack2(tape_place(p, tape, env, rc, lo + k), tape_place(p, tape, env, rc, N + lo + k)) : 0u;
+    int cur = 2 * N;
+    for (;;) {
+      unsigned hitmask = 0u;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (k < nown) {
+          const int cell = (int)(pos[k] >> 16) * S + (int)(pos[k] & 0xFFFFu);
+          const unsigned bit = 1u << (cell & 31);
+          if (atomicOr(&sbit[cell >> 5], bit) & bit) hitmask |= 1u << k;
+        }
+      }
+      const int H = block_sum(__popc(hitmask), bs);
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k < nown) sbit[((int)(pos[k] >> 16) * S + (int)(pos[k] & 0xFFFFu)) >> 5] = 0u;
+      if (H == 0) { __syncthreads(); break; }
+      unsigned long long cpack = 0ull;
+      int extra = 0;
+      int big = 0;                                   // a cell with more than 16 agents: the 4-bit slots cannot hold it
+      const bool small = H <= COLL_HC / 2;
+      if (small) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (hitmask & (1u << k)) hash_insert(hkeys, hcnt, COLL_HC - 1, 12, pos[k]);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (k < nown) {
+            const unsigned key = pos[k];
+            unsigned sl = hash_slot(key, 12);
+            unsigned cnt = 0u;
+            for (;;) {
+              const unsigned kk = hkeys[sl];
+              if (kk == key) { cnt = hcnt[sl]; break; }
+              if (kk == HASH_EMPTY) break;
+              sl = (sl + 1u) & (COLL_HC - 1);
+            }
+            big |= cnt > 15u;
+            cnt = min(cnt, 15u);
+            cpack |= (unsigned long long)cnt << (4 * k);
+            extra += (int)cnt;
+          }
+        }
+      } else {                                       // very dense placement: exact counts from the global hash
+        for (int k = 0; k < nown; ++k) {
+          unsigned pk = 0u;
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (q == k) pk = pos[q];
+          x[lo + k] = (int16_t)(pk & 0xFFFFu);
+          y[lo + k] = (int16_t)(pk >> 16);
+        }
+        __syncthreads();
+        hash_count_extra(gh, lo, hi, [&](int i) { return pack2(x[i], y[i]); });
+        extra = 0;
+        for (int i = lo; i < hi; ++i) {
+          const int e = hash_c(gh, i) - 1;
+          big |= e > 15;
+          cpack |= (unsigned long long)min(e, 15) << (4 * (i - lo));
+          extra += min(e, 15);
+        }
+      }
+      int L;
+      int off = block_excl_scan(extra, L, bs);
+      // (more than 16 agents drawn onto one cell is treated like an exhausted tape: flagged, never silently wrong)
+      const bool overflow = cur + 2 * L > p.PL || __syncthreads_or(big);
+      if (!overflow) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int e = (int)((cpack >> (4 * k)) & 15ull);
+          if (e > 0) {                                // SDE:208-209: (2,L) block, last duplicate wins
+            const int sidx = off + e - 1;
+            pos[k] = pack2(tape_place(p, tape, env, rc, cur + sidx), tape_place(p, tape, env, rc, cur + L + sidx));
+          }
+          off += e;
+        }
+      }
+      if (small) {
+        for (int w = threadIdx.x; w < COLL_HC; w += blockDim.x) { hkeys[w] = HASH_EMPTY; hcnt[w] = 0u; }
+        __syncthreads();
+      } else {
+        hash_clear(gh, lo, hi);
+      }
+      if (overflow) { err |= SWARM_ERR_PLACE_OVERFLOW; break; }
+      cur += 2 * L;
+    }
+    const int16_t* __restrict__ pt = ptape_row(p, env, rc);
+    int a = 0, px = 0, py = 0;
+    for (;;) {                                        // SDE:92-105
+      if (a >= p.KP) { err |= SWARM_ERR_PRED_OVERFLOW; break; }
+      tape_pred(p, pt, env, rc, a, px, py);
+      ++a;
+      const unsigned pk = pack2(px, py);
+      int hit = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) hit |= (k < nown) && pos[k] == pk;
+      if (!__syncthreads_or(hit)) break;
+    }
+    unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;    // SDE:109
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (k < nown) {
+        const int xi = (int)(pos[k] & 0xFFFFu), yi = (int)(pos[k] >> 16);
+        x[lo + k] = (int16_t)xi;
+        y[lo + k] = (int16_t)yi;
+        const int d = max(iabs(px - xi), iabs(py - yi));
+        klo = min(klo, nn_key_lo(d, lo + k));
+        khi = min(khi, nn_key_hi(d, lo + k));
+      }
+    }
+    klo = block_umin(klo, bs);
+    khi = block_umin(khi, bs);
+    if (threadIdx.x == 0) {
+      p.px[env] = (int16_t)px;
+      p.py[env] = (int16_t)py;
+      p.target[env] = nn_pick(klo, khi, S);
+      p.orient[env] = 0;
+      if (mode == 0) {
+        p.frozen[env] = 0;
+        p.err[env] = err;
+      } else if (err) {
+        p.err[env] |= err;
+      }
+      if (p.track_stats && mode == 0) {
+        p.ep_len[env] = 0u;
+        reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
+        p.fin_count[env] = 0u;
+        p.fin_len[env] = 0u;
+        reinterpret_cast<float4*>(p.fin_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // standalone swarm_pairwise epilogue: accumulators -> (rew_rep_i, rew_attr_i)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pair_counts_kernel(const StepParams p, const unsigned* __restrict__ pcounts,

@@ -236,6 +236,8 @@ static int staged_alloc(Ctx* c) {
       c->box = bp;
       CUDA_TRY(c, cudaFuncSetAttribute(collide_bitmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        c->coll_smem_bytes));
+      CUDA_TRY(c, cudaFuncSetAttribute(reset_bitmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(words * 4 + (long long)COLL_HC * 8)));
       CUDA_TRY(c, cudaFuncSetAttribute(boxcount_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(words * 4 + 2LL * S * 4)));
     }
@@ -535,7 +537,11 @@ static int do_reset(Ctx* c, const uint8_t* mask, int mode, cudaStream_t s) {
     FUSED_DISPATCH(c, CALL);
 #undef CALL
   } else {
-    reset_kernel<<<c->sc.env_grid, c->per_env_threads, 0, s>>>(p, c->sc, mask, mode);
+    if (c->coll_bm_words > 0)
+      reset_bitmap_kernel<<<c->sc.env_grid, c->per_env_threads, c->coll_bm_words * 4 + COLL_HC * 8, s>>>(
+          p, c->sc, c->coll_bm_words, mask, mode);
+    else
+      reset_kernel<<<c->sc.env_grid, c->per_env_threads, 0, s>>>(p, c->sc, mask, mode);
     CUDA_TRY(c, cudaGetLastError());
   }
   c->launches = 1;
@@ -657,7 +663,11 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     else { finalize_agents_kernel<false><<<ga, 256, 0, s>>>(p, sc); finalize_env_kernel<false><<<ge, 128, 0, s>>>(p, sc); }
   }
   if (p.auto_reset) {
-    reset_kernel<<<sc.env_grid, c->per_env_threads, 0, s>>>(p, sc, p.done, 1);
+    if (c->coll_bm_words > 0)
+      reset_bitmap_kernel<<<sc.env_grid, c->per_env_threads, c->coll_bm_words * 4 + COLL_HC * 8, s>>>(p, sc, c->coll_bm_words,
+                                                                                                      p.done, 1);
+    else
+      reset_kernel<<<sc.env_grid, c->per_env_threads, 0, s>>>(p, sc, p.done, 1);
     c->launches += 1;
   }
   CUDA_TRY(c, cudaGetLastError());
