@@ -602,8 +602,9 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     }
     c->launches = 1;
     if (p.auto_reset) {
-      if (c->tiny_n == TINY_N) tiny_reset_kernel<TINY_N><<<grid, TINY_THREADS, 0, s>>>(p, p.done);
-      else tiny_reset_kernel<TINY_N_BIG><<<grid, TINY_THREADS, 0, s>>>(p, p.done);
+      const int rgrid = (p.E + TINY_RESET_SPAN - 1) / TINY_RESET_SPAN;
+      if (c->tiny_n == TINY_N) tiny_reset_kernel<TINY_N><<<rgrid, TINY_THREADS, 0, s>>>(p, p.done);
+      else tiny_reset_kernel<TINY_N_BIG><<<rgrid, TINY_THREADS, 0, s>>>(p, p.done);
       c->launches = 2;
     }
     CUDA_TRY(c, cudaGetLastError());

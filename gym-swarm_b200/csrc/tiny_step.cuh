@@ -449,37 +449,52 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
 }
 
 // Masked reset of finished envs (auto-reset after tiny_step_kernel).  Finished envs are rare (a few per cent) and
-// scattered, so each CTA first compacts its finished envs into a shared list and then resets them with consecutive
-// threads: one or two warps run the (long, divergent) reset code instead of every warp running it for one lane.
+// scattered, so each CTA first compacts the finished envs among its TINY_RESET_SPAN envs into a shared list and then
+// resets them with consecutive threads: a couple of full warps run the (long, divergent) reset code, with all their
+// dependent tape loads in flight together, instead of every warp running it for one lane.
+constexpr int TINY_RESET_SPAN = TINY_THREADS * 8;     // envs scanned per CTA (8 mask bytes = one 64-bit load per thread)
+
 template <int TN>
 __global__ void __launch_bounds__(TINY_THREADS) tiny_reset_kernel(const __grid_constant__ StepParams p,
                                                                    const uint8_t* __restrict__ mask) {
-  __shared__ int s_list[TINY_THREADS];
+  __shared__ int s_list[TINY_RESET_SPAN];
   __shared__ int s_count;
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
   {
-    const int e = blockIdx.x * TINY_THREADS + threadIdx.x;
-    if (e < p.E && mask[e]) s_list[atomicAdd(&s_count, 1)] = e;
+    const long long e0 = (long long)blockIdx.x * TINY_RESET_SPAN + (long long)threadIdx.x * 8;
+    if (e0 + 8 <= p.E && ((((uintptr_t)mask) + (uintptr_t)e0) & 7) == 0) {
+      const uint2 m = *reinterpret_cast<const uint2*>(mask + e0);
+      if (m.x | m.y) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (((q < 4 ? m.x : m.y) >> (8 * (q & 3))) & 0xFFu) s_list[atomicAdd(&s_count, 1)] = (int)e0 + q;
+      }
+    } else {
+      for (int q = 0; q < 8; ++q)
+        if (e0 + q < p.E && mask[e0 + q]) s_list[atomicAdd(&s_count, 1)] = (int)e0 + q;
+    }
   }
   __syncthreads();
-  if ((int)threadIdx.x >= s_count) return;
-  const int env = s_list[threadIdx.x];
+  const int count = s_count;
   const int N = p.N;
-  const size_t base = (size_t)env * (size_t)N;
-  const unsigned rc = p.reset_count[env];
-  p.reset_count[env] = rc + 1u;
-  int x[TN], y[TN], px, py, target;
-  unsigned err = 0;
-  tiny_reset<TN>(p, env, rc, x, y, px, py, target, err);
+  for (int q = threadIdx.x; q < count; q += TINY_THREADS) {
+    const int env = s_list[q];
+    const size_t base = (size_t)env * (size_t)N;
+    const unsigned rc = p.reset_count[env];
+    p.reset_count[env] = rc + 1u;
+    int x[TN], y[TN], px, py, target;
+    unsigned err = 0;
+    tiny_reset<TN>(p, env, rc, x, y, px, py, target, err);
 #pragma unroll
-  for (int k = 0; k < TN; ++k)
-    if (k < N) { p.x[base + k] = (int16_t)x[k]; p.y[base + k] = (int16_t)y[k]; }
-  p.px[env] = (int16_t)px;
-  p.py[env] = (int16_t)py;
-  p.target[env] = target;
-  p.orient[env] = 0;                                    // SDE:107
-  if (err) p.err[env] |= err;
+    for (int k = 0; k < TN; ++k)
+      if (k < N) { p.x[base + k] = (int16_t)x[k]; p.y[base + k] = (int16_t)y[k]; }
+    p.px[env] = (int16_t)px;
+    p.py[env] = (int16_t)py;
+    p.target[env] = target;
+    p.orient[env] = 0;                                    // SDE:107
+    if (err) p.err[env] |= err;
+  }
 }
 
 }  // namespace swarm
