@@ -50,6 +50,35 @@ def test_golden_staged_path(name):
     impl.env.close()
 
 
+def _small_n_cases(lo, hi):
+    out = []
+    for n in case_names():
+        cfg, _ = load_case(n)
+        if lo <= cfg["N"] <= hi:
+            out.append(n)
+    return out
+
+
+@pytest.mark.parametrize("name", _small_n_cases(2, 8))
+def test_golden_lane_group_kernel_small_n(name):
+    """Fixtures with N <= 8 normally run on the thread-per-env kernel; the lane-group kernel must reproduce them too."""
+    cfg, z = load_case(name)
+    impl = CudaImpl(cfg, z, "group")
+    replay(impl, cfg, z, steps=120)
+    impl.env.close()
+
+
+@pytest.mark.parametrize("name", _small_n_cases(9, 16))
+def test_golden_thread_per_env_kernel_16(name, monkeypatch):
+    """Fixtures with 9..16 agents through the 16-agent thread-per-env kernel (normally reserved for huge batches)."""
+    monkeypatch.setenv("SWARM_TINY16_MIN_ENVS", "1")
+    cfg, z = load_case(name)
+    impl = CudaImpl(cfg, z, "auto")
+    assert impl.env.path_name.startswith("tiny<16>") or cfg["vf"] is not None, impl.env.path_name
+    replay(impl, cfg, z, steps=150)
+    impl.env.close()
+
+
 def _oracle_lockstep(E, N, S, T, seed, path="auto", att=5, rep=2, eat=-10.0, vf=None, n_actions=8, K=None, KR=None,
                      weights=(1.0, 1.0, 1.0), auto_reset=True, check_agents=True, agent_out=True):
     from gym_swarm_b200 import tapes
