@@ -1,17 +1,20 @@
 // staged.cuh -- the staged transition for large N (N > 256, up to 16384 agents per env) and the
 // standalone roofline kernels named by the C ABI (swarm_move / swarm_predator / swarm_pairwise).
 //
-//   K1 move_kernel        flat, 128-bit vectorised; HBM bound         SDE:60-80, 467-475
-//   K2 collide_kernel     CTA per env, exact occupancy counts via a global (L2-resident) hash
-//                         table + block scan for the re-draw slots     SDE:246-255, 269-292
-//   K3 predator_kernel    warp per env, shuffle argmin, pursuit, termination test
-//                                                                       SDE:111-165, 307-309
-//   K4 pairprep_kernel    packs positions into 16x2 "pair words"
-//   K5 pairwise_kernel    persistent, statically partitioned (env, i-tile, j-chunk) units; the j-chunk
-//                         is staged in shared memory by a TMA bulk copy (cp.async.bulk + mbarrier,
-//                         double buffered) and swept with DPX VIADDMNMX.S16x2 ops   SDE:330-343
-//   K6 finalize_kernel    CTA per env: reward epilogue, statistics, commit   SDE:363-379, 260
-//   K7 reset_kernel       CTA per env (masked): reference reset            SDE:197-221, 90-109
+//   K1  move_kernel             flat, 128-bit vectorised; HBM bound                    SDE:60-80, 467-475
+//   K2  collide_kernel          CTA per env, exact occupancy counts via a global (L2-resident) hash table + block
+//                               scan for the re-draw slots (grids too large for shared memory)   SDE:246-255, 269-292
+//   K2b collide_bitmap_kernel   the same rounds on the env's occupancy bitmap in SHARED memory, positions in registers
+//   K2c boxcount_kernel         reward threshold counts as box popcounts on that bitmap (also inside K2b)   SDE:330-343
+//   K3  predator_{group,block}_kernel  lane group / CTA per env: shuffle arg-min, pursuit, termination test
+//                                                                                       SDE:111-165, 307-309
+//   K4  pairprep_kernel         packs positions into 16x2 "pair words", per-env alignment sums
+//   K5s pairwise_sym_kernel     symmetric tile sweep (ring of 128-agent tiles per warp), DPX + IMAD counters  SDE:330-343
+//   K5  pairwise_kernel<true>   vf_size variant: row sweep, j-chunks staged by TMA bulk copies (cp.async.bulk +
+//                               mbarrier, double buffered)
+//   K6a/b finalize_{agents,env}_kernel  flat per-agent epilogue + per-env reward / statistics   SDE:363-379, 260
+//   K7  reset_kernel / K7b reset_bitmap_kernel  CTA per env (masked): reference reset       SDE:197-221, 90-109
+//   observe_vf_kernel           visual-field windows (the policy-side output)
 //
 // (SDE = /root/reference/gym_swarm/envs/swarm_discrete_env.py)
 #pragma once
