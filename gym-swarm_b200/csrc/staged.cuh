@@ -1626,14 +1626,17 @@ __global__ void __launch_bounds__(OBS_CHUNK) observe_vf_kernel(int E, int N, int
   const int W = 2 * vf + 1, WW = W * W;
   int* spos = reinterpret_cast<int*>(obs_smem);                   // [N] packed (x | y << 16)
   unsigned* sbit = reinterpret_cast<unsigned*>(spos + N);         // [bm_words] (BITMAP)
-  unsigned char* swin = reinterpret_cast<unsigned char*>(sbit + bm_words);   // [OBS_CHUNK][WW]
+  unsigned char* swin = obs_smem + (((size_t)(N + bm_words) * 4 + 15) & ~(size_t)15);   // [OBS_CHUNK][WW], 16 B aligned
   const int chunks = (N + OBS_CHUNK - 1) / OBS_CHUNK;
   const int env = blockIdx.x / chunks, i0 = (blockIdx.x % chunks) * OBS_CHUNK;
   const size_t base = (size_t)env * (size_t)N;
   if (BITMAP)
     for (int w = threadIdx.x; w < bm_words; w += OBS_CHUNK) sbit[w] = 0u;
   const int nwin = min(OBS_CHUNK, N - i0) * WW;
-  for (int q = threadIdx.x; q < nwin; q += OBS_CHUNK) swin[q] = 0;
+  {                                                    // (swin is 4-byte aligned: it follows two word arrays)
+    unsigned* w32 = reinterpret_cast<unsigned*>(swin);
+    for (int q = threadIdx.x; q < (nwin + 3) / 4; q += OBS_CHUNK) w32[q] = 0u;
+  }
   __syncthreads();
   for (int j = threadIdx.x; j < N; j += OBS_CHUNK) {
     const int xj = x[base + j], yj = y[base + j];
@@ -1673,7 +1676,15 @@ __global__ void __launch_bounds__(OBS_CHUNK) observe_vf_kernel(int E, int N, int
   }
   __syncthreads();
   uint8_t* __restrict__ o = out + (base + i0) * (size_t)WW;
-  for (int q = threadIdx.x; q < nwin; q += OBS_CHUNK) o[q] = swin[q];
+  if ((((uintptr_t)o) & 15) == 0) {                     // the chunk's windows leave as 128-bit stores
+    const uint4* s16 = reinterpret_cast<const uint4*>(swin);
+    uint4* o16 = reinterpret_cast<uint4*>(o);
+    const int n16 = nwin >> 4;
+    for (int q = threadIdx.x; q < n16; q += OBS_CHUNK) o16[q] = s16[q];
+    for (int q = (n16 << 4) + threadIdx.x; q < nwin; q += OBS_CHUNK) o[q] = swin[q];
+  } else {
+    for (int q = threadIdx.x; q < nwin; q += OBS_CHUNK) o[q] = swin[q];
+  }
 }
 
 }  // namespace swarm

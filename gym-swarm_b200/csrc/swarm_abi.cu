@@ -768,7 +768,7 @@ int swarm_observe_vf(int32_t E, int32_t N, int32_t S, int32_t vf, const int16_t*
   const long long words = (cells + 31) / 32 + 1;
   const bool bitmap = words * 4 <= 160 * 1024;                       // the env's occupancy bitmap fits in shared memory
   const int bm_words = bitmap ? (int)words : 0;
-  const int smem = N * 4 + bm_words * 4 + OBS_CHUNK * W * W;
+  const int smem = ((N + bm_words) * 4 + 15) / 16 * 16 + OBS_CHUNK * W * W + 16;
   static int opted[2] = {0, 0};
   if (smem > 48 * 1024 && opted[bitmap] < smem) {
     if (bitmap) CUDA_TRY(nullptr, cudaFuncSetAttribute(observe_vf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
