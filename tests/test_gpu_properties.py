@@ -11,6 +11,12 @@ Properties (SDE = swarm_discrete_env.py):
   P6  integer identities: global counts == sum of the per-agent counts (SDE:338/372, 343/373)
   P7  episode statistics: finished episodes == number of done flags seen; lengths add up to the steps taken
   P8  no sticky error bit
+  P10 integer reward counts, exactly, on a strided subset of envs (first and last included): global and per-agent
+      repulsion / attraction counts recomputed from the new positions with the literal N x N formulas of SDE:330-343
+  P9  predator, exactly, for every env: on a retarget step the target is the canonical nearest
+      agent of the PRE-move positions (SDE:111-131: lowest index at the minimum Chebyshev distance, the highest one when
+      lowest != highest and 2 d_min >= S), otherwise it is unchanged; the predator then moves one cell towards the
+      target's PRE-move cell, both axes negated when the signed max offset exceeds S // 2 (SDE:142-165)
 """
 import numpy as np
 import pytest
@@ -21,6 +27,23 @@ pytestmark = pytest.mark.gpu
 def _torus_step_ok(a, b, S):
     d = (b.int() - a.int()).abs()
     return (d <= 1) | (d == S - 1)
+
+
+def _literal_counts(nx, ny, S, rep, att, rows=1024):
+    """SDE:330-343 / 371-373 on [n, N] position tensors -> per-agent [n, N, 2] and global [n, 2] integer counts."""
+    import torch
+    n, N = nx.shape
+    per_agent = torch.zeros((n, N, 2), dtype=torch.int64, device=nx.device)
+    for r0 in range(0, N, rows):
+        xr, yr = nx[:, r0:r0 + rows, None].int(), ny[:, r0:r0 + rows, None].int()
+        D = torch.maximum((xr - nx[:, None, :].int()).abs(), (yr - ny[:, None, :].int()).abs())
+        D2 = S - D
+        R = (D < rep).int() + (D2 < rep).int()
+        A = ((D < att) == (D >= rep)).int() + ((D2 < att) == (D2 >= rep)).int()
+        per_agent[:, r0:r0 + rows, 0] = -(R.sum(2, dtype=torch.int64) - 1)
+        per_agent[:, r0:r0 + rows, 1] = A.sum(2, dtype=torch.int64)
+    glob = per_agent.sum(1)
+    return per_agent, glob
 
 
 def _run_properties(E, N, S, T, per_agent, path="auto", seed=0):
@@ -39,6 +62,7 @@ def _run_properties(E, N, S, T, per_agent, path="auto", seed=0):
     for t in range(T):
         x0, y0 = env.x.clone(), env.y.clone()
         px0, py0 = env.px.clone(), env.py.clone()
+        tgt0 = env.target.clone()
         actions = torch.randint(0, 8, (E, N), dtype=torch.uint8, device=dev, generator=g)
         retarget = (torch.rand((E,), device=dev, generator=g) < 0.1).to(torch.uint8)
         slab = torch.randint(0, 8, (E, env.K), dtype=torch.uint8, device=dev, generator=g)
@@ -63,6 +87,23 @@ def _run_properties(E, N, S, T, per_agent, path="auto", seed=0):
         assert bool(_torus_step_ok(px0, pn[:, 0], S).all()) and bool(_torus_step_ok(py0, pn[:, 1], S).all())
         tgt = info["predator_target"]
         assert int(tgt.min()) >= 0 and int(tgt.max()) < N
+        # P9
+        d0 = torch.maximum((px0[:, None].int() - x0.int()).abs(), (py0[:, None].int() - y0.int()).abs())
+        dmin = d0.min(dim=1).values
+        at_min = d0 == dmin[:, None]
+        lo = at_min.int().argmax(dim=1)
+        hi = (N - 1) - at_min.flip(1).int().argmax(dim=1)
+        nearest = torch.where((lo == hi) | (2 * dmin < S), lo, hi)
+        want_tgt = torch.where(retarget.bool(), nearest, tgt0.long())
+        assert bool(torch.equal(tgt.long(), want_tgt)), "predator target"     # (the step's target, also for done envs)
+        step_tgt = tgt.long()
+        cdx = px0.int() - x0.gather(1, step_tgt[:, None]).squeeze(1).int()
+        cdy = py0.int() - y0.gather(1, step_tgt[:, None]).squeeze(1).int()
+        flip = torch.where(torch.maximum(cdx, cdy) > S // 2, -1, 1)
+        want_px = torch.remainder(px0.int() - torch.sign(cdx) * flip, S)
+        want_py = torch.remainder(py0.int() - torch.sign(cdy) * flip, S)
+        assert bool(torch.equal(pn[:, 0].int(), want_px)) and bool(torch.equal(pn[:, 1].int(), want_py)), "predator move"
+        del d0, at_min
         # P4
         hit = (nx == pn[:, 0:1]) & (ny == pn[:, 1:2])
         assert bool(torch.equal(hit.any(dim=1), done_b))
@@ -86,6 +127,14 @@ def _run_properties(E, N, S, T, per_agent, path="auto", seed=0):
             assert bool(torch.equal(ac.sum(dim=1, dtype=torch.int64), reward["counts"].long()))
             ar = reward["agents"]
             assert bool((ar[done_b][:, :, :3] == 0).all())
+        # P10
+        sel = torch.unique(torch.linspace(0, E - 1, 256 if N <= 256 else 2, device=dev).long())
+        sel = sel[live[sel]]
+        if sel.numel() > 0:
+            pa, gl = _literal_counts(nx[sel], ny[sel], S, 2, 5)
+            assert bool(torch.equal(reward["counts"][sel].long(), gl)), "global counts"
+            if per_agent:
+                assert bool(torch.equal(env.agent_counts[sel].long(), pa)), "per-agent counts"
         dones_seen += done_b.sum()
     # P7
     st = env.stats()
