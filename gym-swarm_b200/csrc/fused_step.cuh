@@ -21,6 +21,9 @@
 #define FUSED_MINB 6     // minimum resident CTAs per SM the step kernel is compiled for (caps registers at 80:
                          // measured on cfg3: 8 warps x 2 CTAs 0.339 ms, 4 x 5 0.328 ms, 4 x 6 0.316 ms per step)
 #endif
+#ifndef FUSED_VF_MINB
+#define FUSED_VF_MINB 5  // the same for the sparse visual-field variant (hit bookkeeping needs a few more registers)
+#endif
 
 namespace swarm {
 
@@ -313,13 +316,20 @@ __device__ __noinline__ void reset_group(const StepParams& p, const Seg<LPE>& g,
 // ---- symmetric ring sweep (see the comment at its call site) ---------------------------------------------------
 // FAR = false: the two far thresholds were already counted by the border pass (far_border_counts), the sweep carries
 // only the {rep, att} counter pair.
-template <int LPE, int APL, bool FAR>
+//
+// VIS = true (visual-field steps, sparse mode): every round also records WHICH of its pairs are within the visual
+// field -- bit t = w * APL + k of the low / high half of one word per (round, lane) for the visiting agents 2w / 2w+1
+// against the owned agent k -- in shits[round * LPE + lane].  The (few) set bits are turned into the gated alignment
+// sums after the sweep (vf_sparse_accumulate); the dense alternative evaluates every ordered pair (kernel, VFM == 1).
+template <int LPE, int APL, bool FAR, bool VIS>
 __device__ __forceinline__ void ring_sweep(const Seg<LPE>& g, const uint4* __restrict__ spw, const unsigned (&XI)[APL],
                                            const unsigned (&YI)[APL], const unsigned (&NXI)[APL], const unsigned (&NYI)[APL],
                                            unsigned TR, unsigned TA, unsigned TRf, unsigned TAf, unsigned one, unsigned c256,
-                                           unsigned (&aR)[APL], unsigned (&aA)[APL], unsigned (&aRf)[APL], unsigned (&aAf)[APL]) {
+                                           unsigned (&aR)[APL], unsigned (&aA)[APL], unsigned (&aRf)[APL], unsigned (&aAf)[APL],
+                                           unsigned TV, unsigned* __restrict__ shits) {
   constexpr int W = APL / 2;
   constexpr int HALF = LPE / 2;
+  unsigned hits = 0u;
   // Counters are BYTE packed: a 16x2 indicator word holds 0/1 in bytes 0 and 2, so ind(t0) + 256 * ind(t1)
   // carries two thresholds for two agents in one register ({t0,t1} = {rep,att} and {rep_far,att_far}); it is
   // built once (IMAD) and added to the row and to the column counter.  No byte can overflow: a row byte
@@ -342,10 +352,18 @@ __device__ __forceinline__ void ring_sweep(const Seg<LPE>& g, const uint4* __res
           row[k][1] = lt2(TRf, m) * one + row[k][1];
           row[k][1] = lt2(TAf, m) * c256 + row[k][1];
         }
+        if constexpr (VIS) hits += lt2(TV, m) << (w * APL + k);
       }
     }
   };
   rows_only(g.li);                                       // round 0: own block
+  if constexpr (VIS) {
+    unsigned self = 0u;                                  // an agent is not its own neighbour
+#pragma unroll
+    for (int k = 0; k < APL; ++k) self |= 1u << ((k >> 1) * APL + k + 16 * (k & 1));
+    shits[g.li] = hits & ~self;
+    hits = 0u;
+  }
   const int nxt = (g.li + 1) & (LPE - 1);
 #pragma unroll 1
   for (int r = 1; r < HALF; ++r) {
@@ -371,8 +389,10 @@ __device__ __forceinline__ void ring_sweep(const Seg<LPE>& g, const uint4* __res
           row[k][1] = n1 * one + row[k][1];
           col[w][1] = n1 * one + col[w][1];
         }
+        if constexpr (VIS) hits += lt2(TV, m) << (w * APL + k);
       }
     }
+    if constexpr (VIS) { shits[r * LPE + g.li] = hits; hits = 0u; }
   }
   // send the column counters home: lane l holds those of block l + HALF - 1
   if constexpr (HALF > 1) {
@@ -384,6 +404,7 @@ __device__ __forceinline__ void ring_sweep(const Seg<LPE>& g, const uint4* __res
     }
   }
   rows_only((g.li + HALF) & (LPE - 1));                  // round LPE/2: met from both sides
+  if constexpr (VIS) shits[HALF * LPE + g.li] = hits;
   // fold: total = both agents' bytes of the row counter + this agent's bytes of the column counter
 #pragma unroll
   for (int k = 0; k < APL; ++k) {
@@ -393,6 +414,43 @@ __device__ __forceinline__ void ring_sweep(const Seg<LPE>& g, const uint4* __res
     if constexpr (FAR) {
       aRf[k] = __dp4a(row[k][1], 0x00010001u, 0u) + ((col[k >> 1][1] >> sh) & 0xFFu);
       aAf[k] = __dp4a(row[k][1], 0x01000100u, 0u) + ((col[k >> 1][1] >> (sh + 8)) & 0xFFu);
+    }
+  }
+}
+
+// ---- visual-field alignment from the recorded hits (sparse mode) ------------------------------------------------
+// Every lane walks the hit words IT wrote (one per round): bit -> (owned agent i, visiting agent j).  i receives j's
+// move vector and one visible neighbour; in the symmetric rounds 1 .. LPE/2 - 1 the pair was evaluated by this lane
+// only, so j receives i's as well.  sacc = {count[NMAX], axis sums[NMAX], diagonal sums[NMAX]} (shared-memory atomics:
+// a hit is rare -- (2 vf + 1)^2 / S^2 of the pairs).  svf[j] = j's move as two biased 16x2 words (axis, diagonal).
+template <int LPE, int APL>
+__device__ __forceinline__ void vf_sparse_accumulate(const Seg<LPE>& g, const unsigned* __restrict__ shits,
+                                                     const uint2* __restrict__ svf, unsigned* __restrict__ sacc, int N, int i0) {
+  constexpr int NMAX = LPE * APL;
+  constexpr int HALF = LPE / 2;
+#pragma unroll 1
+  for (int r = 0; r <= HALF; ++r) {
+    unsigned h = shits[r * LPE + g.li];
+    const int j0 = ((g.li + r) & (LPE - 1)) * APL;
+    const bool both = r > 0 && r < HALF;
+    while (h) {
+      const int b = __ffs(h) - 1;
+      h &= h - 1u;
+      const int t = b & 15;
+      const int i = i0 + (t & (APL - 1));
+      const int j = j0 + 2 * (t / APL) + (b >> 4);
+      if (i < N && j < N) {                                // (two padding agents share a cell)
+        const uint2 uj = svf[j];
+        atomicAdd(&sacc[i], 1u);
+        atomicAdd(&sacc[NMAX + i], uj.x);
+        atomicAdd(&sacc[2 * NMAX + i], uj.y);
+        if (both) {
+          const uint2 ui = svf[i];
+          atomicAdd(&sacc[j], 1u);
+          atomicAdd(&sacc[NMAX + j], ui.x);
+          atomicAdd(&sacc[2 * NMAX + j], ui.y);
+        }
+      }
     }
   }
 }
@@ -455,13 +513,25 @@ struct FusedCfg {
   static constexpr int WARPS = FUSED_WARPS;  // warps per CTA
   // bytes of smem per warp: pair words (aliased by the collision keys) + VF words + bitmap
   __host__ __device__ static constexpr int pair_bytes() { return EPW * PW * 16; }
-  __host__ __device__ static constexpr int vf_bytes() { return EPW * NMAX * 8; }
+  // visual-field steps: VFM = 1 dense (move words of every agent), VFM = 2 sparse (+ three accumulators per agent and
+  // one hit word per (round, lane) of the ring sweep)
+  __host__ __device__ static constexpr bool ring_ok() { return (APL == 2 || APL == 4) && LPE >= 4; }
+  __host__ __device__ static constexpr int hit_words() { return (LPE / 2 + 1) * LPE; }
+  __host__ __device__ static constexpr int vf_env_bytes(int vfm) {
+    return vfm == 0 ? 0 : vfm == 1 ? NMAX * 8 : NMAX * 20 + hit_words() * 4;
+  }
+  __host__ __device__ static constexpr int vf_bytes(int vfm) { return EPW * vf_env_bytes(vfm); }
 };
 
-template <int LPE, int APL, bool HAS_VF>
-__global__ void __launch_bounds__(FusedCfg<LPE, APL>::WARPS * 32, (APL == 8 || HAS_VF) ? 3 : FUSED_MINB)
+template <int LPE, int APL, int VFM>
+__global__ void __launch_bounds__(FusedCfg<LPE, APL>::WARPS * 32,
+                                  (APL == 8 || VFM == 1) ? 3 : (VFM == 2 ? FUSED_VF_MINB : FUSED_MINB))
 fused_step_kernel(const __grid_constant__ StepParams p) {
   using C = FusedCfg<LPE, APL>;
+  constexpr bool HAS_VF = VFM != 0;
+  constexpr bool VF_SPARSE = VFM == 2;
+  static_assert(!VF_SPARSE || C::ring_ok(), "sparse visual-field mode rides on the ring sweep");
+  constexpr bool RING = VFM != 1 && C::ring_ok();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const Seg<LPE> g;
@@ -470,12 +540,15 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
 
   // smem carve-up (per warp, then per env group)
   const int hist_words = (p.box.enabled && p.box.need_hist) ? 2 * S : 0;   // per-env column / row histograms
-  const int warp_bytes = C::pair_bytes() + (HAS_VF ? C::vf_bytes() : 0) + C::EPW * (p.bitmap_words + hist_words) * 4;
+  const int warp_bytes = C::pair_bytes() + C::vf_bytes(VFM) + C::EPW * (p.bitmap_words + hist_words) * 4;
   unsigned char* wbase = smem_raw + (size_t)warp * warp_bytes;
   uint4* spw = reinterpret_cast<uint4*>(wbase) + g.seg * C::PW;
   unsigned* skey = reinterpret_cast<unsigned*>(spw);   // aliases the pair words (NMAX words <= PW*4 words)
-  uint2* svf = reinterpret_cast<uint2*>(wbase + C::pair_bytes()) + g.seg * C::NMAX;
-  unsigned* sbit = reinterpret_cast<unsigned*>(wbase + C::pair_bytes() + (HAS_VF ? C::vf_bytes() : 0)) +
+  unsigned char* vbase = wbase + C::pair_bytes() + g.seg * C::vf_env_bytes(VFM);
+  uint2* svf = reinterpret_cast<uint2*>(vbase);
+  unsigned* sacc = reinterpret_cast<unsigned*>(vbase + C::NMAX * 8);   // sparse mode: count / axis / diagonal sums
+  unsigned* shits = sacc + 3 * C::NMAX;                                 // sparse mode: hit words of the sweep
+  unsigned* sbit = reinterpret_cast<unsigned*>(wbase + C::pair_bytes() + C::vf_bytes(VFM)) +
                    g.seg * (p.bitmap_words + hist_words);
   int* shist = reinterpret_cast<int*>(sbit + p.bitmap_words);
   if (p.bitmap_words) {
@@ -640,7 +713,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
       }
     } else {
       bool far_done = false;
-      if constexpr (!HAS_VF && (APL == 2 || APL == 4) && LPE >= 4) {
+      if constexpr (RING) {
         if (p.far_border) {                              // both far thresholds > S/2: only border agents can be far apart
           far_border_counts<LPE, APL>(p, g, skey, N, S, i0, nx, ny, aRf, aAf);
           far_done = true;
@@ -663,7 +736,6 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
         }
       } else {
         // ring sweep: word w of every lane contiguous ([w][lane]) so that the rotated LDS.128 is conflict free
-        constexpr bool RING = !HAS_VF && (APL == 2 || APL == 4) && LPE >= 4;
   #pragma unroll
         for (int k = 0; k < APL; k += 2)
           spw[RING ? (k >> 1) * LPE + g.li : (i0 + k) >> 1] =
@@ -679,6 +751,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
           const bool diag = (a & 1) != 0;
           svf[i0 + k] = make_uint2(pack2((diag ? 0 : mx) + 1, (diag ? 0 : my) + 1),
                                    pack2((diag ? mx : 0) + 1, (diag ? my : 0) + 1));
+          if constexpr (VF_SPARSE) sacc[i0 + k] = sacc[C::NMAX + i0 + k] = sacc[2 * C::NMAX + i0 + k] = 0u;
         }
       }
       g.sync();
@@ -690,7 +763,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
       }
       const unsigned TR = rep2(p.t_rep), TA = rep2(p.t_att), TRf = rep2(p.t_repf), TAf = rep2(p.t_attf);
       const unsigned TV = rep2(HAS_VF ? p.t_vf : 0);
-      if constexpr (!HAS_VF && (APL == 2 || APL == 4) && LPE >= 4) {
+      if constexpr (RING) {
         // ---- symmetric ring sweep: every unordered block pair is evaluated once --------------------
         // Lane l owns block B_l (APL agents = W pair words).  In round r it meets the block of lane l+r (pair words
         // read from smem), adds each indicator to its own ROW counters and to the visiting block's COLUMN counters;
@@ -699,15 +772,23 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
         // count rows.  The accumulations are IMADs by a runtime 1 so that they issue on the FMA pipe and leave the
         // ALU pipe to the DPX ops.
         const unsigned one = (unsigned)p.one, c256 = (unsigned)p.one << 8;
-        if (far_done) ring_sweep<LPE, APL, false>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf);
-        else ring_sweep<LPE, APL, true>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf);
+        if (far_done)
+          ring_sweep<LPE, APL, false, VF_SPARSE>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf, TV, shits);
+        else
+          ring_sweep<LPE, APL, true, VF_SPARSE>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf, TV, shits);
+        if constexpr (VF_SPARSE) {
+          vf_sparse_accumulate<LPE, APL>(g, shits, svf, sacc, N, i0);
+          g.sync();
+#pragma unroll
+          for (int k = 0; k < APL; ++k) { aV[k] = sacc[i0 + k]; accA[k] = sacc[C::NMAX + i0 + k]; accD[k] = sacc[2 * C::NMAX + i0 + k]; }
+        }
       } else {
         const int NW = (N + 1) >> 1;
   #pragma unroll 2
         for (int q = 0; q < NW; ++q) {
           const uint4 w = spw[q];
           uint4 u = make_uint4(0, 0, 0, 0);
-          if constexpr (HAS_VF) u = *reinterpret_cast<const uint4*>(&svf[2 * q]);
+          if constexpr (VFM == 1) u = *reinterpret_cast<const uint4*>(&svf[2 * q]);
   #pragma unroll
           for (int k = 0; k < APL; ++k) {
             const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], w);
@@ -715,7 +796,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
             aA[k] += lt2(TA, m);
             aRf[k] += lt2(TRf, m);
             aAf[k] += lt2(TAf, m);
-            if constexpr (HAS_VF) {
+            if constexpr (VFM == 1) {
               const unsigned gate = lt2(TV, m);
               const unsigned g0 = gate & 0xFFFFu, g1 = gate >> 16;
               aV[k] += gate;
@@ -748,7 +829,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
     }
 
     const int selfR = p.t_rep >= 1, selfA = p.t_att >= 1, selfRf = p.t_repf >= 1, selfAf = p.t_attf >= 1;
-    const int selfV = HAS_VF ? (p.t_vf >= 1) : 1;
+    const int selfV = VF_SPARSE ? 0 : HAS_VF ? (p.t_vf >= 1) : 1;   // (the sparse sums never include the agent itself)
     int s_rep = 0, s_att = 0, s_P = 0, s_Q = 0, s_vis = 0;
     int rep_i[APL], att_i[APL];
     double una_i[APL];
@@ -757,7 +838,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
       const bool v = i0 + k < N;
       int vis, P, Q;
       if constexpr (HAS_VF) {
-        const int vin = hsum2(aV[k]);                       // gated count incl. self
+        const int vin = VF_SPARSE ? (int)aV[k] : hsum2(aV[k]);   // gated count (dense: incl. self)
         const int gAx = (int)(accA[k] & 0xFFFFu) - vin, gAy = (int)(accA[k] >> 16) - vin;
         const int gDx = (int)(accD[k] & 0xFFFFu) - vin, gDy = (int)(accD[k] >> 16) - vin;
         vis = vin - selfV;

@@ -141,31 +141,50 @@ static StepParams base_params(const Ctx* c) {
 
 // ---- fused dispatch -------------------------------------------------------------------------------
 template <int LPE, int APL>
-static int fused_smem_bytes(const StepParams& p, bool vf) {
+static int fused_smem_bytes(const StepParams& p, int vfm) {
   using C = FusedCfg<LPE, APL>;
   const int hist_words = (p.box.enabled && p.box.need_hist) ? 2 * p.S : 0;
-  return C::WARPS * (C::pair_bytes() + (vf ? C::vf_bytes() : 0) + C::EPW * (p.bitmap_words + hist_words) * 4);
+  return C::WARPS * (C::pair_bytes() + C::vf_bytes(vfm) + C::EPW * (p.bitmap_words + hist_words) * 4);
 }
 
-// once per handle (swarm_create): opt in to the dynamic shared memory the two step kernels need.  Nothing but
+// Visual-field steps: 1 = dense (every ordered pair evaluated with the gate), 2 = sparse (symmetric ring sweep records
+// the visible pairs, alignment sums from those).  Sparse pays while few pairs are visible: expected fraction
+// ((2 vf + 1) / S)^2 <= 1/16; measured at 65,536 x 128 on 128^2, vf = 5: see DESIGN.md 5.2.
+template <int LPE, int APL>
+static int fused_vf_mode(const StepParams& p) {
+  if (p.t_vf < 0) return 0;
+  if (!FusedCfg<LPE, APL>::ring_ok()) return 1;
+  if (const char* ev = getenv("SWARM_VF_DENSE")) if (atoi(ev)) return 1;   // experiments / tests
+  const long long w = 2LL * (p.t_vf - 1) + 1;
+  return (w * w * 16 <= (long long)p.S * p.S) ? 2 : 1;
+}
+
+// once per handle (swarm_create): opt in to the dynamic shared memory the step kernels need.  Nothing but
 // kernel launches happens in swarm_step, so a step can be captured into a CUDA graph.
 template <int LPE, int APL>
 static cudaError_t prepare_fused_step(const StepParams& p) {
-  cudaError_t e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       fused_smem_bytes<LPE, APL>(p, true));
+  cudaError_t e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       fused_smem_bytes<LPE, APL>(p, 0));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(fused_step_kernel<LPE, APL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              fused_smem_bytes<LPE, APL>(p, false));
+  e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           fused_smem_bytes<LPE, APL>(p, 1));
+  if (e != cudaSuccess) return e;
+  if constexpr (FusedCfg<LPE, APL>::ring_ok())
+    e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             fused_smem_bytes<LPE, APL>(p, 2));
+  return e;
 }
 
 template <int LPE, int APL>
-static cudaError_t launch_fused_step(const StepParams& p, bool vf, cudaStream_t s) {
+static cudaError_t launch_fused_step(const StepParams& p, cudaStream_t s) {
   using C = FusedCfg<LPE, APL>;
   const int envs_per_cta = C::WARPS * C::EPW;
   const int grid = (p.E + envs_per_cta - 1) / envs_per_cta;
-  const int smem = fused_smem_bytes<LPE, APL>(p, vf);
-  if (vf) fused_step_kernel<LPE, APL, true><<<grid, C::WARPS * 32, smem, s>>>(p);
-  else fused_step_kernel<LPE, APL, false><<<grid, C::WARPS * 32, smem, s>>>(p);
+  const int vfm = fused_vf_mode<LPE, APL>(p);
+  const int smem = fused_smem_bytes<LPE, APL>(p, vfm);
+  if (vfm == 0) fused_step_kernel<LPE, APL, 0><<<grid, C::WARPS * 32, smem, s>>>(p);
+  else if (vfm == 1) fused_step_kernel<LPE, APL, 1><<<grid, C::WARPS * 32, smem, s>>>(p);
+  else if constexpr (C::ring_ok()) fused_step_kernel<LPE, APL, 2><<<grid, C::WARPS * 32, smem, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -611,7 +630,7 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     return SWARM_OK;
   }
   if (c->fused) {
-#define CALL(L, A) CUDA_TRY(c, (launch_fused_step<L, A>(p, vf, s)))
+#define CALL(L, A) CUDA_TRY(c, (launch_fused_step<L, A>(p, s)))
     FUSED_DISPATCH(c, CALL);
 #undef CALL
     c->launches = 1;

@@ -274,6 +274,20 @@ def test_oracle_lockstep_large_n16384():
     _oracle_lockstep(E=2, N=16384, S=1024, T=2, seed=4, check_agents=True)
 
 
+@pytest.mark.parametrize("N,S,vf", [(12, 24, 1), (16, 32, 2), (30, 40, 2), (60, 64, 5), (100, 128, 0), (128, 128, 5),
+                                    (128, 200, 12), (37, 50, 4), (128, 16384, 9)])
+@pytest.mark.parametrize("dense", [False, True])
+def test_vf_sparse_and_dense_modes(N, S, vf, dense, monkeypatch):
+    """vf_size steps on the ring-sweep shapes: the sparse mode (visible pairs recorded by the symmetric sweep, picked when
+    (2 vf + 1)^2 <= S^2 / 16) and the dense mode (every ordered pair gated; SWARM_VF_DENSE=1 forces it) both reproduce the
+    oracle; att / rep far thresholds, action 8 and auto-reset included."""
+    if dense:
+        monkeypatch.setenv("SWARM_VF_DENSE", "1")
+    for (att, rep) in ((5, 2), (2, 5)):
+        _oracle_lockstep(E=37, N=N, S=S, T=6, seed=N + S + vf, vf=vf, att=att, rep=rep, weights=(0.5, 1.0, 2.0),
+                         n_actions=9)
+
+
 @pytest.mark.parametrize("vf", [0, 3, 40])
 def test_vf_gate(vf):
     _oracle_lockstep(E=5, N=24, S=20, T=20, seed=vf, vf=vf, weights=(0.5, 1.0, 2.0), n_actions=9)
