@@ -318,18 +318,29 @@ __device__ __noinline__ void reset_group(const StepParams& p, const Seg<LPE>& g,
 // only the {rep, att} counter pair.
 //
 // VIS = true (visual-field steps, sparse mode): every round also records WHICH of its pairs are within the visual
-// field -- bit t = w * APL + k of the low / high half of one word per (round, lane) for the visiting agents 2w / 2w+1
-// against the owned agent k -- in shits[round * LPE + lane].  The (few) set bits are turned into the gated alignment
-// sums after the sweep (vf_sparse_accumulate); the dense alternative evaluates every ordered pair (kernel, VFM == 1).
+// field: bit W * APL - 1 - (w * APL + k) of the low / high half of a hit word stands for the visiting agents 2w / 2w+1
+// against the owned agent k.  Non-zero hit words (few) are appended, tagged with round and lane, to the env's list
+// shits[0, nhit) by a ballot compaction; the list is turned into the gated alignment sums after the sweep
+// (vf_sparse_accumulate).  The dense alternative evaluates every ordered pair (kernel, VFM == 1).
 template <int LPE, int APL, bool FAR, bool VIS>
 __device__ __forceinline__ void ring_sweep(const Seg<LPE>& g, const uint4* __restrict__ spw, const unsigned (&XI)[APL],
                                            const unsigned (&YI)[APL], const unsigned (&NXI)[APL], const unsigned (&NYI)[APL],
                                            unsigned TR, unsigned TA, unsigned TRf, unsigned TAf, unsigned one, unsigned c256,
                                            unsigned (&aR)[APL], unsigned (&aA)[APL], unsigned (&aRf)[APL], unsigned (&aAf)[APL],
-                                           unsigned TV, unsigned* __restrict__ shits) {
+                                           unsigned TV, unsigned* __restrict__ shits, int& nhit) {
   constexpr int W = APL / 2;
   constexpr int HALF = LPE / 2;
   unsigned hits = 0u;
+  const unsigned two = one + one;
+  const unsigned lt_mask = (1u << (threadIdx.x & 31)) - 1u;
+  nhit = 0;
+  auto push_hits = [&](int r) {                          // {hit bits | round << 8 | lane << 24}
+    const bool nz = hits != 0u;
+    const unsigned b = __ballot_sync(g.mask, nz) & g.mask;
+    if (nz) shits[nhit + __popc(b & lt_mask)] = hits | ((unsigned)r << 8) | ((unsigned)g.li << 24);
+    nhit += __popc(b);
+    hits = 0u;
+  };
   // Counters are BYTE packed: a 16x2 indicator word holds 0/1 in bytes 0 and 2, so ind(t0) + 256 * ind(t1)
   // carries two thresholds for two agents in one register ({t0,t1} = {rep,att} and {rep_far,att_far}); it is
   // built once (IMAD) and added to the row and to the column counter.  No byte can overflow: a row byte
@@ -352,7 +363,7 @@ __device__ __forceinline__ void ring_sweep(const Seg<LPE>& g, const uint4* __res
           row[k][1] = lt2(TRf, m) * one + row[k][1];
           row[k][1] = lt2(TAf, m) * c256 + row[k][1];
         }
-        if constexpr (VIS) hits += lt2(TV, m) << (w * APL + k);
+        if constexpr (VIS) hits = hits * two + lt2(TV, m);   // (FMA pipe) test n = w * APL + k ends up in bit W * APL - 1 - n
       }
     }
   };
@@ -360,9 +371,9 @@ __device__ __forceinline__ void ring_sweep(const Seg<LPE>& g, const uint4* __res
   if constexpr (VIS) {
     unsigned self = 0u;                                  // an agent is not its own neighbour
 #pragma unroll
-    for (int k = 0; k < APL; ++k) self |= 1u << ((k >> 1) * APL + k + 16 * (k & 1));
-    shits[g.li] = hits & ~self;
-    hits = 0u;
+    for (int k = 0; k < APL; ++k) self |= 1u << (W * APL - 1 - ((k >> 1) * APL + k) + 16 * (k & 1));
+    hits &= ~self;
+    push_hits(0);
   }
   const int nxt = (g.li + 1) & (LPE - 1);
 #pragma unroll 1
@@ -389,10 +400,10 @@ __device__ __forceinline__ void ring_sweep(const Seg<LPE>& g, const uint4* __res
           row[k][1] = n1 * one + row[k][1];
           col[w][1] = n1 * one + col[w][1];
         }
-        if constexpr (VIS) hits += lt2(TV, m) << (w * APL + k);
+        if constexpr (VIS) hits = hits * two + lt2(TV, m);   // (FMA pipe) test n = w * APL + k ends up in bit W * APL - 1 - n
       }
     }
-    if constexpr (VIS) { shits[r * LPE + g.li] = hits; hits = 0u; }
+    if constexpr (VIS) push_hits(r);
   }
   // send the column counters home: lane l holds those of block l + HALF - 1
   if constexpr (HALF > 1) {
@@ -404,7 +415,7 @@ __device__ __forceinline__ void ring_sweep(const Seg<LPE>& g, const uint4* __res
     }
   }
   rows_only((g.li + HALF) & (LPE - 1));                  // round LPE/2: met from both sides
-  if constexpr (VIS) shits[HALF * LPE + g.li] = hits;
+  if constexpr (VIS) push_hits(HALF);
   // fold: total = both agents' bytes of the row counter + this agent's bytes of the column counter
 #pragma unroll
   for (int k = 0; k < APL; ++k) {
@@ -419,25 +430,27 @@ __device__ __forceinline__ void ring_sweep(const Seg<LPE>& g, const uint4* __res
 }
 
 // ---- visual-field alignment from the recorded hits (sparse mode) ------------------------------------------------
-// Every lane walks the hit words IT wrote (one per round): bit -> (owned agent i, visiting agent j).  i receives j's
-// move vector and one visible neighbour; in the symmetric rounds 1 .. LPE/2 - 1 the pair was evaluated by this lane
-// only, so j receives i's as well.  sacc = {count[NMAX], axis sums[NMAX], diagonal sums[NMAX]} (shared-memory atomics:
-// a hit is rare -- (2 vf + 1)^2 / S^2 of the pairs).  svf[j] = j's move as two biased 16x2 words (axis, diagonal).
+// The env's lanes share the hit list: entry -> (lane and round that saw it) -> owned agent i, visiting agent j per set
+// bit.  i receives j's move vector and one visible neighbour; in the symmetric rounds 1 .. LPE/2 - 1 the pair was
+// evaluated once only, so j receives i's as well.  sacc = {count[NMAX], axis sums[NMAX], diagonal sums[NMAX]}
+// (shared-memory atomics: a hit is rare -- (2 vf + 1)^2 / S^2 of the pairs).  svf[j] = j's move as two biased 16x2
+// words (axis, diagonal).
 template <int LPE, int APL>
-__device__ __forceinline__ void vf_sparse_accumulate(const Seg<LPE>& g, const unsigned* __restrict__ shits,
-                                                     const uint2* __restrict__ svf, unsigned* __restrict__ sacc, int N, int i0) {
+__device__ __forceinline__ void vf_sparse_accumulate(const Seg<LPE>& g, const unsigned* __restrict__ shits, int nhit,
+                                                     const uint2* __restrict__ svf, unsigned* __restrict__ sacc, int N) {
   constexpr int NMAX = LPE * APL;
   constexpr int HALF = LPE / 2;
-#pragma unroll 1
-  for (int r = 0; r <= HALF; ++r) {
-    unsigned h = shits[r * LPE + g.li];
-    const int j0 = ((g.li + r) & (LPE - 1)) * APL;
+  for (int e = g.li; e < nhit; e += LPE) {
+    const unsigned ent = shits[e];
+    const int r = (int)((ent >> 8) & 31u), ln = (int)(ent >> 24);
+    unsigned h = ent & 0x00FF00FFu;
+    const int ib = ln * APL, j0 = ((ln + r) & (LPE - 1)) * APL;
     const bool both = r > 0 && r < HALF;
     while (h) {
       const int b = __ffs(h) - 1;
       h &= h - 1u;
-      const int t = b & 15;
-      const int i = i0 + (t & (APL - 1));
+      const int t = (APL / 2) * APL - 1 - (b & 15);
+      const int i = ib + (t & (APL - 1));
       const int j = j0 + 2 * (t / APL) + (b >> 4);
       if (i < N && j < N) {                                // (two padding agents share a cell)
         const uint2 uj = svf[j];
@@ -772,12 +785,14 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
         // count rows.  The accumulations are IMADs by a runtime 1 so that they issue on the FMA pipe and leave the
         // ALU pipe to the DPX ops.
         const unsigned one = (unsigned)p.one, c256 = (unsigned)p.one << 8;
+        int nhit = 0;
         if (far_done)
-          ring_sweep<LPE, APL, false, VF_SPARSE>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf, TV, shits);
+          ring_sweep<LPE, APL, false, VF_SPARSE>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf, TV, shits, nhit);
         else
-          ring_sweep<LPE, APL, true, VF_SPARSE>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf, TV, shits);
+          ring_sweep<LPE, APL, true, VF_SPARSE>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf, TV, shits, nhit);
         if constexpr (VF_SPARSE) {
-          vf_sparse_accumulate<LPE, APL>(g, shits, svf, sacc, N, i0);
+          g.sync();
+          vf_sparse_accumulate<LPE, APL>(g, shits, nhit, svf, sacc, N);
           g.sync();
 #pragma unroll
           for (int k = 0; k < APL; ++k) { aV[k] = sacc[i0 + k]; accA[k] = sacc[C::NMAX + i0 + k]; accD[k] = sacc[2 * C::NMAX + i0 + k]; }

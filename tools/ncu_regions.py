@@ -3,7 +3,7 @@
 captured with --import-source on (regions are delimited by marker comments in the embedded source)."""
 import csv, io, subprocess, sys
 MARKERS = [("helpers (Seg, ld/st)", "struct Seg {"), ("occupancy_counts", "void occupancy_counts("), ("bitmap_counts", "bool bitmap_counts("),
-           ("closest_target", "int closest_target("), ("reset_group", "void reset_group("), ("ring sweep", "void ring_sweep("), ("far-threshold border pass", "void far_border_counts("), ("kernel prologue + loads", "fused_step_kernel(const __grid_constant__"),
+           ("closest_target", "int closest_target("), ("reset_group", "void reset_group("), ("ring sweep", "void ring_sweep("), ("visual-field hits -> sums", "void vf_sparse_accumulate("), ("far-threshold border pass", "void far_border_counts("), ("kernel prologue + loads", "fused_step_kernel(const __grid_constant__"),
            ("move + collision rounds", "// ---- move + collision"), ("predator", "// ---- predator (SDE"), ("termination", "// ---- termination"),
            ("stage pair words", "// ---- reward (SDE"), ("pair sweep", "const unsigned TR = rep2"), ("alignment + epilogue", "// alignment sums"),
            ("per-env outputs + stats", "// ---- per-env outputs"), ("commit / auto-reset", "// ---- commit / auto-reset"), ("reset kernel", "fused_reset_kernel(")]
