@@ -334,11 +334,13 @@ __device__ __forceinline__ void ring_sweep(const Seg<LPE>& g, const uint4* __res
   const unsigned two = one + one;
   const unsigned lt_mask = (1u << (threadIdx.x & 31)) - 1u;
   nhit = 0;
-  auto push_hits = [&](int r) {                          // {hit bits | round << 8 | lane << 24}
+  unsigned tag = (unsigned)g.li << 24;                   // {hit bits | round << 8 | lane << 24}
+  auto push_hits = [&](int) {                            // (called once per round, in round order)
     const bool nz = hits != 0u;
     const unsigned b = __ballot_sync(g.mask, nz) & g.mask;
-    if (nz) shits[nhit + __popc(b & lt_mask)] = hits | ((unsigned)r << 8) | ((unsigned)g.li << 24);
+    if (nz) shits[nhit + __popc(b & lt_mask)] = hits | tag;
     nhit += __popc(b);
+    tag += 256u;
     hits = 0u;
   };
   // Counters are BYTE packed: a 16x2 indicator word holds 0/1 in bytes 0 and 2, so ind(t0) + 256 * ind(t1)
