@@ -1,0 +1,28 @@
+// launchers.h -- host entry points of the kernel translation units.  Every kernel family lives in its own .cu file
+// (fused_launch.cu, fused_vf_launch.cu, tiny_launch.cu; the staged kernels stay with the ABI in swarm_abi.cu) so that
+// the library builds in parallel; no device code is shared across translation units except through headers.
+#pragma once
+#include "swarm_common.cuh"
+
+namespace swarm {
+
+constexpr int TINY_N = 8;        // largest N of the default thread-per-env kernel
+constexpr int TINY_N_BIG = 16;   // second instantiation (9..16 agents), used for large batches only
+
+// lane-group shape <LPE, APL> for N agents (N <= SWARM_FUSED_MAX_AGENTS)
+void choose_fused_shape(int N, int& lpe, int& apl);
+
+// fused_launch.cu: steps without vf_size and the (masked) reset.  fused_prepare opts in to the dynamic shared memory
+// of every step kernel of the shape (both files) once per handle, so that swarm_step itself only launches.
+cudaError_t fused_prepare(int lpe, int apl, const StepParams& p);
+cudaError_t fused_step_launch(int lpe, int apl, const StepParams& p, cudaStream_t s);   // forwards vf_size steps
+cudaError_t fused_reset_launch(int lpe, int apl, const StepParams& p, const uint8_t* mask, int zero_counts, cudaStream_t s);
+
+// fused_vf_launch.cu: vf_size steps (dense and sparse visual-field modes)
+cudaError_t fused_vf_prepare(int lpe, int apl, const StepParams& p);
+cudaError_t fused_vf_step_launch(int lpe, int apl, const StepParams& p, cudaStream_t s);
+
+// tiny_launch.cu: thread-per-env step (+ masked auto-reset launch); returns the number of launches in *launches
+cudaError_t tiny_step_launch(int tiny_n, const StepParams& p, cudaStream_t s, int* launches);
+
+}  // namespace swarm

@@ -8,8 +8,7 @@
 #include <algorithm>
 #include <string>
 
-#include "fused_step.cuh"
-#include "tiny_step.cuh"
+#include "launchers.h"
 #include "staged.cuh"
 
 namespace swarm {
@@ -137,87 +136,6 @@ static StepParams base_params(const Ctx* c) {
   p.place = c->place; p.ptape = c->ptape;
   p.rst_seed_lo = (unsigned)(c->rst_seed & 0xFFFFFFFFull); p.rst_seed_hi = (unsigned)(c->rst_seed >> 32);
   return p;
-}
-
-// ---- fused dispatch -------------------------------------------------------------------------------
-template <int LPE, int APL>
-static int fused_smem_bytes(const StepParams& p, int vfm) {
-  using C = FusedCfg<LPE, APL>;
-  const int hist_words = (p.box.enabled && p.box.need_hist) ? 2 * p.S : 0;
-  return C::WARPS * (C::pair_bytes() + C::vf_bytes(vfm) + C::EPW * (p.bitmap_words + hist_words) * 4);
-}
-
-// Visual-field steps: 1 = dense (every ordered pair evaluated with the gate), 2 = sparse (symmetric ring sweep records
-// the visible pairs, alignment sums from those).  Sparse pays while few pairs are visible: expected fraction
-// ((2 vf + 1) / S)^2 <= 1/16; measured at 65,536 x 128 on 128^2, vf = 5: see DESIGN.md 5.2.
-template <int LPE, int APL>
-static int fused_vf_mode(const StepParams& p) {
-  if (p.t_vf < 0) return 0;
-  if (!FusedCfg<LPE, APL>::ring_ok()) return 1;
-  if (const char* ev = getenv("SWARM_VF_DENSE")) if (atoi(ev)) return 1;   // experiments / tests
-  const long long w = 2LL * (p.t_vf - 1) + 1;
-  return (w * w * 16 <= (long long)p.S * p.S) ? 2 : 1;
-}
-
-// once per handle (swarm_create): opt in to the dynamic shared memory the step kernels need.  Nothing but
-// kernel launches happens in swarm_step, so a step can be captured into a CUDA graph.
-template <int LPE, int APL>
-static cudaError_t prepare_fused_step(const StepParams& p) {
-  cudaError_t e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       fused_smem_bytes<LPE, APL>(p, 0));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           fused_smem_bytes<LPE, APL>(p, 1));
-  if (e != cudaSuccess) return e;
-  if constexpr (FusedCfg<LPE, APL>::ring_ok())
-    e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             fused_smem_bytes<LPE, APL>(p, 2));
-  return e;
-}
-
-template <int LPE, int APL>
-static cudaError_t launch_fused_step(const StepParams& p, cudaStream_t s) {
-  using C = FusedCfg<LPE, APL>;
-  const int envs_per_cta = C::WARPS * C::EPW;
-  const int grid = (p.E + envs_per_cta - 1) / envs_per_cta;
-  const int vfm = fused_vf_mode<LPE, APL>(p);
-  const int smem = fused_smem_bytes<LPE, APL>(p, vfm);
-  if (vfm == 0) fused_step_kernel<LPE, APL, 0><<<grid, C::WARPS * 32, smem, s>>>(p);
-  else if (vfm == 1) fused_step_kernel<LPE, APL, 1><<<grid, C::WARPS * 32, smem, s>>>(p);
-  else if constexpr (C::ring_ok()) fused_step_kernel<LPE, APL, 2><<<grid, C::WARPS * 32, smem, s>>>(p);
-  return cudaGetLastError();
-}
-
-template <int LPE, int APL>
-static cudaError_t launch_fused_reset(const StepParams& p, const uint8_t* mask, int zero_counts, cudaStream_t s) {
-  using C = FusedCfg<LPE, APL>;
-  const int envs_per_cta = C::WARPS * C::EPW;
-  const int grid = (p.E + envs_per_cta - 1) / envs_per_cta;
-  const int smem = C::WARPS * C::EPW * C::NMAX * 4;
-  fused_reset_kernel<LPE, APL><<<grid, C::WARPS * 32, smem, s>>>(p, mask, zero_counts);
-  return cudaGetLastError();
-}
-
-#define FUSED_DISPATCH(c, CALL)                                  \
-  do {                                                           \
-    const int _l = (c)->lpe, _a = (c)->apl;                      \
-    if (_l == 4 && _a == 1) { CALL(4, 1); }                      \
-    else if (_l == 8 && _a == 1) { CALL(8, 1); }                 \
-    else if (_l == 8 && _a == 2) { CALL(8, 2); }                 \
-    else if (_l == 8 && _a == 4) { CALL(8, 4); }                 \
-    else if (_l == 16 && _a == 4) { CALL(16, 4); }               \
-    else if (_l == 32 && _a == 4) { CALL(32, 4); }               \
-    else { CALL(32, 8); }                                        \
-  } while (0)
-
-static void choose_fused_shape(int N, int& lpe, int& apl) {
-  if (N <= 4) { lpe = 4; apl = 1; }
-  else if (N <= 8) { lpe = 8; apl = 1; }
-  else if (N <= 16) { lpe = 8; apl = 2; }
-  else if (N <= 32) { lpe = 8; apl = 4; }
-  else if (N <= 64) { lpe = 16; apl = 4; }
-  else if (N <= 128) { lpe = 32; apl = 4; }
-  else { lpe = 32; apl = 8; }
 }
 
 // ---- staged scratch ---------------------------------------------------------------------------------
@@ -472,10 +390,7 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
   }
   if (c->fused) {
     const StepParams p0 = base_params(c);
-    cudaError_t pe = cudaSuccess;
-#define CALL(L, A) pe = prepare_fused_step<L, A>(p0)
-    FUSED_DISPATCH(c, CALL);
-#undef CALL
+    const cudaError_t pe = fused_prepare(c->lpe, c->apl, p0);
     if (pe != cudaSuccess) {
       const std::string m = std::string("swarm_create: shared memory opt-in failed: ") + cudaGetErrorString(pe);
       delete c;
@@ -552,9 +467,7 @@ static int do_reset(Ctx* c, const uint8_t* mask, int mode, cudaStream_t s) {
   StepParams p = base_params(c);
   c->launches = 0;
   if (c->fused) {
-#define CALL(L, A) CUDA_TRY(c, (launch_fused_reset<L, A>(p, mask, mode == 0 ? 1 : 0, s)))
-    FUSED_DISPATCH(c, CALL);
-#undef CALL
+    CUDA_TRY(c, fused_reset_launch(c->lpe, c->apl, p, mask, mode == 0 ? 1 : 0, s));
   } else {
     if (c->coll_bm_words > 0)
       reset_bitmap_kernel<<<c->sc.env_grid, c->per_env_threads, c->coll_bm_words * 4 + COLL_HC * 8, s>>>(
@@ -610,29 +523,11 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
   if (c->tiny && !vf) {
     if (p.N == c->tiny_n && ((uintptr_t)in->actions & 7))
       return fail(c, SWARM_E_INVALID, "swarm_step: actions must be 8-byte aligned");
-    const int grid = (p.E + TINY_THREADS - 1) / TINY_THREADS;
-    const bool agent_out = p.agent_reward || p.agent_counts;
-    if (c->tiny_n == TINY_N) {
-      if (agent_out) tiny_step_kernel<TINY_N, true><<<grid, TINY_THREADS, 0, s>>>(p);
-      else tiny_step_kernel<TINY_N, false><<<grid, TINY_THREADS, 0, s>>>(p);
-    } else {
-      if (agent_out) tiny_step_kernel<TINY_N_BIG, true><<<grid, TINY_THREADS, 0, s>>>(p);
-      else tiny_step_kernel<TINY_N_BIG, false><<<grid, TINY_THREADS, 0, s>>>(p);
-    }
-    c->launches = 1;
-    if (p.auto_reset) {
-      const int rgrid = (p.E + TINY_RESET_SPAN - 1) / TINY_RESET_SPAN;
-      if (c->tiny_n == TINY_N) tiny_reset_kernel<TINY_N><<<rgrid, TINY_THREADS, 0, s>>>(p, p.done);
-      else tiny_reset_kernel<TINY_N_BIG><<<rgrid, TINY_THREADS, 0, s>>>(p, p.done);
-      c->launches = 2;
-    }
-    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, tiny_step_launch(c->tiny_n, p, s, &c->launches));
     return SWARM_OK;
   }
   if (c->fused) {
-#define CALL(L, A) CUDA_TRY(c, (launch_fused_step<L, A>(p, s)))
-    FUSED_DISPATCH(c, CALL);
-#undef CALL
+    CUDA_TRY(c, fused_step_launch(c->lpe, c->apl, p, s));
     c->launches = 1;
     return SWARM_OK;
   }

@@ -281,18 +281,18 @@ __device__ __forceinline__ void box_direct_sweep(const BoxPlan& bp, const unsign
 // ---- tape accessors: a bound tape (row pointer) or the in-kernel Philox stream -----------------------------------
 // The Philox paths are separate NON-INLINED functions: inlined, their ~60 instructions and live registers were paid by
 // every kernel even with bound tapes (tiny_step_kernel 96 -> 112 registers, 87 -> 99 us at cfg5).
-__device__ __noinline__ int philox_retarget(unsigned k0, unsigned k1, unsigned step, int env) {
+static __device__ __noinline__ int philox_retarget(unsigned k0, unsigned k1, unsigned step, int env) {
   return philox4x32_10(make_uint4((unsigned)env, step, 0u, 1u), k0, k1).x < 429496730u;
 }
-__device__ __noinline__ int philox_slab(unsigned k0, unsigned k1, unsigned step, int env, int d) {
+static __device__ __noinline__ int philox_slab(unsigned k0, unsigned k1, unsigned step, int env, int d) {
   const uint4 v = philox4x32_10(make_uint4((unsigned)env, step, 1u + (unsigned)(d >> 4), 1u), k0, k1);
   return (int)((word_of(v, (d >> 2) & 3) >> (8 * (d & 3))) & 7u);
 }
-__device__ __noinline__ int philox_place(unsigned k0, unsigned k1, int S, int env, unsigned rc, int i) {
+static __device__ __noinline__ int philox_place(unsigned k0, unsigned k1, int S, int env, unsigned rc, int i) {
   const uint4 v = philox4x32_10(make_uint4((unsigned)env, rc, (unsigned)(i >> 2), 2u), k0, k1);
   return (int)__umulhi(word_of(v, i & 3), (unsigned)S);
 }
-__device__ __noinline__ unsigned philox_pred(unsigned k0, unsigned k1, int S, int env, unsigned rc, int a) {
+static __device__ __noinline__ unsigned philox_pred(unsigned k0, unsigned k1, int S, int env, unsigned rc, int a) {
   const uint4 v = philox4x32_10(make_uint4((unsigned)env, rc, (unsigned)(a >> 1), 3u), k0, k1);
   return pack2((int)__umulhi((a & 1) ? v.z : v.x, (unsigned)S), (int)__umulhi((a & 1) ? v.w : v.y, (unsigned)S));
 }

@@ -17,12 +17,11 @@
 // it is what keeps it inside the instruction cache (measured: 30 % of the stall samples were instruction
 // fetches with the reset inlined).
 #pragma once
+#include "launchers.h"   // TINY_N, TINY_N_BIG
 #include "swarm_common.cuh"
 
 namespace swarm {
 
-constexpr int TINY_N = 8;        // largest N of the default thread-per-env kernel
-constexpr int TINY_N_BIG = 16;   // second instantiation (9..16 agents), used for large batches only
 constexpr int TINY_THREADS = 128;
 
 // c[k] = number of agents on agent k's cell (SDE:269-292); keys of padding agents are unique. Returns sum(c-1).
