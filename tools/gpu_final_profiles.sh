@@ -3,6 +3,7 @@
 mkdir -p gpurun_out
 R=${1:-r01}
 python bench.py --steps 200 --warmup 10 > gpurun_out/${R}_bench_cfg3.json 2> gpurun_out/${R}_bench_cfg3.err; echo cfg3 rc=$?
+python bench.py --steps 100 --warmup 10 --vf 5 > gpurun_out/${R}_bench_cfg3_vf5.json 2> gpurun_out/${R}_bench_cfg3_vf5.err; echo cfg3 vf5 rc=$?
 for c in cfg2 cfg4 cfg5 stream; do python bench.py --config $c --steps 100 --warmup 10 > gpurun_out/${R}_bench_$c.json 2> gpurun_out/${R}_bench_$c.err; echo $c rc=$?; done
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${R}_bench_reference_cfg3.json 2>/dev/null; echo ref rc=$?
 python tools/kernel_roofline.py > gpurun_out/${R}_kernel_roofline.jsonl 2> gpurun_out/kernel_roofline.err; echo kr rc=$?
