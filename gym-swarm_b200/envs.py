@@ -220,6 +220,9 @@ class BatchedSwarmEnv:
         """
         rt = DEFAULT_REWARD_TYPE if reward_type is None else reward_type
         vf = rt.get("vf_size", None)
+        w_alignment = float(rt["alignment"])
+        if vf is not None and vf < 0:                   # SDE:355 `unalign[dist_1 > vf_size] = 0` then clears every
+            vf, w_alignment = None, 0.0                 # pair (D >= 0 > vf): the alignment term is identically zero
         actions = _as_dev(actions, torch.uint8, self.device)
         assert tuple(actions.shape) == (self.E, self.N), tuple(actions.shape)
         if self.device_tapes and retarget is None and slab is None:
@@ -234,7 +237,7 @@ class BatchedSwarmEnv:
             assert tuple(retarget.shape) == (self.E,) and tuple(slab.shape) == (self.E, self.K), (retarget.shape, slab.shape)
         sin = _lib.StepIn(actions=_ptr(actions), retarget=_ptr(retarget), slab=_ptr(slab),
                           w_attraction=float(rt["attraction"]), w_repulsion=float(rt["repulsion"]),
-                          w_alignment=float(rt["alignment"]), vf_size=-1 if vf is None else int(math.floor(vf)),
+                          w_alignment=w_alignment, vf_size=-1 if vf is None else int(math.floor(vf)),
                           rng_step=self.step_index & 0xFFFFFFFF, rng_seed=self.seed & 0xFFFFFFFFFFFFFFFF)
         self.step_index += 1
         self._keep = (actions, retarget, slab)      # keep inputs alive until the kernels ran

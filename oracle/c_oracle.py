@@ -92,6 +92,8 @@ class COracleBatch:
 
     def step(self, actions, slab, retarget, weights=(1.0, 1.0, 1.0), vf=None, want_agents=True, want_state=True):
         E, N = self.E, self.N
+        if vf is not None and vf < 0:          # SDE:355 clears every pair (D >= 0 > vf): alignment is identically 0
+            vf, weights = None, (weights[0], weights[1], 0.0)
         actions = np.ascontiguousarray(actions, dtype=np.uint8)
         slab = np.ascontiguousarray(slab, dtype=np.uint8)
         retarget = np.ascontiguousarray(retarget, dtype=np.uint8)

@@ -288,6 +288,14 @@ def test_vf_sparse_and_dense_modes(N, S, vf, dense, monkeypatch):
                          n_actions=9)
 
 
+@pytest.mark.parametrize("vf", [-1, 2.5])
+def test_vf_negative_and_fractional(vf):
+    """SDE:355 `unalign[dist_1 > vf_size] = 0` literally: a negative vf_size clears every pair, a fractional one acts
+    like its floor (distances are integers)."""
+    _oracle_lockstep(E=5, N=24, S=20, T=8, seed=3, vf=vf, weights=(0.5, 1.0, 2.0), n_actions=9)
+    _oracle_lockstep(E=5, N=8, S=12, T=8, seed=4, vf=vf, weights=(0.5, 1.0, 2.0), n_actions=9)
+
+
 @pytest.mark.parametrize("vf", [0, 3, 40])
 def test_vf_gate(vf):
     _oracle_lockstep(E=5, N=24, S=20, T=20, seed=vf, vf=vf, weights=(0.5, 1.0, 2.0), n_actions=9)

@@ -86,6 +86,9 @@ def _lockstep(N, S, att, rep, eat, T, seed, stable, vf=None, n_actions=9):
     (16, 32, 5, 2, -10, 200, None),
     (10, 20, 10, 200, -50, 120, None),    # the reference test-suite's thresholds
     (33, 40, 2, 5, -1, 60, 7),            # rep > att
+    (9, 12, 5, 2, -10, 60, -1),           # negative vf_size: every pair is gated out (SDE:355)
+    (9, 12, 5, 2, -10, 60, 2.5),          # fractional vf_size
+    (9, 12, 5, 2, -10, 60, 0),
 ])
 def test_oracle_lockstep_with_stable_reference_on_fresh_seeds(N, S, att, rep, eat, T, vf):
     for seed in (101, 202):
