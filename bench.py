@@ -348,7 +348,8 @@ def main():
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(tpath) and args.envs is None and args.scaling == "weak":
-        ent = json.load(open(tpath)).get(f"{args.config}:{env.path_name}")
+        key = f"{args.config}:{env.path_name}" if args.vf is None else f"{args.config}:vf{args.vf}:{env.path_name}"
+        ent = json.load(open(tpath)).get(key)
         if ent:
             traffic, traffic_src = ent["traffic_bytes"], ent["source"]
     roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
