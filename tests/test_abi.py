@@ -60,3 +60,54 @@ def test_product_path_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def _cfg(**kw):
+    base = dict(abi_version=_lib.ABI_VERSION, device=0, num_envs=4, num_agents=4, grid_size=20, attraction_thresh=5,
+                repulsion_thresh=2, predator_eat_rew=-10.0, slab_len=32, place_len=2 * 4 + 64, pred_attempts=8,
+                reset_slots=1, auto_reset=0, track_stats=0, path=_lib.PATH_AUTO)
+    base.update(kw)
+    return _lib.Config(**base)
+
+
+@pytest.mark.parametrize("kw,needle", [
+    (dict(abi_version=_lib.ABI_VERSION + 1), "ABI version"),
+    (dict(num_envs=0), "num_envs"),
+    (dict(num_agents=1), "num_agents"),
+    (dict(num_agents=16385), "num_agents"),
+    (dict(grid_size=1), "grid_size"),
+    (dict(num_agents=25, grid_size=5, place_len=200), "more cells"),
+    (dict(place_len=7), "tape geometry"),
+    (dict(reset_slots=0), "tape geometry"),
+    (dict(num_agents=300, place_len=2 * 300 + 64, path=_lib.PATH_FUSED), "fused path"),
+])
+def test_create_rejects_bad_configs_before_touching_cuda(built, kw, needle):
+    """Argument validation (include/swarm_abi.h conventions: negative code + swarm_last_error text) runs before the
+    first CUDA call, so it is checkable on a box without a GPU."""
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    cfg = _cfg(**kw)
+    rc = lib.swarm_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc < 0 and not h.value
+    assert needle in lib.swarm_last_error(None).decode()
+
+
+def test_create_without_gpu_reports_no_cpu_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    cfg = _cfg()
+    rc = lib.swarm_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc < 0 and not h.value
+    assert "no CPU fallback" in lib.swarm_last_error(None).decode()
+
+
+def test_null_arguments(built):
+    lib = _lib.load()
+    assert lib.swarm_create(None, None) < 0
+    assert lib.swarm_reset(None, None) < 0
+    lib.swarm_destroy(None)                                   # destroying a null handle is a no-op
+    assert lib.swarm_path_name(None) == b""
+    assert lib.swarm_last_launch_count(None) == 0
