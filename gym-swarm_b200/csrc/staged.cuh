@@ -622,13 +622,14 @@ __device__ __forceinline__ void predator_write(const PredIO& io, int env, int pp
   if (io.step_target) io.step_target[env] = target;
 }
 
-// Lane-group variant: LPE lanes per env (32/LPE envs per warp), 8 agents per vector, up to PRED_VPL vectors per
-// lane prefetched into registers.  N % 8 == 0.  Round trip 1 is the predator's state (tiny, coalesced over envs);
+// Lane-group variant: LPE lanes per env (32/LPE envs per warp), 8 agents per vector, up to VPL vectors per
+// lane prefetched into registers (VPL = 1 / 2 for envs of 8 / 16 agents: a thread per env with no padding vectors in
+// registers, so that more envs are in flight per SM).  N % 8 == 0.  Round trip 1 is the predator's state (tiny, coalesced over envs);
 // round trip 2 issues the bulk together: NEW positions, the stored target's OLD cell, and -- for the envs that
 // retarget -- the OLD positions.
 constexpr int PRED_VPL = 4;
 
-template <int LPE>
+template <int LPE, int VPL = PRED_VPL>
 __global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int env = gtid / LPE;
@@ -655,9 +656,9 @@ __global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
   int target = io.target[env];
   const int retarget = pred_retarget(io, env);
   target = min(max(target, 0), N - 1);
-  uint4 xn[PRED_VPL], yn[PRED_VPL];
+  uint4 xn[VPL], yn[VPL];
 #pragma unroll
-  for (int q = 0; q < PRED_VPL; ++q) {
+  for (int q = 0; q < VPL; ++q) {
     const int v = li + q * LPE;
     if (v < NV) { xn[q] = __ldg(xn4 + v); yn[q] = __ldg(yn4 + v); }
     else { xn[q] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu); yn[q] = xn[q]; }
@@ -686,9 +687,9 @@ __global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
   unsigned hit = 0xFFFFFFFFu;                                  // SDE:307-309 on the NEW positions
   const unsigned kx = rep2(px), ky = rep2(py);
 #pragma unroll
-  for (int q = 0; q < PRED_VPL; ++q) hit8(xn[q], yn[q], kx, ky, (li + q * LPE) * 8, hit);   // padding = 0xFFFF: never a cell
+  for (int q = 0; q < VPL; ++q) hit8(xn[q], yn[q], kx, ky, (li + q * LPE) * 8, hit);   // padding = 0xFFFF: never a cell
 #pragma unroll 4
-  for (int v = li + PRED_VPL * LPE; v < NV; v += LPE) hit8(__ldg(xn4 + v), __ldg(yn4 + v), kx, ky, v * 8, hit);
+  for (int v = li + VPL * LPE; v < NV; v += LPE) hit8(__ldg(xn4 + v), __ldg(yn4 + v), kx, ky, v * 8, hit);
 #pragma unroll
   for (int d = LPE / 2; d > 0; d >>= 1) hit = min(hit, __shfl_xor_sync(gmask, hit, d));
   if (li == 0) predator_write(io, env, ppx, ppy, px, py, target, orient, hit);
@@ -790,6 +791,8 @@ static inline void launch_predator(const PredIO& io, int num_sms, cudaStream_t s
   int lpe = 1;
   while (lpe < 32 && lpe * PRED_VPL < nv) lpe <<= 1;
   const int grid = (int)((E * lpe + 255) / 256);
+  if (nv == 1) { predator_group_kernel<1, 1><<<grid, 256, 0, s>>>(io); return; }
+  if (nv == 2) { predator_group_kernel<1, 2><<<grid, 256, 0, s>>>(io); return; }
   switch (lpe) {
     case 1: predator_group_kernel<1><<<grid, 256, 0, s>>>(io); break;
     case 2: predator_group_kernel<2><<<grid, 256, 0, s>>>(io); break;
