@@ -288,6 +288,14 @@ def test_vf_sparse_and_dense_modes(N, S, vf, dense, monkeypatch):
                          n_actions=9)
 
 
+@pytest.mark.parametrize("N,S", [(16, 32), (64, 64), (128, 128)])
+def test_vf_sparse_with_four_threshold_sweep(N, S, monkeypatch):
+    """Sparse visual-field mode on the ring sweep that carries all four thresholds (no border pass), the variant taken
+    when a far threshold is at or below S/2."""
+    monkeypatch.setenv("SWARM_NO_FAR_BORDER", "1")
+    _oracle_lockstep(E=9, N=N, S=S, T=6, seed=N + S, vf=2, n_actions=9, weights=(0.5, 1.0, 2.0))
+
+
 @pytest.mark.parametrize("vf", [-1, 2.5])
 def test_vf_negative_and_fractional(vf):
     """SDE:355 `unalign[dist_1 > vf_size] = 0` literally: a negative vf_size clears every pair, a fractional one acts
