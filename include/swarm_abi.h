@@ -109,7 +109,8 @@ typedef struct swarm_step_in {
   double w_attraction;     /* reward_type["attraction"] (bool or float: the reward curriculum) */
   double w_repulsion;      /* reward_type["repulsion"] */
   double w_alignment;      /* reward_type["alignment"] */
-  int32_t vf_size;         /* floor(reward_type["vf_size"]) or -1 for None (SDE:349-355) */
+  int32_t vf_size;         /* floor(reward_type["vf_size"]) or -1 for None (SDE:349-355); a NEGATIVE Python vf_size clears
+                              every pair (alignment term 0): the caller passes -1 together with w_alignment = 0 */
   uint32_t rng_step;       /* device tapes: index of this step (the caller increments it) */
   uint64_t rng_seed;       /* device tapes: key of the step streams */
 } swarm_step_in;
