@@ -14,8 +14,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(_HERE, "libswarm_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "swarm_abi.h")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 PATH_AUTO, PATH_STAGED, PATH_FUSED, PATH_GROUP, PATH_STAGED_PAIRWISE = 0, 1, 2, 3, 4
+
+E_NOT_READY = -5
+FLAG_NO_FAR_BORDER, FLAG_VF_DENSE = 1, 4
 
 ERR_SLAB_OVERFLOW = 1
 ERR_PLACE_OVERFLOW = 2
@@ -37,13 +40,15 @@ class Config(C.Structure):
                 ("num_agents", C.c_int32), ("grid_size", C.c_int32), ("attraction_thresh", C.c_int32),
                 ("repulsion_thresh", C.c_int32), ("predator_eat_rew", C.c_float), ("slab_len", C.c_int32),
                 ("place_len", C.c_int32), ("pred_attempts", C.c_int32), ("reset_slots", C.c_int32),
-                ("auto_reset", C.c_int32), ("track_stats", C.c_int32), ("path", C.c_int32)]
+                ("auto_reset", C.c_int32), ("track_stats", C.c_int32), ("path", C.c_int32),
+                ("flags", C.c_uint32), ("tiny16_min_envs", C.c_int32), ("env_offset", C.c_uint32),
+                ("reserved", C.c_int32)]
 
 
 class State(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("x", "y", "px", "py", "target", "pred_orient", "frozen", "err", "reset_count",
-                 "ep_len", "ep_ret", "fin_count", "fin_len", "fin_ret")]
+                ("x", "y", "px", "py", "target", "pred_orient", "frozen", "err", "reset_count", "tcell",
+                 "ep_rec", "fin_count", "fin_len", "fin_ret")]
 
 
 class StepIn(C.Structure):
@@ -55,11 +60,11 @@ class StepIn(C.Structure):
 class StepOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("done", "eaten", "reward", "counts", "pred_prev", "pred_next", "step_orient", "step_target",
-                 "consumed", "term_x", "term_y", "agent_reward", "agent_counts", "eff_action")]
+                 "consumed", "term_x", "term_y", "agent_reward", "agent_counts", "eff_action", "agent_terms")]
 
 
 # every symbol include/swarm_abi.h declares: name -> (restype, argtypes)
-_VP, _I32, _DP = C.c_void_p, C.c_int32, C.POINTER(C.c_double)
+_VP, _I32, _U64, _DP = C.c_void_p, C.c_int32, C.c_uint64, C.POINTER(C.c_double)
 EXPORTS = {
     "swarm_create": (C.c_int, [C.POINTER(Config), C.POINTER(_VP)]),
     "swarm_destroy": (C.c_int, [_VP]),
@@ -73,11 +78,15 @@ EXPORTS = {
     "swarm_path_name": (C.c_char_p, [_VP]),
     "swarm_last_launch_count": (C.c_int, [_VP]),
     "swarm_move": (C.c_int, [_I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP]),
-    "swarm_predator": (C.c_int, [_I32, _I32, _I32] + [_VP] * 13),
-    "swarm_pairwise": (C.c_int, [_I32, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP]),
+    "swarm_predator": (C.c_int, [_I32, _I32, _I32] + [_VP] * 14),
+    "swarm_pairwise": (C.c_int, [_I32, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _U64, _VP]),
+    "swarm_pairwise_scratch_bytes": (_U64, [_I32, _I32]),
     "swarm_autoreset": (C.c_int, [_VP, _VP, _VP]),
     "swarm_observe_vf": (C.c_int, [_I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "swarm_stats_begin": (C.c_int, [_VP, _I32, _VP]),
+    "swarm_stats_end": (C.c_int, [_VP, _DP, _I32]),
     "swarm_stats_read": (C.c_int, [_VP, _DP, _VP]),
+    "swarm_nccl_adopt": (C.c_int, [_VP, _VP]),
     "swarm_nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "swarm_nccl_init": (C.c_int, [_VP, C.POINTER(C.c_uint8), _I32, _I32]),
     "swarm_stats_allreduce": (C.c_int, [_VP, _DP, _VP]),

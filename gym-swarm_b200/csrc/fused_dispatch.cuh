@@ -8,8 +8,7 @@ namespace swarm {
 template <int LPE, int APL>
 static int fused_smem_bytes(const StepParams& p, int vfm) {
   using C = FusedCfg<LPE, APL>;
-  const int hist_words = (p.box.enabled && p.box.need_hist) ? 2 * p.S : 0;
-  return C::WARPS * (C::pair_bytes() + C::vf_bytes(vfm) + C::EPW * (p.bitmap_words + hist_words) * 4);
+  return C::WARPS * (C::pair_bytes() + C::vf_bytes(vfm) + C::far_bytes() + C::EPW * p.bitmap_words * 4);
 }
 
 #define FUSED_DISPATCH(_l, _a, CALL)                             \

@@ -15,8 +15,7 @@ void choose_fused_shape(int N, int& lpe, int& apl) {
 
 template <int LPE, int APL>
 static cudaError_t prepare(const StepParams& p) {
-  return cudaFuncSetAttribute(fused_step_kernel<LPE, APL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              fused_smem_bytes<LPE, APL>(p, 0));
+  return smem_opt_in(fused_step_kernel<LPE, APL, 0>, fused_smem_bytes<LPE, APL>(p, 0));
 }
 
 template <int LPE, int APL>

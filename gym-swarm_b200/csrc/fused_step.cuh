@@ -53,7 +53,19 @@ struct Seg {
   }
   __device__ __forceinline__ bool any(bool pred) const { return (__ballot_sync(mask, pred) & mask) != 0u; }
   __device__ __forceinline__ unsigned bcast(unsigned v, int src) const { return __shfl_sync(mask, v, src, LPE); }
+#ifdef SWARM_RACE_JITTER
+  // Race canary build (tools/race_canary.py): after every lane-group barrier the lanes are pushed out of lockstep by
+  // lane- and call-dependent sleeps, so that an exchange through shared memory that lacks its barrier -- and only works
+  // because a converged warp happens to run in lockstep -- produces results that differ from the production build.
+  mutable unsigned jit = 0x9E3779B9u;
+  __device__ __forceinline__ void sync() const {
+    __syncwarp(mask);
+    jit = jit * 1664525u + 1013904223u + (unsigned)li * 0x85EBCA6Bu;
+    if ((jit >> 29) < 3u) __nanosleep(64u + ((jit >> 20) & 255u));
+  }
+#else
   __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+#endif
 };
 
 // ---- vectorised per-lane loads / stores of APL consecutive elements -------------------------------
@@ -176,22 +188,9 @@ __device__ __forceinline__ void occupancy_counts(const Seg<LPE>& g, unsigned* sk
 //     c_i = 1 + #{hit agents standing on agent i's cell}.
 // The (few) hit agents broadcast their cell one after the other and everybody compares: O(hits * APL) per lane
 // instead of the O(N * APL) all-pairs sweep.  Returns false (c untouched) when no cell is shared.
-// keep_clean: when no cell is shared, leave the bits set (the caller runs the box-count reward on the bitmap and
-// clears it afterwards with bitmap_clear).
-template <int LPE, int APL>
-__device__ __forceinline__ void bitmap_clear(const Seg<LPE>& g, unsigned* sbit, int N, int S, int i0,
-                                             const int (&cx)[APL], const int (&cy)[APL]) {
-  g.sync();
-#pragma unroll
-  for (int k = 0; k < APL; ++k)
-    if (i0 + k < N) sbit[(cy[k] * S + cx[k]) >> 5] = 0u;
-  g.sync();
-}
-
 template <int LPE, int APL>
 __device__ __forceinline__ bool bitmap_counts(const Seg<LPE>& g, unsigned* sbit, int N, int S, int i0,
-                                              const int (&cx)[APL], const int (&cy)[APL], int (&c)[APL],
-                                              bool keep_clean) {
+                                              const int (&cx)[APL], const int (&cy)[APL], int (&c)[APL]) {
   unsigned pending = 0u;
   int word[APL];
 #pragma unroll
@@ -207,7 +206,6 @@ __device__ __forceinline__ bool bitmap_counts(const Seg<LPE>& g, unsigned* sbit,
   }
   const bool any = g.any(pending != 0u);   // ballot also orders the atomics before the clears below
   g.sync();
-  if (!any && keep_clean) return false;    // bitmap = exact occupancy of the final positions, left in place
 #pragma unroll
   for (int k = 0; k < APL; ++k)
     if (word[k] >= 0) sbit[word[k]] = 0u;
@@ -275,7 +273,7 @@ __device__ __noinline__ void reset_group(const StepParams& p, const Seg<LPE>& g,
   for (;;) {
     int c[APL];
     if (sbit) {                                   // (clean) per-env bitmap of the step kernel: O(hits) instead of O(N)
-      if (!bitmap_counts<LPE, APL>(g, sbit, N, S, i0, x, y, c, false)) break;
+      if (!bitmap_counts<LPE, APL>(g, sbit, N, S, i0, x, y, c)) break;
     } else {
       occupancy_counts<LPE, APL>(g, skey, N, i0, x, y, c);
     }
@@ -471,52 +469,69 @@ __device__ __forceinline__ void vf_sparse_accumulate(const Seg<LPE>& g, const un
 }
 
 // ---- far thresholds from the border agents only ------------------------------------------------------------------
-// For a threshold t > S/2 a pair with D >= t needs one agent within b = S - t cells of a border and the other within
-// b cells of the OPPOSITE border, so #{j : D_ij < t} = N-1 for every agent outside the border band and only the
-// (few) band agents have to be paired with each other.  They are compacted into shared memory (positions in
-// slist[0, nb), counters in slist[NMAX, NMAX + nb)) and every (i, j) pair among them is evaluated once by some lane.
+// For a threshold t > S/2 a pair with D >= t needs |dx| >= t or |dy| >= t, i.e. one agent within b = S - t cells of a
+// border and the other within b cells of the OPPOSITE border.  So #{j : D_ij < t} = N-1 for every agent outside the
+// border band, and only LOW-band x HIGH-band candidate pairs have to be looked at, per axis:
+//   X pass: i in LX (x < b), j in HX (x >= S-b):  far  <=>  xj - xi >= t
+//   Y pass: i in LY (y < b), j in HY (y >= S-b):  far  <=>  yj - yi >= t  and not |xj - xi| >= t   (a pair far apart in
+//           both axes sits in opposite X bands as well and was counted by the X pass)
+// ~ (N b / S)^2 candidates per axis instead of the (4 N b / S)^2 of an all-band x all-band loop (16 + 16 instead of 240
+// at N = S = 128, att = 5).  Runs after the ring sweep: the positions are read from the staged pair words, the lists
+// hold agent indices.  sfar (per env): [0,4) list lengths nLX nHX nLY nHY; [4, 4+NMAX) per-agent counters
+// (#far(t_repf) | #far(t_attf) << 16); then two u16 arrays of NMAX entries: the X lists (LX grows from the front, HX
+// from the back -- an agent is in at most one of them) and the Y lists.
 // Outputs aRf / aAf in the sweep's convention (self included): N - #{j != i : D_ij >= t}.
 template <int LPE, int APL>
-__device__ __forceinline__ void far_border_counts(const StepParams& p, const Seg<LPE>& g, unsigned* slist, int N, int S, int i0,
-                                                  const int (&cx)[APL], const int (&cy)[APL], unsigned (&aRf)[APL],
-                                                  unsigned (&aAf)[APL]) {
+__device__ __forceinline__ void far_border_counts(const StepParams& p, const Seg<LPE>& g, const uint4* __restrict__ spw,
+                                                  unsigned* __restrict__ sfar, int N, int S, int i0,
+                                                  const unsigned (&XI)[APL], const unsigned (&YI)[APL],
+                                                  unsigned (&aRf)[APL], unsigned (&aAf)[APL]) {
   constexpr int NMAX = LPE * APL;
+  unsigned* __restrict__ ctr = sfar + 4;
+  unsigned short* __restrict__ xl = reinterpret_cast<unsigned short*>(sfar + 4 + NMAX);
+  unsigned short* __restrict__ yl = xl + NMAX;
   const int b = p.far_band;
-  const unsigned lt_mask = (1u << (threadIdx.x & 31)) - 1u;
-  int slot[APL];
-  int nb = 0;
+  if (g.li < 4) sfar[g.li] = 0u;
+#pragma unroll
+  for (int k = 0; k < APL; ++k) ctr[i0 + k] = 0u;
+  g.sync();
 #pragma unroll
   for (int k = 0; k < APL; ++k) {
-    const bool f = (i0 + k < N) && (cx[k] < b || cx[k] >= S - b || cy[k] < b || cy[k] >= S - b);
-    const unsigned ball = __ballot_sync(g.mask, f) & g.mask;
-    slot[k] = f ? nb + __popc(ball & lt_mask) : -1;
-    if (f) slist[slot[k]] = pack2(cx[k], cy[k]);
-    nb += __popc(ball);
-  }
-  g.sync();
-  // lane j owns band agent j (one chunk of LPE at a time) and sweeps all band agents i: independent broadcast loads,
-  // the count stays in a register (no atomics)
-  for (int j0 = 0; j0 < nb; j0 += LPE) {
-    const int j = j0 + g.li;
-    const unsigned pj = j < nb ? slist[j] : 0u;
-    const int xj = (int)(pj & 0xFFFFu), yj = (int)(pj >> 16);
-    unsigned acc = 0u;
-#pragma unroll 4
-    for (int i = 0; i < nb; ++i) {
-      const unsigned pi = slist[i];
-      const int d = max(iabs(xj - (int)(pi & 0xFFFFu)), iabs(yj - (int)(pi >> 16)));
-      acc += (i != j) ? ((unsigned)(d >= p.t_repf) | ((unsigned)(d >= p.t_attf) << 16)) : 0u;
+    const int x = (int)(XI[k] & 0xFFFFu), y = (int)(YI[k] & 0xFFFFu);
+    if (i0 + k < N && (x < b || x >= S - b || y < b || y >= S - b)) {      // ~ 4 b / S of the agents
+      const unsigned short id = (unsigned short)(i0 + k);
+      if (x < b) xl[atomicAdd(&sfar[0], 1u)] = id;
+      else if (x >= S - b) xl[NMAX - 1 - atomicAdd(&sfar[1], 1u)] = id;
+      if (y < b) yl[atomicAdd(&sfar[2], 1u)] = id;
+      else if (y >= S - b) yl[NMAX - 1 - atomicAdd(&sfar[3], 1u)] = id;
     }
-    if (j < nb) slist[NMAX + j] = acc;
+  }
+  g.sync();
+  const int nLX = (int)sfar[0], nHX = (int)sfar[1], nLY = (int)sfar[2], nHY = (int)sfar[3];
+  const int totX = nLX * nHX, tot = totX + nLY * nHY;
+  for (int q = g.li; q < tot; q += LPE) {
+    const bool yp = q >= totX;
+    const int qq = yp ? q - totX : q, nh = yp ? nHY : nHX;
+    const int ii = qq / nh, jj = qq - ii * nh;
+    const unsigned short* __restrict__ lst = yp ? yl : xl;
+    const int a = lst[ii], c = lst[NMAX - 1 - jj];
+    // agent n sits in half n % 2 of pair word (n % APL / 2) * LPE + n / APL (the ring sweep's [word][lane] layout)
+    const uint4 wa = spw[((a % APL) >> 1) * LPE + a / APL], wc = spw[((c % APL) >> 1) * LPE + c / APL];
+    const int sa = 16 * (a & 1), sc = 16 * (c & 1);
+    const int xa = (int)((wa.x >> sa) & 0xFFFFu), ya = (int)((wa.y >> sa) & 0xFFFFu);
+    const int xc = (int)((wc.x >> sc) & 0xFFFFu), yc = (int)((wc.y >> sc) & 0xFFFFu);
+    const int dm = yp ? yc - ya : xc - xa;                 // along the pass axis (c is the high-band agent: dm > 0)
+    const int dox = yp ? iabs(xc - xa) : -1;               // Y pass: the pair must not be far in x already
+    const unsigned v = (unsigned)(dm >= p.t_repf && dox < p.t_repf) | ((unsigned)(dm >= p.t_attf && dox < p.t_attf) << 16);
+    if (v) { atomicAdd(&ctr[a], v); atomicAdd(&ctr[c], v); }
   }
   g.sync();
 #pragma unroll
   for (int k = 0; k < APL; ++k) {
-    const unsigned v = slot[k] >= 0 ? slist[NMAX + slot[k]] : 0u;
+    const unsigned v = ctr[i0 + k];
     aRf[k] = (unsigned)N - (v & 0xFFFFu);
     aAf[k] = (unsigned)N - (v >> 16);
   }
-  g.sync();                                                       // the list region is the pair-word staging area next
 }
 
 // ---- the fused step kernel ------------------------------------------------------------------------
@@ -536,7 +551,57 @@ struct FusedCfg {
     return vfm == 0 ? 0 : vfm == 1 ? NMAX * 8 : NMAX * 20 + hit_words() * 4;
   }
   __host__ __device__ static constexpr int vf_bytes(int vfm) { return EPW * vf_env_bytes(vfm); }
+  // scratch of the far-threshold border pass (ring kernels): 4 list lengths + NMAX counters + 2 x NMAX u16 list entries
+  __host__ __device__ static constexpr int far_env_words() { return ring_ok() ? 4 + 2 * NMAX : 0; }
+  __host__ __device__ static constexpr int far_bytes() { return EPW * far_env_words() * 4; }
 };
+
+// Terminal step of one env group (SDE:321-327) + auto-reset (SDE:197-221): rare (an env finishes every ~100 steps), so
+// it lives out of line and its registers do not count against the hot path.
+template <int LPE, int APL>
+__device__ __noinline__ void terminal_step(const StepParams& p, const Seg<LPE>& g, int env, unsigned* skey, unsigned* sbit,
+                                           int i0, int (&nx)[APL], int (&ny)[APL], int px, int py, int target, int orient,
+                                           int eaten, uint4 ep0) {
+  const int N = p.N;
+  const size_t base = (size_t)env * (size_t)N;
+  const bool vec = (N % APL) == 0;
+#pragma unroll
+  for (int k = 0; k < APL; ++k) {
+    if (i0 + k < N) {
+      if (p.agent_reward)
+        reinterpret_cast<float4*>(p.agent_reward)[base + i0 + k] = make_float4(0.f, 0.f, 0.f, (i0 + k == eaten) ? p.eat : 0.f);
+      if (p.agent_counts) reinterpret_cast<int2*>(p.agent_counts)[base + i0 + k] = make_int2(0, 0);
+      if (p.agent_terms) reinterpret_cast<uint2*>(p.agent_terms)[base + i0 + k] = make_uint2(0u, 0u);
+    }
+  }
+  if (g.li == 0) {
+    float* rw = p.reward + 5 * (size_t)env;
+    rw[0] = p.eat; rw[1] = 0.f; rw[2] = 0.f; rw[3] = 0.f; rw[4] = p.eat;
+    p.counts[2 * env] = 0;
+    p.counts[2 * env + 1] = 0;
+    if (p.track_stats) episode_update(p, env, ep0, true, p.eat, 0.f, 0.f, 0.f);
+  }
+  if (p.term_x) {
+    store_i16<APL>(p.term_x + base, i0, N, vec, nx);
+    store_i16<APL>(p.term_y + base, i0, N, vec, ny);
+  }
+  unsigned err = 0;
+  if (p.auto_reset) {
+    reset_group<LPE, APL>(p, g, env, skey, sbit, i0, nx, ny, px, py, target, err);
+    orient = 0;                                             // SDE:107
+  } else if (g.li == 0) {
+    p.frozen[env] = 1;
+  }
+  store_i16<APL>(p.x + base, i0, N, vec, nx);
+  store_i16<APL>(p.y + base, i0, N, vec, ny);
+  if (g.li == 0) {
+    p.px[env] = (int16_t)px;
+    p.py[env] = (int16_t)py;
+    p.target[env] = target;
+    p.orient[env] = (uint8_t)orient;
+    if (err) p.err[env] |= err;
+  }
+}
 
 template <int LPE, int APL, int VFM>
 __global__ void __launch_bounds__(FusedCfg<LPE, APL>::WARPS * 32,
@@ -553,9 +618,9 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
   const int env = (blockIdx.x * C::WARPS + warp) * C::EPW + g.seg;
   const int N = p.N, S = p.S;
 
-  // smem carve-up (per warp, then per env group)
-  const int hist_words = (p.box.enabled && p.box.need_hist) ? 2 * S : 0;   // per-env column / row histograms
-  const int warp_bytes = C::pair_bytes() + C::vf_bytes(VFM) + C::EPW * (p.bitmap_words + hist_words) * 4;
+  // smem carve-up (per warp, then per env group): pair words (aliased by the collision keys) | visual-field words |
+  // border-pass scratch | occupancy bitmap
+  const int warp_bytes = C::pair_bytes() + C::vf_bytes(VFM) + C::far_bytes() + C::EPW * p.bitmap_words * 4;
   unsigned char* wbase = smem_raw + (size_t)warp * warp_bytes;
   uint4* spw = reinterpret_cast<uint4*>(wbase) + g.seg * C::PW;
   unsigned* skey = reinterpret_cast<unsigned*>(spw);   // aliases the pair words (NMAX words <= PW*4 words)
@@ -563,9 +628,9 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
   uint2* svf = reinterpret_cast<uint2*>(vbase);
   unsigned* sacc = reinterpret_cast<unsigned*>(vbase + C::NMAX * 8);   // sparse mode: count / axis / diagonal sums
   unsigned* shits = sacc + 3 * C::NMAX;                                 // sparse mode: hit words of the sweep
-  unsigned* sbit = reinterpret_cast<unsigned*>(wbase + C::pair_bytes() + C::vf_bytes(VFM)) +
-                   g.seg * (p.bitmap_words + hist_words);
-  int* shist = reinterpret_cast<int*>(sbit + p.bitmap_words);
+  unsigned* sfar = reinterpret_cast<unsigned*>(wbase + C::pair_bytes() + C::vf_bytes(VFM)) + g.seg * C::far_env_words();
+  unsigned* sbit = reinterpret_cast<unsigned*>(wbase + C::pair_bytes() + C::vf_bytes(VFM) + C::far_bytes()) +
+                   g.seg * p.bitmap_words;
   if (p.bitmap_words) {
     for (int w = g.li; w < p.bitmap_words; w += LPE) sbit[w] = 0u;
   }
@@ -576,8 +641,8 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
   const size_t base = (size_t)env * (size_t)N;
   const bool vec = (N % APL) == 0;
 
-  // every load the step needs is issued here, before the first dependent branch, so that one DRAM round trip covers
-  // all of it (the frozen flag, the state and -- for lane 0 -- the running episode statistics)
+  // every load the first phases need is issued here, before the first dependent branch, so that one DRAM round trip
+  // covers all of it
   const int is_frozen = p.frozen[env];
   int x[APL], y[APL], act[APL];
   load_i16<APL>(p.x + base, i0, N, vec, x);
@@ -585,12 +650,9 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
   load_u8<APL>(p.actions + base, i0, N, vec, act);
   int px = p.px[env], py = p.py[env];
   int target = p.target[env];
-  unsigned ep_len0 = 0u;
-  float4 ep_ret0 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.track_stats && g.li == 0) { ep_len0 = p.ep_len[env]; ep_ret0 = reinterpret_cast<const float4*>(p.ep_ret)[env]; }
 
-  if (is_frozen) {                          // SDE:233-234: finished episode, auto-reset off
-    if (g.li == 0) {
+  if (is_frozen) {                          // SDE:233-234: finished episode, auto-reset off: nothing moves, every output
+    if (g.li == 0) {                        // of the step is defined (zero reward, the predator where it stands)
       p.err[env] |= SWARM_ERR_STEP_WHEN_DONE;
       p.done[env] = 1;
       p.eaten[env] = -1;
@@ -598,6 +660,19 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
       p.consumed[env] = 0;
 #pragma unroll
       for (int q = 0; q < 5; ++q) p.reward[5 * env + q] = 0.f;
+      p.pred_prev[2 * env] = (int16_t)px; p.pred_prev[2 * env + 1] = (int16_t)py;
+      p.pred_next[2 * env] = (int16_t)px; p.pred_next[2 * env + 1] = (int16_t)py;
+      p.step_orient[env] = p.orient[env];
+      p.step_target[env] = target;
+    }
+#pragma unroll
+    for (int k = 0; k < APL; ++k) {
+      if (i0 + k < N) {
+        if (p.agent_reward) reinterpret_cast<float4*>(p.agent_reward)[base + i0 + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.agent_counts) reinterpret_cast<int2*>(p.agent_counts)[base + i0 + k] = make_int2(0, 0);
+        if (p.agent_terms) reinterpret_cast<uint2*>(p.agent_terms)[base + i0 + k] = make_uint2(0u, 0u);
+        if (p.eff_action) p.eff_action[base + i0 + k] = 8;
+      }
     }
     return;
   }
@@ -614,9 +689,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
     if (g.any(bad)) err |= SWARM_ERR_BAD_ACTION;
   }
   int cur = 0;
-  const uint8_t* __restrict__ slab = p.slab + (size_t)env * (size_t)p.K;
-  const bool use_box = !HAS_VF && p.box.enabled && p.bitmap_words > 0;
-  bool bits_live = false;        // the bitmap holds the final (collision free) positions: box-count reward
+  const uint8_t* __restrict__ slab = p.slab ? p.slab + (size_t)env * (size_t)p.K : nullptr;
   for (;;) {
 #pragma unroll
     for (int k = 0; k < APL; ++k) {
@@ -625,7 +698,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
     }
     int c[APL];
     if (p.bitmap_words) {
-      if (!bitmap_counts<LPE, APL>(g, sbit, N, S, i0, nx, ny, c, use_box)) { bits_live = use_box; break; }
+      if (!bitmap_counts<LPE, APL>(g, sbit, N, S, i0, nx, ny, c)) break;
     } else {
       occupancy_counts<LPE, APL>(g, skey, N, i0, nx, ny, c);
     }
@@ -659,7 +732,6 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
     const unsigned tp = g.bcast(mine, lt);
     pursue(px, py, (int)(int16_t)(tp & 0xFFFFu), (int)(int16_t)(tp >> 16), S, px, py, orient);
   }
-  const int step_target = target;
 
   // ---- termination (SDE:307-309, 321-327) on the NEW positions ---------------------------------
   unsigned hit = 0xFFFFu;
@@ -668,75 +740,50 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
     if (i0 + k < N && nx[k] == px && ny[k] == py) hit = min(hit, (unsigned)(i0 + k));
   hit = g.umin(hit);
   const bool done = hit != 0xFFFFu;
-  const int eaten = done ? (int)hit : -1;
+
+  // ---- everything that does not depend on the reward is written NOW: the per-env scalars die here instead of
+  // staying in registers across the pair sweep (which is what bounds the number of envs in flight per SM) ----------
+  if (p.eff_action) store_u8<APL>(p.eff_action + base, i0, N, vec, eff);
+  if (g.li == 0) {
+    p.done[env] = done ? 1 : 0;
+    p.eaten[env] = done ? (int)hit : -1;
+    p.pred_prev[2 * env] = (int16_t)prev_px; p.pred_prev[2 * env + 1] = (int16_t)prev_py;
+    p.pred_next[2 * env] = (int16_t)px; p.pred_next[2 * env + 1] = (int16_t)py;
+    p.step_orient[env] = (uint8_t)orient;
+    p.step_target[env] = target;
+    p.consumed[env] = cur;
+    if (err) p.err[env] |= err;
+  }
+  if (done) {                                               // rare, out of line
+    uint4 ep0 = make_uint4(0u, 0u, 0u, 0u);
+    if (p.track_stats && g.li == 0) ep0 = reinterpret_cast<const uint4*>(p.ep_rec)[env];
+    terminal_step<LPE, APL>(p, g, env, skey, p.bitmap_words ? sbit : nullptr, i0, nx, ny, px, py, target, orient, (int)hit, ep0);
+    return;
+  }
+  // commit of the running episode (SDE:260)
+  store_i16<APL>(p.x + base, i0, N, vec, nx);
+  store_i16<APL>(p.y + base, i0, N, vec, ny);
+  if (g.li == 0) {
+    p.px[env] = (int16_t)px;
+    p.py[env] = (int16_t)py;
+    p.target[env] = target;
+    p.orient[env] = (uint8_t)orient;
+  }
 
   // ---- reward (SDE:330-379) ---------------------------------------------------------------------
-  double r_surv = 0.0, r_att = 0.0, r_rep = 0.0, r_ali = 0.0, r_sum = 0.0;
-  int g_rep = 0, g_att = 0;
-  if (!done) {
-    unsigned aR[APL], aA[APL], aRf[APL], aAf[APL];       // threshold counts of each owned agent, self included
-    unsigned aV[APL], accA[APL], accD[APL];
+  unsigned aR[APL], aA[APL], aRf[APL], aAf[APL];       // threshold counts of each owned agent, self included
+  unsigned aV[APL], accA[APL], accD[APL];
 #pragma unroll
-    for (int k = 0; k < APL; ++k) aR[k] = aA[k] = aRf[k] = aAf[k] = aV[k] = accA[k] = accD[k] = 0u;
-    if (bits_live) {
-      // ---- box counts on the env's occupancy bitmap (see swarm_common.cuh) ----------
-      int* hx = shist;
-      int* hy = shist + S;
-      if (p.box.need_hist) {
-        for (int a = g.li; a < 2 * S; a += LPE) shist[a] = 0;
-        g.sync();
+  for (int k = 0; k < APL; ++k) aR[k] = aA[k] = aRf[k] = aAf[k] = aV[k] = accA[k] = accD[k] = 0u;
+  unsigned effp = 0u;                                  // the effective actions, 4 bits each (eff[] dies here)
 #pragma unroll
-        for (int k = 0; k < APL; ++k)
-          if (i0 + k < N) { atomicAdd(&hx[nx[k]], 1); atomicAdd(&hy[ny[k]], 1); }
-        g.sync();
-        const int hper = (S + LPE - 1) / LPE;
-        const int h0 = min(S, g.li * hper), h1 = min(S, h0 + hper);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          int* h = q ? hy : hx;
-          int run = 0;
-          for (int a = h0; a < h1; ++a) run += h[a];
-          int tot;
-          int carry = g.excl_scan(run, tot);
-          for (int a = h0; a < h1; ++a) { carry += h[a]; h[a] = carry; }
-        }
-        g.sync();
-      }
-      if (p.box.fast_rmax >= 0) {
-#pragma unroll
-        for (int k = 0; k < APL; ++k) {
-          // padding agents sweep (clamped, in-range) rows too so that the row loop stays convergent; their counts
-          // are never used
-          const int xi = i0 + k < N ? nx[k] : 0, yi = i0 + k < N ? ny[k] : 0;
-          int cnt[4];
-          box_direct_sweep(p.box, sbit, xi, yi, S, cnt);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (p.box.mode[q] != BOX_DIRECT) cnt[q] = box_count(p.box, q, sbit, hx, hy, xi, yi, S, N);
-          aR[k] = (unsigned)cnt[0]; aA[k] = (unsigned)cnt[1]; aRf[k] = (unsigned)cnt[2]; aAf[k] = (unsigned)cnt[3];
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < APL; ++k) {
-          if (i0 + k < N) {
-            aR[k] = (unsigned)box_count(p.box, 0, sbit, hx, hy, nx[k], ny[k], S, N);
-            aA[k] = (unsigned)box_count(p.box, 1, sbit, hx, hy, nx[k], ny[k], S, N);
-            aRf[k] = (unsigned)box_count(p.box, 2, sbit, hx, hy, nx[k], ny[k], S, N);
-            aAf[k] = (unsigned)box_count(p.box, 3, sbit, hx, hy, nx[k], ny[k], S, N);
-          }
-        }
-      }
-    } else {
-      bool far_done = false;
-      if constexpr (RING) {
-        if (p.far_border) {                              // both far thresholds > S/2: only border agents can be far apart
-          far_border_counts<LPE, APL>(p, g, skey, N, S, i0, nx, ny, aRf, aAf);
-          far_done = true;
-        }
-      }
-      // stage the env's positions as packed pair words {x2, y2, -x2, -y2}; padding agents sit at x=-S
+  for (int k = 0; k < APL; ++k) effp |= (unsigned)eff[k] << (4 * k);
+  {
+    // stage the env's positions as packed pair words {x2, y2, -x2, -y2}; padding agents sit at x=-S
+    unsigned XI[APL], YI[APL], NXI[APL], NYI[APL];
+    {
       int sx[APL], sy[APL];
-  #pragma unroll
+#pragma unroll
       for (int k = 0; k < APL; ++k) {
         const bool v = i0 + k < N;
         sx[k] = v ? nx[k] : -S;
@@ -751,14 +798,14 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
         }
       } else {
         // ring sweep: word w of every lane contiguous ([w][lane]) so that the rotated LDS.128 is conflict free
-  #pragma unroll
+#pragma unroll
         for (int k = 0; k < APL; k += 2)
           spw[RING ? (k >> 1) * LPE + g.li : (i0 + k) >> 1] =
               make_uint4(pack2(sx[k], sx[k + 1]), pack2(sy[k], sy[k + 1]), pack2(-sx[k], -sx[k + 1]),
                          pack2(-sy[k], -sy[k + 1]));
       }
       if constexpr (HAS_VF) {
-  #pragma unroll
+#pragma unroll
         for (int k = 0; k < APL; ++k) {
           const int a = eff[k];
           const bool mover = (i0 + k < N) && a < 8;
@@ -769,210 +816,132 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
           if constexpr (VF_SPARSE) sacc[i0 + k] = sacc[C::NMAX + i0 + k] = sacc[2 * C::NMAX + i0 + k] = 0u;
         }
       }
-      g.sync();
-
-      unsigned XI[APL], YI[APL], NXI[APL], NYI[APL];
-  #pragma unroll
+#pragma unroll
       for (int k = 0; k < APL; ++k) {
         XI[k] = rep2(sx[k]); YI[k] = rep2(sy[k]); NXI[k] = rep2(-sx[k]); NYI[k] = rep2(-sy[k]);
       }
-      const unsigned TR = rep2(p.t_rep), TA = rep2(p.t_att), TRf = rep2(p.t_repf), TAf = rep2(p.t_attf);
-      const unsigned TV = rep2(HAS_VF ? p.t_vf : 0);
-      if constexpr (RING) {
-        // ---- symmetric ring sweep: every unordered block pair is evaluated once --------------------
-        // Lane l owns block B_l (APL agents = W pair words).  In round r it meets the block of lane l+r (pair words
-        // read from smem), adds each indicator to its own ROW counters and to the visiting block's COLUMN counters;
-        // the column counters travel round the ring by shuffles together with the block they belong to and are
-        // sent home after the last symmetric round.  Rounds 0 (own block) and LPE/2 (met from both sides) only
-        // count rows.  The accumulations are IMADs by a runtime 1 so that they issue on the FMA pipe and leave the
-        // ALU pipe to the DPX ops.
-        const unsigned one = (unsigned)p.one, c256 = (unsigned)p.one << 8;
-        int nhit = 0;
-        if (far_done)
-          ring_sweep<LPE, APL, false, VF_SPARSE>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf, TV, shits, nhit);
-        else
-          ring_sweep<LPE, APL, true, VF_SPARSE>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf, TV, shits, nhit);
-        if constexpr (VF_SPARSE) {
-          g.sync();
-          vf_sparse_accumulate<LPE, APL>(g, shits, nhit, svf, sacc, N);
-          g.sync();
+    }
+    g.sync();
+
+    const unsigned TR = rep2(p.t_rep), TA = rep2(p.t_att), TRf = rep2(p.t_repf), TAf = rep2(p.t_attf);
+    const unsigned TV = rep2(HAS_VF ? p.t_vf : 0);
+    if constexpr (RING) {
+      // ---- symmetric ring sweep: every unordered block pair is evaluated once --------------------
+      // Lane l owns block B_l (APL agents = W pair words).  In round r it meets the block of lane l+r (pair words
+      // read from smem), adds each indicator to its own ROW counters and to the visiting block's COLUMN counters;
+      // the column counters travel round the ring by shuffles together with the block they belong to and are
+      // sent home after the last symmetric round.  Rounds 0 (own block) and LPE/2 (met from both sides) only
+      // count rows.  The accumulations are IMADs by a runtime 1 so that they issue on the FMA pipe and leave the
+      // ALU pipe to the DPX ops.
+      const unsigned one = (unsigned)p.one, c256 = (unsigned)p.one << 8;
+      int nhit = 0;
+      if (p.far_border)      // both far thresholds > S/2: they come from the border pass below, the sweep carries {rep, att}
+        ring_sweep<LPE, APL, false, VF_SPARSE>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf, TV, shits, nhit);
+      else
+        ring_sweep<LPE, APL, true, VF_SPARSE>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf, TV, shits, nhit);
+      if constexpr (VF_SPARSE) {
+        g.sync();
+        vf_sparse_accumulate<LPE, APL>(g, shits, nhit, svf, sacc, N);
+        g.sync();
 #pragma unroll
-          for (int k = 0; k < APL; ++k) { aV[k] = sacc[i0 + k]; accA[k] = sacc[C::NMAX + i0 + k]; accD[k] = sacc[2 * C::NMAX + i0 + k]; }
-        }
-      } else {
-        const int NW = (N + 1) >> 1;
-  #pragma unroll 2
-        for (int q = 0; q < NW; ++q) {
-          const uint4 w = spw[q];
-          uint4 u = make_uint4(0, 0, 0, 0);
-          if constexpr (VFM == 1) u = *reinterpret_cast<const uint4*>(&svf[2 * q]);
-  #pragma unroll
-          for (int k = 0; k < APL; ++k) {
-            const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], w);
-            aR[k] += lt2(TR, m);
-            aA[k] += lt2(TA, m);
-            aRf[k] += lt2(TRf, m);
-            aAf[k] += lt2(TAf, m);
-            if constexpr (VFM == 1) {
-              const unsigned gate = lt2(TV, m);
-              const unsigned g0 = gate & 0xFFFFu, g1 = gate >> 16;
-              aV[k] += gate;
-              accA[k] += g0 * u.x + g1 * u.z;
-              accD[k] += g0 * u.y + g1 * u.w;
-            }
+        for (int k = 0; k < APL; ++k) { aV[k] = sacc[i0 + k]; accA[k] = sacc[C::NMAX + i0 + k]; accD[k] = sacc[2 * C::NMAX + i0 + k]; }
+      }
+      if (p.far_border) far_border_counts<LPE, APL>(p, g, spw, sfar, N, S, i0, XI, YI, aRf, aAf);
+    } else {
+      const int NW = (N + 1) >> 1;
+#pragma unroll 2
+      for (int q = 0; q < NW; ++q) {
+        const uint4 w = spw[q];
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if constexpr (VFM == 1) u = *reinterpret_cast<const uint4*>(&svf[2 * q]);
+#pragma unroll
+        for (int k = 0; k < APL; ++k) {
+          const unsigned m = neg_cheb2(XI[k], YI[k], NXI[k], NYI[k], w);
+          aR[k] += lt2(TR, m);
+          aA[k] += lt2(TA, m);
+          aRf[k] += lt2(TRf, m);
+          aAf[k] += lt2(TAf, m);
+          if constexpr (VFM == 1) {
+            const unsigned gate = lt2(TV, m);
+            const unsigned g0 = gate & 0xFFFFu, g1 = gate >> 16;
+            aV[k] += gate;
+            accA[k] += g0 * u.x + g1 * u.z;
+            accD[k] += g0 * u.y + g1 * u.w;
           }
         }
       }
-
     }
+  }
+  // the running-episode record is fetched now (lane 0): its latency hides behind the epilogue arithmetic
+  uint4 ep0 = make_uint4(0u, 0u, 0u, 0u);
+  if (p.track_stats && g.li == 0) ep0 = reinterpret_cast<const uint4*>(p.ep_rec)[env];
 
-    // alignment sums (SDE:346-359)
-    int Ax = 0, Ay = 0, Dx = 0, Dy = 0;
-    if constexpr (!HAS_VF) {
-      int ax = 0, ay = 0, dx = 0, dy = 0;
-#pragma unroll
-      for (int k = 0; k < APL; ++k) {
-        const int a = eff[k];
-        if (i0 + k < N && a < 8) {
-          const int mx = move_dx(a), my = move_dy(a);
-          if (a & 1) { dx += mx; dy += my; } else { ax += mx; ay += my; }
-        }
-      }
-      // two biased 16-bit fields per word keep the group reduction at 2 words
-      const unsigned s1 = (unsigned)g.sum((int)pack2(ax + APL, ay + APL));
-      const unsigned s2 = (unsigned)g.sum((int)pack2(dx + APL, dy + APL));
-      Ax = (int)(s1 & 0xFFFFu) - C::NMAX; Ay = (int)(s1 >> 16) - C::NMAX;
-      Dx = (int)(s2 & 0xFFFFu) - C::NMAX; Dy = (int)(s2 >> 16) - C::NMAX;
-    }
-
-    const int selfR = p.t_rep >= 1, selfA = p.t_att >= 1, selfRf = p.t_repf >= 1, selfAf = p.t_attf >= 1;
-    const int selfV = VF_SPARSE ? 0 : HAS_VF ? (p.t_vf >= 1) : 1;   // (the sparse sums never include the agent itself)
-    int s_rep = 0, s_att = 0, s_P = 0, s_Q = 0, s_vis = 0;
-    int rep_i[APL], att_i[APL];
-    double una_i[APL];
+  // alignment sums (SDE:346-359)
+  int Ax = 0, Ay = 0, Dx = 0, Dy = 0;
+  if constexpr (!HAS_VF) {
+    int ax = 0, ay = 0, dx = 0, dy = 0;
 #pragma unroll
     for (int k = 0; k < APL; ++k) {
-      const bool v = i0 + k < N;
-      int vis, P, Q;
-      if constexpr (HAS_VF) {
-        const int vin = VF_SPARSE ? (int)aV[k] : hsum2(aV[k]);   // gated count (dense: incl. self)
-        const int gAx = (int)(accA[k] & 0xFFFFu) - vin, gAy = (int)(accA[k] >> 16) - vin;
-        const int gDx = (int)(accD[k] & 0xFFFFu) - vin, gDy = (int)(accD[k] >> 16) - vin;
-        vis = vin - selfV;
-        align_PQ(eff[k], gAx, gAy, gDx, gDy, selfV, P, Q);
-      } else {
-        vis = N - 1;
-        align_PQ(eff[k], Ax, Ay, Dx, Dy, 1, P, Q);
+      const int a = (int)((effp >> (4 * k)) & 15u);
+      if (i0 + k < N && a < 8) {
+        const int mx = move_dx(a), my = move_dy(a);
+        if (a & 1) { dx += mx; dy += my; } else { ax += mx; ay += my; }
       }
-      const AgentTerms t = agent_terms(p, hsum2(aR[k]) - selfR, hsum2(aA[k]) - selfA, hsum2(aRf[k]) - selfRf,
-                                       hsum2(aAf[k]) - selfAf, vis, P, Q);
-      rep_i[k] = v ? t.rep_i : 0;
-      att_i[k] = v ? t.att_i : 0;
-      una_i[k] = v ? t.una : 0.0;
-      if (v) { s_rep += t.rep_i; s_att += t.att_i; s_P += P; s_Q += Q; s_vis += vis; }
     }
-    g_rep = g.sum(s_rep);
-    g_att = g.sum(s_att);
-    const int g_P = g.sum(s_P), g_Q = g.sum(s_Q);
-    const int g_vis = HAS_VF ? g.sum(s_vis) : N * (N - 1);
-    const double g_una = 0.5 * (double)g_vis - 0.25 * (double)g_P - 0.35355339059327376220 * (double)g_Q;
-    r_rep = p.w_rep * (double)g_rep * p.inv_nn;             // SDE:363-366
-    r_att = p.w_att * (double)g_att * p.inv_nn;
-    r_ali = p.w_ali * (-g_una) * p.inv_nn;
-    r_sum = r_rep + r_att + r_ali;
+    // two biased 16-bit fields per word keep the group reduction at 2 words
+    const unsigned s1 = (unsigned)g.sum((int)pack2(ax + APL, ay + APL));
+    const unsigned s2 = (unsigned)g.sum((int)pack2(dx + APL, dy + APL));
+    Ax = (int)(s1 & 0xFFFFu) - C::NMAX; Ay = (int)(s1 >> 16) - C::NMAX;
+    Dx = (int)(s2 & 0xFFFFu) - C::NMAX; Dy = (int)(s2 >> 16) - C::NMAX;
+  }
 
-    if (p.agent_reward) {                                   // SDE:371-379
-      float4* __restrict__ ar = reinterpret_cast<float4*>(p.agent_reward) + base;
+  const int selfR = p.t_rep >= 1, selfA = p.t_att >= 1, selfRf = p.t_repf >= 1, selfAf = p.t_attf >= 1;
+  const int selfV = VF_SPARSE ? 0 : HAS_VF ? (p.t_vf >= 1) : 1;   // (the sparse sums never include the agent itself)
+  int s_rep = 0, s_att = 0, s_P = 0, s_Q = 0, s_vis = 0;
 #pragma unroll
-      for (int k = 0; k < APL; ++k) {
-        if (i0 + k < N) {
-          const double a_rep = p.w_rep * (double)rep_i[k] * p.inv_nn;
-          const double a_att = p.w_att * (double)att_i[k] * p.inv_nn;
-          const double a_ali = p.w_ali * (-una_i[k]) * p.inv_nn;
-          ar[i0 + k] = make_float4((float)a_att, (float)a_rep, (float)a_ali, (float)(a_rep + a_att + a_ali));
-        }
+  for (int k = 0; k < APL; ++k) {
+    const bool v = i0 + k < N;
+    const int a = (int)((effp >> (4 * k)) & 15u);
+    int vis, P, Q;
+    if constexpr (HAS_VF) {
+      const int vin = VF_SPARSE ? (int)aV[k] : hsum2(aV[k]);   // gated count (dense: incl. self)
+      const int gAx = (int)(accA[k] & 0xFFFFu) - vin, gAy = (int)(accA[k] >> 16) - vin;
+      const int gDx = (int)(accD[k] & 0xFFFFu) - vin, gDy = (int)(accD[k] >> 16) - vin;
+      vis = vin - selfV;
+      align_PQ(a, gAx, gAy, gDx, gDy, selfV, P, Q);
+    } else {
+      vis = N - 1;
+      align_PQ(a, Ax, Ay, Dx, Dy, 1, P, Q);
+    }
+    const AgentTerms t = agent_terms(p, hsum2(aR[k]) - selfR, hsum2(aA[k]) - selfA, hsum2(aRf[k]) - selfRf,
+                                     hsum2(aAf[k]) - selfAf, vis, P, Q);
+    if (v) {
+      s_rep += t.rep_i; s_att += t.att_i; s_P += P; s_Q += Q; s_vis += vis;
+      if (p.agent_reward) {                                 // SDE:371-379
+        const double a_rep = p.w_rep * (double)t.rep_i * p.inv_nn;
+        const double a_att = p.w_att * (double)t.att_i * p.inv_nn;
+        const double a_ali = p.w_ali * (-t.una) * p.inv_nn;
+        reinterpret_cast<float4*>(p.agent_reward)[base + i0 + k] =
+            make_float4((float)a_att, (float)a_rep, (float)a_ali, (float)(a_rep + a_att + a_ali));
       }
-    }
-    if (p.agent_counts) {
-      int2* __restrict__ ac = reinterpret_cast<int2*>(p.agent_counts) + base;
-#pragma unroll
-      for (int k = 0; k < APL; ++k)
-        if (i0 + k < N) ac[i0 + k] = make_int2(rep_i[k], att_i[k]);
-    }
-    g.sync();   // pair words are dead; the reset path reuses the region as keys
-  } else {
-    r_surv = (double)p.eat;
-    r_sum = (double)p.eat;
-    if (p.agent_reward) {
-      float4* __restrict__ ar = reinterpret_cast<float4*>(p.agent_reward) + base;
-#pragma unroll
-      for (int k = 0; k < APL; ++k)
-        if (i0 + k < N) ar[i0 + k] = make_float4(0.f, 0.f, 0.f, (i0 + k == eaten) ? p.eat : 0.f);
-    }
-    if (p.agent_counts) {
-      int2* __restrict__ ac = reinterpret_cast<int2*>(p.agent_counts) + base;
-#pragma unroll
-      for (int k = 0; k < APL; ++k)
-        if (i0 + k < N) ac[i0 + k] = make_int2(0, 0);
+      if (p.agent_counts) reinterpret_cast<int2*>(p.agent_counts)[base + i0 + k] = make_int2(t.rep_i, t.att_i);
+      if (p.agent_terms) reinterpret_cast<uint2*>(p.agent_terms)[base + i0 + k] = pack_terms(t.rep_i, t.att_i, vis, P, Q);
     }
   }
-  if (bits_live) bitmap_clear<LPE, APL>(g, sbit, N, S, i0, nx, ny);
-  if (p.eff_action) store_u8<APL>(p.eff_action + base, i0, N, vec, eff);
-
-  // ---- per-env outputs ---------------------------------------------------------------------------
+  const int g_rep = g.sum(s_rep);
+  const int g_att = g.sum(s_att);
+  const int g_P = g.sum(s_P), g_Q = g.sum(s_Q);
+  const int g_vis = HAS_VF ? g.sum(s_vis) : N * (N - 1);
   if (g.li == 0) {
-    p.done[env] = done ? 1 : 0;
-    p.eaten[env] = eaten;
+    const double g_una = 0.5 * (double)g_vis - 0.25 * (double)g_P - 0.35355339059327376220 * (double)g_Q;
+    const double r_rep = p.w_rep * (double)g_rep * p.inv_nn;             // SDE:363-366
+    const double r_att = p.w_att * (double)g_att * p.inv_nn;
+    const double r_ali = p.w_ali * (-g_una) * p.inv_nn;
     float* rw = p.reward + 5 * (size_t)env;
-    rw[0] = (float)r_surv; rw[1] = (float)r_att; rw[2] = (float)r_rep; rw[3] = (float)r_ali; rw[4] = (float)r_sum;
+    rw[0] = 0.f; rw[1] = (float)r_att; rw[2] = (float)r_rep; rw[3] = (float)r_ali; rw[4] = (float)(r_rep + r_att + r_ali);
     p.counts[2 * env] = g_rep;
     p.counts[2 * env + 1] = g_att;
-    p.pred_prev[2 * env] = (int16_t)prev_px; p.pred_prev[2 * env + 1] = (int16_t)prev_py;
-    p.pred_next[2 * env] = (int16_t)px; p.pred_next[2 * env + 1] = (int16_t)py;
-    p.step_orient[env] = (uint8_t)orient;
-    p.step_target[env] = step_target;
-    p.consumed[env] = cur;
-    if (p.track_stats) {
-      const unsigned len = ep_len0 + 1u;
-      float4 ret = ep_ret0;
-      ret.x += (float)r_surv; ret.y += (float)r_att; ret.z += (float)r_rep; ret.w += (float)r_ali;
-      if (done) {                                  // single writer per env: fire-and-forget reductions, no read round trip
-        atomicAdd(&p.fin_count[env], 1u);
-        atomicAdd(&p.fin_len[env], len);
-        atomicAdd(&p.fin_ret[4 * env + 0], ret.x);
-        atomicAdd(&p.fin_ret[4 * env + 1], ret.y);
-        atomicAdd(&p.fin_ret[4 * env + 2], ret.z);
-        atomicAdd(&p.fin_ret[4 * env + 3], ret.w);
-        p.ep_len[env] = 0u;
-        reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-        p.ep_len[env] = len;
-        reinterpret_cast<float4*>(p.ep_ret)[env] = ret;
-      }
-    }
-  }
-
-  // ---- commit / auto-reset (SDE:260; reset semantics SDE:197-221) -----------------------------
-  if (done) {
-    if (p.term_x) {
-      store_i16<APL>(p.term_x + base, i0, N, vec, nx);
-      store_i16<APL>(p.term_y + base, i0, N, vec, ny);
-    }
-    if (p.auto_reset) {
-      reset_group<LPE, APL>(p, g, env, skey, p.bitmap_words ? sbit : nullptr, i0, nx, ny, px, py, target, err);
-      orient = 0;                                           // SDE:107
-    } else if (g.li == 0) {
-      p.frozen[env] = 1;
-    }
-  }
-  store_i16<APL>(p.x + base, i0, N, vec, nx);
-  store_i16<APL>(p.y + base, i0, N, vec, ny);
-  if (g.li == 0) {
-    p.px[env] = (int16_t)px;
-    p.py[env] = (int16_t)py;
-    p.target[env] = target;
-    p.orient[env] = (uint8_t)orient;
-    if (err) p.err[env] |= err;
+    if (p.track_stats) episode_update(p, env, ep0, false, 0.f, (float)r_att, (float)r_rep, (float)r_ali);
   }
 }
 
@@ -1010,8 +979,7 @@ fused_reset_kernel(const __grid_constant__ StepParams p, const uint8_t* __restri
     if (zero_counts) p.err[env] = err;
     else if (err) p.err[env] |= err;              // masked re-reset: error bits stay sticky
     if (p.track_stats) {
-      p.ep_len[env] = 0u;
-      reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<uint4*>(p.ep_rec)[env] = make_uint4(0u, 0u, 0u, 0u);
       if (zero_counts) {
         p.fin_count[env] = 0u;
         p.fin_len[env] = 0u;

@@ -1,6 +1,4 @@
 // fused_vf_launch.cu -- lane-group step kernels for vf_size steps (SDE:349-355): dense and sparse visual-field modes
-#include <stdlib.h>
-
 #include "fused_dispatch.cuh"
 
 namespace swarm {
@@ -11,19 +9,16 @@ namespace swarm {
 template <int LPE, int APL>
 static int vf_mode(const StepParams& p) {
   if (!FusedCfg<LPE, APL>::ring_ok()) return 1;
-  if (const char* ev = getenv("SWARM_VF_DENSE")) if (atoi(ev)) return 1;   // experiments / tests
+  if (p.vf_dense) return 1;                                                // SWARM_FLAG_VF_DENSE (tests / A-B runs)
   const long long w = 2LL * (p.t_vf - 1) + 1;
   return (w * w * 16 <= (long long)p.S * p.S) ? 2 : 1;
 }
 
 template <int LPE, int APL>
 static cudaError_t prepare(const StepParams& p) {
-  cudaError_t e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       fused_smem_bytes<LPE, APL>(p, 1));
+  cudaError_t e = smem_opt_in(fused_step_kernel<LPE, APL, 1>, fused_smem_bytes<LPE, APL>(p, 1));
   if constexpr (FusedCfg<LPE, APL>::ring_ok()) {
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(fused_step_kernel<LPE, APL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               fused_smem_bytes<LPE, APL>(p, 2));
+    if (e == cudaSuccess) e = smem_opt_in(fused_step_kernel<LPE, APL, 2>, fused_smem_bytes<LPE, APL>(p, 2));
   }
   return e;
 }

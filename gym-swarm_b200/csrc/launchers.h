@@ -6,6 +6,25 @@
 
 namespace swarm {
 
+// Opt-in to dynamic shared memory: cudaFuncAttributeMaxDynamicSharedMemorySize is a per-function, per-device attribute
+// shared by every handle, so it is only ever raised -- to the most the device allows this kernel (opt-in maximum minus
+// the kernel's static shared memory) -- never set to one handle's size: a second, smaller handle would otherwise lower
+// it under the first one's launches.
+template <typename K>
+static cudaError_t smem_opt_in(K kernel, int needed) {
+  int dev = 0, dev_max = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return e;
+  cudaFuncAttributes fa;
+  e = cudaFuncGetAttributes(&fa, kernel);
+  if (e != cudaSuccess) return e;
+  const int limit = dev_max - (int)fa.sharedSizeBytes;
+  if (needed > limit) return cudaErrorInvalidConfiguration;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+}
+
 constexpr int TINY_N = 8;        // largest N of the default thread-per-env kernel
 constexpr int TINY_N_BIG = 16;   // second instantiation (9..16 agents), used for large batches only
 

@@ -557,9 +557,10 @@ struct PredIO {
   int E, N, S;
   const int16_t *xo, *yo, *xn, *yn;
   const uint8_t *retarget, *frozen;   // retarget == NULL: Philox stream 1 (rng_* below)
-  unsigned rng_seed_lo, rng_seed_hi, rng_step;
+  unsigned rng_seed_lo, rng_seed_hi, rng_step, env_offset;
   int16_t *px, *py;
   int32_t* target;
+  int16_t* tcell;                     // [E,2] in/out cell of the target (swarm_state.tcell); NULL: read xo/yo[target]
   uint8_t* orient;
   int16_t *pred_prev, *pred_next;
   uint8_t* step_orient;
@@ -577,7 +578,7 @@ __device__ __forceinline__ unsigned warp_umin(unsigned v) {
 
 __device__ __forceinline__ int pred_retarget(const PredIO& io, int env) {
   if (io.retarget) return io.retarget[env];
-  return philox_retarget(io.rng_seed_lo, io.rng_seed_hi, io.rng_step, env);
+  return philox_retarget(io.rng_seed_lo, io.rng_seed_hi, io.rng_step, env + (int)io.env_offset);
 }
 
 // 8 packed agents (one uint4 of x, one of y) against the predator cell: nearest-neighbour keys
@@ -607,9 +608,25 @@ __device__ __forceinline__ void hit8(const uint4& xv, const uint4& yv, unsigned 
   }
 }
 
+// finished episode, auto-reset off (SDE:233-234): nothing moves, the step's predator outputs are the standing state
+__device__ __forceinline__ void predator_frozen(const PredIO& io, int env) {
+  io.err[env] |= SWARM_ERR_STEP_WHEN_DONE;
+  io.done[env] = 1;
+  io.eaten[env] = -1;
+  const unsigned pp = pack2(io.px[env], io.py[env]);
+  if (io.pred_prev) reinterpret_cast<unsigned*>(io.pred_prev)[env] = pp;
+  if (io.pred_next) reinterpret_cast<unsigned*>(io.pred_next)[env] = pp;
+  if (io.step_orient) io.step_orient[env] = io.orient[env];
+  if (io.step_target) io.step_target[env] = io.target[env];
+}
+
 __device__ __forceinline__ void predator_write(const PredIO& io, int env, int ppx, int ppy, int px, int py, int target,
                                                int orient, unsigned hit) {
   const bool done = hit != 0xFFFFFFFFu;
+  if (io.tcell) {   // the target's NEW cell = what the next step pursues; the line was just streamed (L1 hit)
+    const size_t t = (size_t)env * (size_t)io.N + (size_t)target;
+    reinterpret_cast<unsigned*>(io.tcell)[env] = pack2(io.xn[t], io.yn[t]);
+  }
   io.px[env] = (int16_t)px;
   io.py[env] = (int16_t)py;
   io.target[env] = target;
@@ -640,11 +657,7 @@ __global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
   const int N = io.N, S = io.S;
   const int NV = N >> 3;
   if (io.frozen && io.frozen[env]) {
-    if (li == 0) {
-      io.err[env] |= SWARM_ERR_STEP_WHEN_DONE;
-      io.done[env] = 1;
-      io.eaten[env] = -1;
-    }
+    if (li == 0) predator_frozen(io, env);
     return;
   }
   const size_t vbase = ((size_t)env * (size_t)N) >> 3;
@@ -665,8 +678,13 @@ __global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
   }
   int tx = 0, ty = 0;
   if (!retarget) {
-    tx = io.xo[(size_t)env * N + target];
-    ty = io.yo[(size_t)env * N + target];
+    if (io.tcell) {                                            // coalesced over envs, no dependent random read
+      const unsigned tc = reinterpret_cast<const unsigned*>(io.tcell)[env];
+      tx = (int)(int16_t)(tc & 0xFFFFu); ty = (int)(int16_t)(tc >> 16);
+    } else {
+      tx = io.xo[(size_t)env * N + target];
+      ty = io.yo[(size_t)env * N + target];
+    }
   }
   const int ppx = px, ppy = py;
   if (retarget) {                                              // SDE:138-140
@@ -702,11 +720,7 @@ __global__ void __launch_bounds__(256) predator_block_kernel(const PredIO io) {
   const int NV = N >> 3;
   for (int env = blockIdx.x; env < io.E; env += gridDim.x) {
     if (io.frozen && io.frozen[env]) {                        // uniform per CTA
-      if (threadIdx.x == 0) {
-        io.err[env] |= SWARM_ERR_STEP_WHEN_DONE;
-        io.done[env] = 1;
-        io.eaten[env] = -1;
-      }
+      if (threadIdx.x == 0) predator_frozen(io, env);
       continue;
     }
     const size_t vbase = ((size_t)env * (size_t)N) >> 3;
@@ -745,11 +759,7 @@ __global__ void __launch_bounds__(256) predator_kernel(const PredIO io) {
   if (env >= io.E) return;
   const int N = io.N, S = io.S;
   if (io.frozen && io.frozen[env]) {
-    if (lane == 0) {
-      io.err[env] |= SWARM_ERR_STEP_WHEN_DONE;
-      io.done[env] = 1;
-      io.eaten[env] = -1;
-    }
+    if (lane == 0) predator_frozen(io, env);
     return;
   }
   const size_t base = (size_t)env * (size_t)N;
@@ -1257,10 +1267,18 @@ __global__ void __launch_bounds__(256) finalize_agents_kernel(const StepParams p
           make_float4((float)a_att, (float)a_rep, (float)a_ali, (float)(a_rep + a_att + a_ali));
     }
     if (p.agent_counts) reinterpret_cast<int2*>(p.agent_counts)[i] = make_int2(rep_i, att_i);
+    if (p.agent_terms) reinterpret_cast<uint2*>(p.agent_terms)[i] = pack_terms(rep_i, att_i, vis, P, Q);
   } else if (live && !frozen) {                             // terminated this step (SDE:321-327)
     if (p.agent_reward)
       reinterpret_cast<float4*>(p.agent_reward)[i] = make_float4(0.f, 0.f, 0.f, k == p.eaten[env] ? p.eat : 0.f);
     if (p.agent_counts) reinterpret_cast<int2*>(p.agent_counts)[i] = make_int2(0, 0);
+    if (p.agent_terms) reinterpret_cast<uint2*>(p.agent_terms)[i] = make_uint2(0u, 0u);
+  }
+  if (frozen) {                                             // SDE:233-234: defined (zero) per-agent outputs
+    if (p.agent_reward) reinterpret_cast<float4*>(p.agent_reward)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.agent_counts) reinterpret_cast<int2*>(p.agent_counts)[i] = make_int2(0, 0);
+    if (p.agent_terms) reinterpret_cast<uint2*>(p.agent_terms)[i] = make_uint2(0u, 0u);
+    if (p.eff_action) p.eff_action[i] = 8;
   }
   if (live && !frozen) {                                    // commit (SDE:260) + terminal copy
     const int16_t vx = sc.nx[i], vy = sc.ny[i];
@@ -1309,23 +1327,9 @@ __global__ void __launch_bounds__(128) finalize_env_kernel(const StepParams p, c
   p.counts[2 * env] = g_rep;
   p.counts[2 * env + 1] = g_att;
   if (done && !p.auto_reset) p.frozen[env] = 1;
-  if (p.track_stats) {
-    const unsigned len = p.ep_len[env] + 1u;
-    float4 ret = reinterpret_cast<float4*>(p.ep_ret)[env];
-    ret.x += (float)r_surv; ret.y += (float)r_att; ret.z += (float)r_rep; ret.w += (float)r_ali;
-    if (done) {
-      p.fin_count[env] += 1u;
-      p.fin_len[env] += len;
-      float4 f = reinterpret_cast<float4*>(p.fin_ret)[env];
-      f.x += ret.x; f.y += ret.y; f.z += ret.z; f.w += ret.w;
-      reinterpret_cast<float4*>(p.fin_ret)[env] = f;
-      p.ep_len[env] = 0u;
-      reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-      p.ep_len[env] = len;
-      reinterpret_cast<float4*>(p.ep_ret)[env] = ret;
-    }
-  }
+  if (p.track_stats)
+    episode_update(p, env, reinterpret_cast<const uint4*>(p.ep_rec)[env], done, (float)r_surv, (float)r_att, (float)r_rep,
+                   (float)r_ali);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1398,7 +1402,10 @@ __global__ void __launch_bounds__(1024) reset_kernel(const StepParams p, const S
     if (threadIdx.x == 0) {
       p.px[env] = (int16_t)px;
       p.py[env] = (int16_t)py;
-      p.target[env] = nn_pick(klo, khi, S);
+      const int tgt = nn_pick(klo, khi, S);
+      p.target[env] = tgt;
+      if (p.tcell)     // (another thread's stores, ordered by the block barriers of the reduction above)
+        reinterpret_cast<unsigned*>(p.tcell)[env] = pack2(*(volatile int16_t*)&x[tgt], *(volatile int16_t*)&y[tgt]);
       p.orient[env] = 0;
       if (mode == 0) {
         p.frozen[env] = 0;
@@ -1407,8 +1414,7 @@ __global__ void __launch_bounds__(1024) reset_kernel(const StepParams p, const S
         p.err[env] |= err;
       }
       if (p.track_stats && mode == 0) {
-        p.ep_len[env] = 0u;
-        reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<uint4*>(p.ep_rec)[env] = make_uint4(0u, 0u, 0u, 0u);
         p.fin_count[env] = 0u;
         p.fin_len[env] = 0u;
         reinterpret_cast<float4*>(p.fin_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1572,7 +1578,10 @@ __global__ void __launch_bounds__(1024) reset_bitmap_kernel(const StepParams p, 
     if (threadIdx.x == 0) {
       p.px[env] = (int16_t)px;
       p.py[env] = (int16_t)py;
-      p.target[env] = nn_pick(klo, khi, S);
+      const int tgt = nn_pick(klo, khi, S);
+      p.target[env] = tgt;
+      if (p.tcell)     // (another thread's stores, ordered by the block barriers of the reduction above)
+        reinterpret_cast<unsigned*>(p.tcell)[env] = pack2(*(volatile int16_t*)&x[tgt], *(volatile int16_t*)&y[tgt]);
       p.orient[env] = 0;
       if (mode == 0) {
         p.frozen[env] = 0;
@@ -1581,8 +1590,7 @@ __global__ void __launch_bounds__(1024) reset_bitmap_kernel(const StepParams p, 
         p.err[env] |= err;
       }
       if (p.track_stats && mode == 0) {
-        p.ep_len[env] = 0u;
-        reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<uint4*>(p.ep_rec)[env] = make_uint4(0u, 0u, 0u, 0u);
         p.fin_count[env] = 0u;
         p.fin_len[env] = 0u;
         reinterpret_cast<float4*>(p.fin_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);

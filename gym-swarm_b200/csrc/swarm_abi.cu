@@ -40,15 +40,31 @@ struct Ctx {
   int coll_bm_words = 0;      // > 0: collide_bitmap_kernel (per-env occupancy bitmap fits in shared memory)
   int coll_smem_bytes = 0;
   BoxPlan box{};              // sub-quadratic reward counts inside collide_bitmap_kernel (steps without vf_size)
-  BoxPlan fused_box{};        // the same plan for the fused lane-group kernels (per-env bitmap in shared memory)
-  // stats
-  double* d_stats = nullptr;
+  // statistics: STAT_SLOTS results in flight (device slot + pinned host slot + completion event each); the reduction
+  // runs on the caller's stream, the all-reduce and the copy to the host on the handle's side stream
+  static constexpr int STAT_SLOTS = 4;
+  double* d_stats = nullptr;        // [STAT_SLOTS][8]
+  double* d_partial = nullptr;      // [stat_grid][8] per-CTA partial sums
+  double* h_stats = nullptr;        // pinned [STAT_SLOTS][8]
+  int stat_grid = 1;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_reduced[STAT_SLOTS] = {};
+  cudaEvent_t ev_done[STAT_SLOTS] = {};
+  unsigned long long stat_begun = 0, stat_ended = 0;
   // nccl
   void* nccl_lib = nullptr;
   void* nccl_comm = nullptr;
+  bool nccl_owned = false;
   ~Ctx() {                     // owns only the library scratch; state / tapes / outputs belong to the caller
     if (scratch_block) cudaFree(scratch_block);
     if (d_stats) cudaFree(d_stats);
+    if (d_partial) cudaFree(d_partial);
+    if (h_stats) cudaFreeHost(h_stats);
+    for (int q = 0; q < STAT_SLOTS; ++q) {
+      if (ev_reduced[q]) cudaEventDestroy(ev_reduced[q]);
+      if (ev_done[q]) cudaEventDestroy(ev_done[q]);
+    }
+    if (side) cudaStreamDestroy(side);
   }
 };
 
@@ -67,7 +83,7 @@ static int fail(Ctx* c, int code, const std::string& msg) {
 
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-static void fill_thresholds(StepParams& p, int N, int S, int att, int rep) {
+static void fill_thresholds(StepParams& p, int N, int S, int att, int rep, unsigned flags = 0u) {
   p.N = N;
   p.S = S;
   p.t_rep = clampi(rep, 0, S);
@@ -81,7 +97,7 @@ static void fill_thresholds(StepParams& p, int N, int S, int att, int rep) {
   // far thresholds beyond half the grid: a pair at distance >= t needs both agents in opposite border bands
   p.far_border = (2 * p.t_repf > S && 2 * p.t_attf > S) ? 1 : 0;
   p.far_band = S - std::min(p.t_repf, p.t_attf);
-  if (getenv("SWARM_NO_FAR_BORDER")) p.far_border = 0;     // kernel A/B experiments / tests of the 4-threshold sweep
+  if (flags & SWARM_FLAG_NO_FAR_BORDER) p.far_border = 0;  // kernel A/B runs / tests of the 4-threshold sweep
 }
 
 // Box-count plan: per threshold the cheaper of the direct box and the complement (cost in bitmap word reads per
@@ -120,19 +136,21 @@ static StepParams base_params(const Ctx* c) {
   memset(&p, 0, sizeof(p));
   const swarm_config& g = c->cfg;
   p.E = g.num_envs;
-  fill_thresholds(p, g.num_agents, g.grid_size, g.attraction_thresh, g.repulsion_thresh);
+  fill_thresholds(p, g.num_agents, g.grid_size, g.attraction_thresh, g.repulsion_thresh, g.flags);
   p.t_vf = -1;
+  p.env_offset = g.env_offset;
+  p.vf_dense = (g.flags & SWARM_FLAG_VF_DENSE) ? 1 : 0;
   p.w_att = p.w_rep = p.w_ali = 1.0;
   p.eat = g.predator_eat_rew;
   p.K = g.slab_len; p.PL = g.place_len; p.KP = g.pred_attempts; p.R = g.reset_slots;
   p.auto_reset = g.auto_reset; p.track_stats = g.track_stats;
   p.bitmap_words = c->bitmap_words;
-  p.box = c->fused_box;
   p.one = 1;
   const swarm_state& s = c->st;
   p.x = s.x; p.y = s.y; p.px = s.px; p.py = s.py; p.target = s.target; p.orient = s.pred_orient;
   p.frozen = s.frozen; p.err = s.err; p.reset_count = s.reset_count;
-  p.ep_len = s.ep_len; p.ep_ret = s.ep_ret; p.fin_count = s.fin_count; p.fin_len = s.fin_len; p.fin_ret = s.fin_ret;
+  p.tcell = c->fused ? nullptr : s.tcell;              // state of the staged path only
+  p.ep_rec = s.ep_rec; p.fin_count = s.fin_count; p.fin_len = s.fin_len; p.fin_ret = s.fin_ret;
   p.place = c->place; p.ptape = c->ptape;
   p.rst_seed_lo = (unsigned)(c->rst_seed & 0xFFFFFFFFull); p.rst_seed_hi = (unsigned)(c->rst_seed >> 32);
   return p;
@@ -171,12 +189,11 @@ static int staged_alloc(Ctx* c) {
         c->coll_smem_bytes = (int)(bytes + hist_bytes);
       }
       c->box = bp;
-      CUDA_TRY(c, cudaFuncSetAttribute(collide_bitmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       c->coll_smem_bytes));
-      CUDA_TRY(c, cudaFuncSetAttribute(reset_bitmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(words * 4 + (long long)COLL_HC * 8)));
-      CUDA_TRY(c, cudaFuncSetAttribute(boxcount_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(words * 4 + 2LL * S * 4)));
+      // per-function, per-device attribute shared by all handles: only ever raised (to the opt-in maximum), so that a
+      // later handle with a smaller grid cannot lower it under this one's launches
+      CUDA_TRY(c, smem_opt_in(collide_bitmap_kernel, c->coll_smem_bytes));
+      CUDA_TRY(c, smem_opt_in(reset_bitmap_kernel, (int)(words * 4 + (long long)COLL_HC * 8)));
+      CUDA_TRY(c, smem_opt_in(boxcount_kernel, (int)(words * 4 + 2LL * S * 4)));
     }
   }
   const size_t hs = (size_t)1 << log2hs;
@@ -234,22 +251,12 @@ static int pairwise_launch(const StepParams& p, const StagedScratch& sc, const i
   return 0;
 }
 
-// ---- statistics reduction ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) stats_reduce_kernel(int E, const uint32_t* __restrict__ fin_count,
-                                                            const uint32_t* __restrict__ fin_len,
-                                                            const float* __restrict__ fin_ret,
-                                                            const uint32_t* __restrict__ ep_len,
-                                                            double* __restrict__ out) {
-  __shared__ double sh[8][32];
-  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    const float4 r = reinterpret_cast<const float4*>(fin_ret)[e];
-    acc[0] += (double)fin_count[e];
-    acc[1] += (double)fin_len[e];
-    acc[3] += (double)r.x; acc[4] += (double)r.y; acc[5] += (double)r.z; acc[6] += (double)r.w;
-    acc[7] += (double)ep_len[e];
-  }
-  acc[2] = acc[3] + acc[4] + acc[5] + acc[6];
+// ---- statistics reduction: two stages, both in a fixed order (deterministic) ---------------------------
+// stage 1: CTA b sums the envs b*256*k .. of its contiguous slice into partial[b][8]; stage 2: one CTA adds the partials.
+constexpr int STAT_THREADS = 256;
+
+__device__ __forceinline__ void stats_block_sum(double (&acc)[8], double* __restrict__ out) {
+  __shared__ double sh[8][STAT_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -261,10 +268,43 @@ __global__ void __launch_bounds__(1024) stats_reduce_kernel(int E, const uint32_
   if (warp == 0) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      double v = lane < (int)(blockDim.x >> 5) ? sh[q][lane] : 0.0;
+      double v = lane < STAT_THREADS / 32 ? sh[q][lane] : 0.0;
       for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
       if (lane == 0) out[q] = v;
     }
+  }
+}
+
+__global__ void __launch_bounds__(STAT_THREADS) stats_partial_kernel(int E, int per_cta, const uint32_t* __restrict__ fin_count,
+                                                                     const uint32_t* __restrict__ fin_len,
+                                                                     const float* __restrict__ fin_ret,
+                                                                     const uint32_t* __restrict__ ep_rec,
+                                                                     double* __restrict__ partial) {
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int e0 = blockIdx.x * per_cta, e1 = min(E, e0 + per_cta);
+  for (int e = e0 + threadIdx.x; e < e1; e += STAT_THREADS) {
+    const float4 r = reinterpret_cast<const float4*>(fin_ret)[e];
+    acc[0] += (double)fin_count[e];
+    acc[1] += (double)fin_len[e];
+    acc[3] += (double)r.x; acc[4] += (double)r.y; acc[5] += (double)r.z; acc[6] += (double)r.w;
+    acc[7] += (double)ep_rec[4 * (size_t)e];
+  }
+  stats_block_sum(acc, partial + 8 * (size_t)blockIdx.x);
+}
+
+__global__ void __launch_bounds__(STAT_THREADS) stats_final_kernel(int parts, const double* __restrict__ partial,
+                                                                   double* __restrict__ out) {
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int b = threadIdx.x; b < parts; b += STAT_THREADS)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] += partial[8 * (size_t)b + q];
+  __shared__ double tot[8];
+  stats_block_sum(acc, tot);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tot[2] = tot[3] + tot[4] + tot[5] + tot[6];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) out[q] = tot[q];
   }
 }
 
@@ -349,8 +389,7 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
              (cfg->path == SWARM_PATH_AUTO && cfg->num_agents <= SWARM_FUSED_MAX_AGENTS);
   // thread per env: always for N <= 8; for 9..16 agents only when the batch is large enough to fill the GPU with one
   // thread per env (the lane-group kernel spreads a small batch over 8x more threads and has the shorter latency)
-  int big_min_envs = 65536;
-  if (const char* ev = getenv("SWARM_TINY16_MIN_ENVS")) big_min_envs = atoi(ev);   // tests / experiments
+  const int big_min_envs = cfg->tiny16_min_envs > 0 ? cfg->tiny16_min_envs : 65536;
   c->tiny = c->fused && cfg->path != SWARM_PATH_GROUP &&
             (cfg->num_agents <= TINY_N || (cfg->num_agents <= TINY_N_BIG && cfg->num_envs >= big_min_envs));
   c->tiny_n = cfg->num_agents <= TINY_N ? TINY_N : TINY_N_BIG;
@@ -359,24 +398,12 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
     const long long cells = (long long)cfg->grid_size * cfg->grid_size;
     const long long words = ((cells + 31) / 32 + 3) / 4 * 4;
     c->bitmap_words = (words <= 2048 && cfg->num_agents >= 16) ? (int)words : 0;
-    if (c->bitmap_words > 0 && !c->tiny) {
-      double cost = 0.0;
-      BoxPlan bp = make_box_plan(cfg->num_agents, cfg->grid_size, cfg->attraction_thresh, cfg->repulsion_thresh, cost);
-      // Measured on B200 at cfg3 (N = 128, S = 128, default thresholds), ms / step: ring sweep 0.275-0.278; box counts
-      // 0.42-0.45 (the far thresholds' corner rectangles are rare per agent but hit some lane of nearly every warp);
-      // even with the far thresholds stubbed out the single-sweep direct boxes alone gave 0.270 -- no better than the
-      // ring.  So for the lane-group kernels (N <= 256) the box path is OFF unless SWARM_FUSED_BOX=1 asks for it; it
-      // pays off from N ~ 1000 up, which is the staged path.
-      bp.enabled = 0;
-      (void)cost;
-      const char* force = getenv("SWARM_FUSED_BOX");          // kernel A/B experiments / tests
-      if (force && (force[0] == '0' || force[0] == '1')) bp.enabled = force[0] == '1';
-      c->fused_box = bp;
-    }
+    // (A box-count variant of the reward on this per-env bitmap was measured for the lane-group kernels in round 1:
+    // 0.42-0.45 ms / step at cfg3 against 0.275 for the ring sweep -- the shared-memory gathers of 32 lanes into random
+    // bitmap rows serialise on bank conflicts.  It pays off from N ~ 1000 up, which is the staged path; removed here.)
     char buf[64];
     if (c->tiny) snprintf(buf, sizeof(buf), "tiny<%d> (vf: fused<%d,%d>)", c->tiny_n, c->lpe, c->apl);
-    else snprintf(buf, sizeof(buf), "fused<%d,%d>%s%s", c->lpe, c->apl, c->bitmap_words ? "+bitmap" : "",
-                  c->fused_box.enabled ? "+box" : "");
+    else snprintf(buf, sizeof(buf), "fused<%d,%d>%s", c->lpe, c->apl, c->bitmap_words ? "+bitmap" : "");
     c->path_name = buf;
   } else {
     c->path_name = "staged";   // refined after staged_alloc (box-count plan)
@@ -397,8 +424,23 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
       return fail(nullptr, SWARM_E_CUDA, m);
     }
   }
-  cudaError_t e = cudaMalloc(&c->d_stats, 8 * sizeof(double));
-  if (e != cudaSuccess) { delete c; return fail(nullptr, SWARM_E_CUDA, "cudaMalloc stats"); }
+  {
+    // statistics plumbing: multi-CTA partial sums (a contiguous slice of envs per CTA), result slots, side stream
+    c->stat_grid = std::max(1, std::min(c->num_sms * 4, (cfg->num_envs + STAT_THREADS - 1) / STAT_THREADS));
+    cudaError_t e = cudaMalloc(&c->d_stats, Ctx::STAT_SLOTS * 8 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_partial, (size_t)c->stat_grid * 8 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_stats, Ctx::STAT_SLOTS * 8 * sizeof(double));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    for (int q = 0; q < Ctx::STAT_SLOTS && e == cudaSuccess; ++q) {
+      e = cudaEventCreateWithFlags(&c->ev_reduced[q], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[q], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+      const std::string m = std::string("swarm_create: statistics buffers: ") + cudaGetErrorString(e);
+      delete c;
+      return fail(nullptr, SWARM_E_CUDA, m);
+    }
+  }
   *out = reinterpret_cast<swarm_handle>(c);
   return SWARM_OK;
 }
@@ -407,7 +449,8 @@ int swarm_destroy(swarm_handle h) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
   if (!c) return SWARM_OK;
   cudaSetDevice(c->cfg.device);
-  if (c->nccl_comm && c->nccl_lib) {
+  if (c->side) cudaStreamSynchronize(c->side);
+  if (c->nccl_comm && c->nccl_lib && c->nccl_owned) {
     typedef int (*destroy_t)(void*);
     destroy_t f = (destroy_t)dlsym(c->nccl_lib, "ncclCommDestroy");
     if (f) f(c->nccl_comm);
@@ -422,10 +465,11 @@ int swarm_bind_state(swarm_handle h, const swarm_state* st) {
   if (!st->x || !st->y || !st->px || !st->py || !st->target || !st->pred_orient || !st->frozen || !st->err ||
       !st->reset_count)
     return fail(c, SWARM_E_INVALID, "swarm_bind_state: a required state pointer is null");
-  if (c->cfg.track_stats && (!st->ep_len || !st->ep_ret || !st->fin_count || !st->fin_len || !st->fin_ret))
+  if (c->cfg.track_stats && (!st->ep_rec || !st->fin_count || !st->fin_len || !st->fin_ret))
     return fail(c, SWARM_E_INVALID, "swarm_bind_state: track_stats needs the statistics pointers");
-  if (((uintptr_t)st->x | (uintptr_t)st->y) & 15)
-    return fail(c, SWARM_E_INVALID, "swarm_bind_state: x / y must be 16-byte aligned");
+  if (((uintptr_t)st->x | (uintptr_t)st->y | (uintptr_t)st->ep_rec | (uintptr_t)st->fin_ret) & 15)
+    return fail(c, SWARM_E_INVALID, "swarm_bind_state: x / y / ep_rec / fin_ret must be 16-byte aligned");
+  if ((uintptr_t)st->tcell & 3) return fail(c, SWARM_E_INVALID, "swarm_bind_state: tcell must be 4-byte aligned");
   c->st = *st;
   c->has_state = true;
   return SWARM_OK;
@@ -518,6 +562,10 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
   p.pred_prev = out->pred_prev; p.pred_next = out->pred_next; p.step_orient = out->step_orient;
   p.step_target = out->step_target; p.consumed = out->consumed; p.term_x = out->term_x; p.term_y = out->term_y;
   p.agent_reward = out->agent_reward; p.agent_counts = out->agent_counts; p.eff_action = out->eff_action;
+  p.agent_terms = out->agent_terms;
+  if (out->agent_terms && p.N > 4096)
+    return fail(c, SWARM_E_INVALID, "swarm_step: agent_terms (int16) needs num_agents <= 4096");
+  if ((uintptr_t)out->agent_terms & 15) return fail(c, SWARM_E_INVALID, "swarm_step: agent_terms must be 16-byte aligned");
   const bool vf = p.t_vf >= 0;
   c->launches = 0;
   if (c->tiny && !vf) {
@@ -560,6 +608,7 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     io.E = p.E; io.N = p.N; io.S = p.S; io.xo = p.x; io.yo = p.y; io.xn = sc.nx; io.yn = sc.ny;
     io.retarget = p.retarget; io.frozen = p.frozen; io.px = p.px; io.py = p.py; io.target = p.target;
     io.rng_seed_lo = p.rng_seed_lo; io.rng_seed_hi = p.rng_seed_hi; io.rng_step = p.rng_step;
+    io.env_offset = p.env_offset; io.tcell = p.tcell;
     io.orient = p.orient; io.pred_prev = p.pred_prev; io.pred_next = p.pred_next; io.step_orient = p.step_orient;
     io.step_target = p.step_target; io.done = p.done; io.eaten = p.eaten; io.err = p.err;
     launch_predator(io, c->num_sms, s);
@@ -611,15 +660,15 @@ int swarm_move(int32_t E, int32_t N, int32_t S, const int16_t* x, const int16_t*
 int swarm_predator(int32_t E, int32_t N, int32_t S, const int16_t* x_old, const int16_t* y_old,
                    const int16_t* x_new, const int16_t* y_new, const uint8_t* retarget, int16_t* px, int16_t* py,
                    int32_t* target, uint8_t* pred_orient, int16_t* pred_prev, uint8_t* done, int32_t* eaten,
-                   void* stream) {
+                   int16_t* tcell, void* stream) {
   if (E < 1 || N < 1 || S < 2 || !x_old || !y_old || !x_new || !y_new || !retarget || !px || !py || !target ||
-      !pred_orient || !done || !eaten)
+      !pred_orient || !done || !eaten || ((uintptr_t)tcell & 3))
     return fail(nullptr, SWARM_E_INVALID, "swarm_predator: bad argument");
   PredIO io;
   memset(&io, 0, sizeof(io));
   io.E = E; io.N = N; io.S = S; io.xo = x_old; io.yo = y_old; io.xn = x_new; io.yn = y_new;
   io.retarget = retarget; io.px = px; io.py = py; io.target = target; io.orient = pred_orient;
-  io.pred_prev = pred_prev; io.done = done; io.eaten = eaten;
+  io.pred_prev = pred_prev; io.done = done; io.eaten = eaten; io.tcell = tcell;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -628,10 +677,26 @@ int swarm_predator(int32_t E, int32_t N, int32_t S, const int16_t* x_old, const 
   return SWARM_OK;
 }
 
+static void pairwise_scratch_layout(int E, int N, size_t& b_pairw, size_t& b_pc) {
+  b_pairw = align_up((size_t)E * ((N + 1) / 2) * 16, 256);
+  b_pc = align_up((size_t)E * N * 32 + 64, 256);
+}
+
+uint64_t swarm_pairwise_scratch_bytes(int32_t E, int32_t N) {
+  if (E < 1 || N < 1) return 0;
+  size_t b_pairw, b_pc;
+  pairwise_scratch_layout(E, N, b_pairw, b_pc);
+  return (uint64_t)(b_pairw + b_pc + 256);
+}
+
 int swarm_pairwise(int32_t E, int32_t N, int32_t S, int32_t attraction_thresh, int32_t repulsion_thresh,
-                   const int16_t* x, const int16_t* y, const uint8_t* skip, int32_t* out_counts, void* stream) {
+                   const int16_t* x, const int16_t* y, const uint8_t* skip, int32_t* out_counts, void* scratch,
+                   uint64_t scratch_bytes, void* stream) {
   if (E < 1 || N < 2 || N > SWARM_MAX_AGENTS || S < 2 || S > SWARM_MAX_GRID || !x || !y || !out_counts)
     return fail(nullptr, SWARM_E_INVALID, "swarm_pairwise: bad argument");
+  if (!scratch || ((uintptr_t)scratch & 255) || scratch_bytes < swarm_pairwise_scratch_bytes(E, N))
+    return fail(nullptr, SWARM_E_INVALID, "swarm_pairwise: scratch must be a 256-byte aligned device block of at least "
+                                          "swarm_pairwise_scratch_bytes(E, N) bytes");
   cudaStream_t s = (cudaStream_t)stream;
   StepParams p;
   memset(&p, 0, sizeof(p));
@@ -641,25 +706,11 @@ int swarm_pairwise(int32_t E, int32_t N, int32_t S, int32_t attraction_thresh, i
   StagedScratch sc;
   memset(&sc, 0, sizeof(sc));
   sc.NW = (N + 1) / 2;
-  // scratch of the standalone entry point: one block per device, grown on demand and kept (a stream-ordered
-  // allocation per call made every other launch wait on the pool); calls on the same device must not overlap
-  static void* g_block[64] = {nullptr};
-  static size_t g_bytes[64] = {0};
-  int devi = 0;
-  CUDA_TRY(nullptr, cudaGetDevice(&devi));
-  if (devi < 0 || devi >= 64) return fail(nullptr, SWARM_E_INVALID, "swarm_pairwise: device ordinal out of range");
-  const size_t b_pairw = align_up((size_t)E * sc.NW * 16, 256), b_pc = align_up((size_t)E * N * 32 + 64, 256);
-  if (g_bytes[devi] < b_pairw + b_pc + 256) {
-    CUDA_TRY(nullptr, cudaDeviceSynchronize());
-    if (g_block[devi]) cudaFree(g_block[devi]);
-    g_block[devi] = nullptr; g_bytes[devi] = 0;
-    CUDA_TRY(nullptr, cudaMalloc(&g_block[devi], b_pairw + b_pc + 256));
-    g_bytes[devi] = b_pairw + b_pc + 256;
-  }
-  void* block = g_block[devi];
-  sc.pairw = (uint4*)block;
-  sc.pcounts = (unsigned*)((char*)block + b_pairw);
-  sc.counter = (unsigned*)((char*)block + b_pairw + b_pc);
+  size_t b_pairw, b_pc;                       // caller-owned scratch: calls with different blocks may overlap freely
+  pairwise_scratch_layout(E, N, b_pairw, b_pc);
+  sc.pairw = (uint4*)scratch;
+  sc.pcounts = (unsigned*)((char*)scratch + b_pairw);
+  sc.counter = (unsigned*)((char*)scratch + b_pairw + b_pc);
   const long long words = (long long)E * sc.NW;
   pairprep_kernel<<<(int)((words + 255) / 256), 256, 0, s>>>(E, N, S, sc.NW, x, y, nullptr, sc.pairw, nullptr,
                                                             sc.pcounts, sc.counter, nullptr);
@@ -683,11 +734,13 @@ int swarm_observe_vf(int32_t E, int32_t N, int32_t S, int32_t vf, const int16_t*
   const bool bitmap = words * 4 <= 160 * 1024;                       // the env's occupancy bitmap fits in shared memory
   const int bm_words = bitmap ? (int)words : 0;
   const int smem = ((N + bm_words) * 4 + 15) / 16 * 16 + OBS_CHUNK * W * W + 16;
-  static int opted[2] = {0, 0};
-  if (smem > 48 * 1024 && opted[bitmap] < smem) {
-    if (bitmap) CUDA_TRY(nullptr, cudaFuncSetAttribute(observe_vf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    else CUDA_TRY(nullptr, cudaFuncSetAttribute(observe_vf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    opted[bitmap] = smem;
+  static bool opted[64][2] = {};                                   // per device (the attribute is per function AND device)
+  int devi = 0;
+  CUDA_TRY(nullptr, cudaGetDevice(&devi));
+  if (smem > 48 * 1024 && (devi < 0 || devi >= 64 || !opted[devi][bitmap])) {
+    if (bitmap) CUDA_TRY(nullptr, smem_opt_in(observe_vf_kernel<true>, smem));
+    else CUDA_TRY(nullptr, smem_opt_in(observe_vf_kernel<false>, smem));
+    if (devi >= 0 && devi < 64) opted[devi][bitmap] = true;
   }
   const long long grid = (long long)E * ((N + OBS_CHUNK - 1) / OBS_CHUNK);
   if (grid > 0x7FFFFFFFLL) return fail(nullptr, SWARM_E_INVALID, "swarm_observe_vf: too many agent chunks");
@@ -699,18 +752,77 @@ int swarm_observe_vf(int32_t E, int32_t N, int32_t S, int32_t vf, const int16_t*
 
 // ---- statistics -----------------------------------------------------------------------------------------
 
-int swarm_stats_read(swarm_handle h, double out[8], void* stream) {
+typedef int (*nccl_allreduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+
+int swarm_stats_begin(swarm_handle h, int32_t allreduce, void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
-  if (!c || !out) return fail(c, SWARM_E_INVALID, "swarm_stats_read: null argument");
-  if (!c->cfg.track_stats || !c->has_state) return fail(c, SWARM_E_STATE, "swarm_stats_read: track_stats is off");
+  if (!c) return fail(c, SWARM_E_INVALID, "swarm_stats_begin: null handle");
+  if (!c->cfg.track_stats || !c->has_state) return fail(c, SWARM_E_STATE, "swarm_stats_begin: track_stats is off");
+  if (allreduce && !c->nccl_comm) return fail(c, SWARM_E_STATE, "swarm_stats_begin: call swarm_nccl_init / swarm_nccl_adopt first");
+  if (c->stat_begun - c->stat_ended >= (unsigned long long)Ctx::STAT_SLOTS)
+    return fail(c, SWARM_E_STATE, "swarm_stats_begin: too many results in flight, collect one with swarm_stats_end");
   cudaStream_t s = (cudaStream_t)stream;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  stats_reduce_kernel<<<1, 1024, 0, s>>>(c->cfg.num_envs, c->st.fin_count, c->st.fin_len, c->st.fin_ret, c->st.ep_len,
-                                         c->d_stats);
+  const int slot = (int)(c->stat_begun % Ctx::STAT_SLOTS);
+  double* d = c->d_stats + 8 * slot;
+  const int E = c->cfg.num_envs;
+  const int per_cta = (E + c->stat_grid - 1) / c->stat_grid;
+  // the reduction is ordered with the steps on the caller's stream: it sees exactly the steps enqueued before it
+  stats_partial_kernel<<<c->stat_grid, STAT_THREADS, 0, s>>>(E, per_cta, c->st.fin_count, c->st.fin_len, c->st.fin_ret,
+                                                            c->st.ep_rec, c->d_partial);
+  stats_final_kernel<<<1, STAT_THREADS, 0, s>>>(c->stat_grid, c->d_partial, d);
   CUDA_TRY(c, cudaGetLastError());
-  CUDA_TRY(c, cudaMemcpyAsync(out, c->d_stats, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(c, cudaStreamSynchronize(s));
+  CUDA_TRY(c, cudaEventRecord(c->ev_reduced[slot], s));
+  // everything else happens behind that event on the side stream: the step loop never waits for it
+  CUDA_TRY(c, cudaStreamWaitEvent(c->side, c->ev_reduced[slot], 0));
+  if (allreduce) {
+    nccl_allreduce_t f = (nccl_allreduce_t)dlsym(c->nccl_lib, "ncclAllReduce");
+    if (!f) return fail(c, SWARM_E_NCCL, "ncclAllReduce missing");
+    const int rc = f(d, d, 8, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl_comm, c->side);   // on the device buffer
+    if (rc != 0) return fail(c, SWARM_E_NCCL, "ncclAllReduce failed, code " + std::to_string(rc));
+  }
+  CUDA_TRY(c, cudaMemcpyAsync(c->h_stats + 8 * slot, d, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->side));
+  CUDA_TRY(c, cudaEventRecord(c->ev_done[slot], c->side));
+  // d_partial is reused by the next begin on the caller's stream: stream order already serialises the two reductions
+  c->stat_begun += 1;
   return SWARM_OK;
+}
+
+int swarm_stats_end(swarm_handle h, double out[8], int32_t wait) {
+  Ctx* c = reinterpret_cast<Ctx*>(h);
+  if (!c || !out) return fail(c, SWARM_E_INVALID, "swarm_stats_end: null argument");
+  if (c->stat_begun == c->stat_ended) return fail(c, SWARM_E_STATE, "swarm_stats_end: no swarm_stats_begin outstanding");
+  const int slot = (int)(c->stat_ended % Ctx::STAT_SLOTS);
+  if (wait) {
+    CUDA_TRY(c, cudaEventSynchronize(c->ev_done[slot]));
+  } else {
+    const cudaError_t q = cudaEventQuery(c->ev_done[slot]);
+    if (q == cudaErrorNotReady) return SWARM_E_NOT_READY;
+    if (q != cudaSuccess) return fail(c, SWARM_E_CUDA, std::string("swarm_stats_end: ") + cudaGetErrorString(q));
+  }
+  memcpy(out, c->h_stats + 8 * slot, 8 * sizeof(double));
+  c->stat_ended += 1;
+  return SWARM_OK;
+}
+
+static int stats_sync(Ctx* c, double out[8], int allreduce, void* stream, const char* who) {
+  if (!c || !out) return fail(c, SWARM_E_INVALID, std::string(who) + ": null argument");
+  double tmp[8];
+  while (c->stat_begun != c->stat_ended) {         // drain older asynchronous results first (kept in order)
+    const int rc = swarm_stats_end(reinterpret_cast<swarm_handle>(c), tmp, 1);
+    if (rc != SWARM_OK) return rc;
+  }
+  const int rc = swarm_stats_begin(reinterpret_cast<swarm_handle>(c), allreduce, stream);
+  if (rc != SWARM_OK) return rc;
+  return swarm_stats_end(reinterpret_cast<swarm_handle>(c), out, 1);
+}
+
+int swarm_stats_read(swarm_handle h, double out[8], void* stream) {
+  return stats_sync(reinterpret_cast<Ctx*>(h), out, 0, stream, "swarm_stats_read");
+}
+
+int swarm_stats_allreduce(swarm_handle h, double out[8], void* stream) {
+  return stats_sync(reinterpret_cast<Ctx*>(h), out, 1, stream, "swarm_stats_allreduce");
 }
 
 static void* nccl_open() {
@@ -742,23 +854,18 @@ int swarm_nccl_init(swarm_handle h, const uint8_t id[128], int32_t nranks, int32
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   const int rc = f(&c->nccl_comm, nranks, u, rank);
   if (rc != 0) return fail(c, SWARM_E_NCCL, "ncclCommInitRank failed, code " + std::to_string(rc));
+  c->nccl_owned = true;
   return SWARM_OK;
 }
 
-int swarm_stats_allreduce(swarm_handle h, double inout[8], void* stream) {
+int swarm_nccl_adopt(swarm_handle h, void* comm) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
-  if (!c || !inout) return fail(c, SWARM_E_INVALID, "swarm_stats_allreduce: null argument");
-  if (!c->nccl_comm) return fail(c, SWARM_E_STATE, "swarm_stats_allreduce: call swarm_nccl_init first");
-  typedef int (*ar_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
-  ar_t f = (ar_t)dlsym(c->nccl_lib, "ncclAllReduce");
-  if (!f) return fail(c, SWARM_E_NCCL, "ncclAllReduce missing");
-  cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  CUDA_TRY(c, cudaMemcpyAsync(c->d_stats, inout, 8 * sizeof(double), cudaMemcpyHostToDevice, s));
-  const int rc = f(c->d_stats, c->d_stats, 8, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl_comm, s);
-  if (rc != 0) return fail(c, SWARM_E_NCCL, "ncclAllReduce failed, code " + std::to_string(rc));
-  CUDA_TRY(c, cudaMemcpyAsync(inout, c->d_stats, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(c, cudaStreamSynchronize(s));
+  if (!c || !comm) return fail(c, SWARM_E_INVALID, "swarm_nccl_adopt: null argument");
+  if (c->nccl_comm) return fail(c, SWARM_E_STATE, "swarm_nccl_adopt: the handle already has a communicator");
+  c->nccl_lib = nccl_open();
+  if (!c->nccl_lib) return fail(c, SWARM_E_NCCL, "libnccl.so.2 not found");
+  c->nccl_comm = comm;
+  c->nccl_owned = false;
   return SWARM_OK;
 }
 

@@ -29,7 +29,7 @@ struct BoxPlan {
   int mode[4];       // for t_rep, t_att, t_repf, t_attf
   int t[4];
   int fast_rmax;     // >= 0: word-aligned rows (S % 32 == 0) and every BOX_DIRECT radius t-1 <= fast_rmax <= 15:
-                     // the fused kernel counts all direct thresholds in ONE branch-free sweep of 2*fast_rmax+1 rows
+                     // all direct thresholds of an agent are counted in ONE branch-free sweep of 2*fast_rmax+1 rows
                      // (32-bit window per row by funnel shift); -1: generic box_count per threshold
 };
 
@@ -56,15 +56,17 @@ struct StepParams {
   unsigned rng_seed_lo, rng_seed_hi;   // step streams (retarget, slab): counter (env, rng_step, block, 1)
   unsigned rng_step;
   unsigned rst_seed_lo, rst_seed_hi;   // reset streams (place: stream 2, ptape: stream 3): counter (env, reset index, block, stream)
-  BoxPlan box;       // fused kernels: box-count reward path (needs the per-env bitmap, bitmap_words > 0)
+  unsigned env_offset;                 // added to the env index in every Philox counter (swarm_config.env_offset)
   int one;           // runtime 1: `v * one + acc` compiles to IMAD (FMA pipe) instead of IADD3 (ALU pipe)
+  int vf_dense;      // SWARM_FLAG_VF_DENSE
   // state
   int16_t *x, *y, *px, *py;
   int32_t* target;
   uint8_t *orient, *frozen;
   uint32_t *err, *reset_count;
-  uint32_t *ep_len, *fin_count, *fin_len;
-  float *ep_ret, *fin_ret;
+  int16_t* tcell;                      // [E,2] cell of the predator's target (may be NULL)
+  uint32_t *ep_rec, *fin_count, *fin_len;   // ep_rec [E,4]: {length, f32 bits of attraction / repulsion / alignment}
+  float* fin_ret;
   // tapes
   const int16_t *place, *ptape;
   const uint8_t *actions, *retarget, *slab;
@@ -80,6 +82,7 @@ struct StepParams {
   float* agent_reward;
   int32_t* agent_counts;
   uint8_t* eff_action;
+  int16_t* agent_terms;   // [E,N,4] (rew_rep_i, rew_attr_i, U_i = 2 vis - P, Q_i)
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -192,6 +195,10 @@ struct AgentTerms {
   int att_i;    // rew_attr_i =   sum A1[i,:] + sum A2[i,:]          SDE:373
   double una;   // sum_j unalign[i,j]                                SDE:374
 };
+// compact per-agent credit (swarm_step_out.agent_terms): una = 0.25 * U - (sqrt2/4) * Q with U = 2 vis - P
+__device__ __forceinline__ uint2 pack_terms(int rep_i, int att_i, int vis, int P, int Q) {
+  return make_uint2(pack2(rep_i, att_i), pack2(2 * vis - P, Q));
+}
 __device__ __forceinline__ AgentTerms agent_terms(const StepParams& p, int cR, int cA, int cRf, int cAf, int vis,
                                                   int P, int Q) {
   AgentTerms t;
@@ -278,6 +285,27 @@ __device__ __forceinline__ void box_direct_sweep(const BoxPlan& bp, const unsign
   }
 }
 
+// ---- episode statistics: one 16-byte running record per env (swarm_state.ep_rec), finished sums updated on done ------
+// Called by the single writer of the env.  rec = the record loaded at the top of the step (so that the load shares the
+// step's first DRAM round trip).  The survival term only exists on the terminal step (SDE:321-327).
+__device__ __forceinline__ void episode_update(const StepParams& p, int env, uint4 rec, bool done, float r_surv, float r_att,
+                                               float r_rep, float r_ali) {
+  const unsigned len = rec.x + 1u;
+  const float att = __uint_as_float(rec.y) + r_att, rep = __uint_as_float(rec.z) + r_rep, ali = __uint_as_float(rec.w) + r_ali;
+  uint4* __restrict__ out = reinterpret_cast<uint4*>(p.ep_rec) + env;
+  if (done) {                                    // fire-and-forget reductions: no read round trip
+    atomicAdd(&p.fin_count[env], 1u);
+    atomicAdd(&p.fin_len[env], len);
+    atomicAdd(&p.fin_ret[4 * env + 0], r_surv);
+    atomicAdd(&p.fin_ret[4 * env + 1], att);
+    atomicAdd(&p.fin_ret[4 * env + 2], rep);
+    atomicAdd(&p.fin_ret[4 * env + 3], ali);
+    *out = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    *out = make_uint4(len, __float_as_uint(att), __float_as_uint(rep), __float_as_uint(ali));
+  }
+}
+
 // ---- tape accessors: a bound tape (row pointer) or the in-kernel Philox stream -----------------------------------
 // The Philox paths are separate NON-INLINED functions: inlined, their ~60 instructions and live registers were paid by
 // every kernel even with bound tapes (tiny_step_kernel 96 -> 112 registers, 87 -> 99 us at cfg5).
@@ -299,11 +327,11 @@ static __device__ __noinline__ unsigned philox_pred(unsigned k0, unsigned k1, in
 
 __device__ __forceinline__ int tape_retarget(const StepParams& p, int env) {
   if (p.retarget) return p.retarget[env];
-  return philox_retarget(p.rng_seed_lo, p.rng_seed_hi, p.rng_step, env);
+  return philox_retarget(p.rng_seed_lo, p.rng_seed_hi, p.rng_step, env + (int)p.env_offset);
 }
 __device__ __forceinline__ int tape_slab(const StepParams& p, const uint8_t* __restrict__ row, int env, int d) {
   if (p.slab) return row[d] & 7;
-  return philox_slab(p.rng_seed_lo, p.rng_seed_hi, p.rng_step, env, d);
+  return philox_slab(p.rng_seed_lo, p.rng_seed_hi, p.rng_step, env + (int)p.env_offset, d);
 }
 __device__ __forceinline__ const int16_t* place_row(const StepParams& p, int env, unsigned rc) {
   return p.place ? p.place + ((size_t)(rc % (unsigned)p.R) * (size_t)p.E + (size_t)env) * (size_t)p.PL : nullptr;
@@ -313,12 +341,12 @@ __device__ __forceinline__ const int16_t* ptape_row(const StepParams& p, int env
 }
 __device__ __forceinline__ int tape_place(const StepParams& p, const int16_t* __restrict__ row, int env, unsigned rc, int i) {
   if (row) return row[i];
-  return philox_place(p.rst_seed_lo, p.rst_seed_hi, p.S, env, rc, i);
+  return philox_place(p.rst_seed_lo, p.rst_seed_hi, p.S, env + (int)p.env_offset, rc, i);
 }
 __device__ __forceinline__ void tape_pred(const StepParams& p, const int16_t* __restrict__ row, int env, unsigned rc, int a,
                                           int& px, int& py) {
   if (row) { px = row[2 * a]; py = row[2 * a + 1]; return; }
-  const unsigned v = philox_pred(p.rst_seed_lo, p.rst_seed_hi, p.S, env, rc, a);
+  const unsigned v = philox_pred(p.rst_seed_lo, p.rst_seed_hi, p.S, env + (int)p.env_offset, rc, a);
   px = (int)(v & 0xFFFFu); py = (int)(v >> 16);
 }
 

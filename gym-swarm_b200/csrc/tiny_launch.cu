@@ -6,7 +6,7 @@ namespace swarm {
 
 cudaError_t tiny_step_launch(int tiny_n, const StepParams& p, cudaStream_t s, int* launches) {
   const int grid = (p.E + TINY_THREADS - 1) / TINY_THREADS;
-  const bool agent_out = p.agent_reward || p.agent_counts;
+  const bool agent_out = p.agent_reward || p.agent_counts || p.agent_terms;
   if (tiny_n == TINY_N) {
     if (agent_out) tiny_step_kernel<TINY_N, true><<<grid, TINY_THREADS, 0, s>>>(p);
     else tiny_step_kernel<TINY_N, false><<<grid, TINY_THREADS, 0, s>>>(p);

@@ -130,14 +130,25 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   const int N = p.N, S = p.S;
   const size_t base = (size_t)env * (size_t)N;
 
-  if (p.frozen[env]) {                      // SDE:233-234: finished episode, auto-reset off
-    p.err[env] |= SWARM_ERR_STEP_WHEN_DONE;
+  if (p.frozen[env]) {                      // SDE:233-234: finished episode, auto-reset off: nothing moves, every output
+    p.err[env] |= SWARM_ERR_STEP_WHEN_DONE; // of the step is defined (zero reward, the predator where it stands)
     p.done[env] = 1;
     p.eaten[env] = -1;
     p.counts[2 * env] = 0; p.counts[2 * env + 1] = 0;
     p.consumed[env] = 0;
 #pragma unroll
     for (int q = 0; q < 5; ++q) p.reward[5 * env + q] = 0.f;
+    const unsigned pp = pack2(p.px[env], p.py[env]);
+    reinterpret_cast<unsigned*>(p.pred_prev)[env] = pp;
+    reinterpret_cast<unsigned*>(p.pred_next)[env] = pp;
+    p.step_orient[env] = p.orient[env];
+    p.step_target[env] = p.target[env];
+    for (int k = 0; k < N; ++k) {
+      if (AGENT_OUT && p.agent_reward) reinterpret_cast<float4*>(p.agent_reward)[base + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (AGENT_OUT && p.agent_counts) reinterpret_cast<int2*>(p.agent_counts)[base + k] = make_int2(0, 0);
+      if (AGENT_OUT && p.agent_terms) reinterpret_cast<uint2*>(p.agent_terms)[base + k] = make_uint2(0u, 0u);
+      if (p.eff_action) p.eff_action[base + k] = 8;
+    }
     return;
   }
 
@@ -172,9 +183,8 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   int target = p.target[env];
   const int retarget = tape_retarget(p, env);
   // everything else the step will read, issued now so that one DRAM round trip covers all of it
-  unsigned ep_len0 = 0u;
-  float4 ep_ret0 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.track_stats) { ep_len0 = p.ep_len[env]; ep_ret0 = reinterpret_cast<const float4*>(p.ep_ret)[env]; }
+  uint4 ep0 = make_uint4(0u, 0u, 0u, 0u);
+  if (p.track_stats) ep0 = reinterpret_cast<const uint4*>(p.ep_rec)[env];
   unsigned err = 0;
   {
     bool bad = false;
@@ -195,7 +205,7 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   int L = tiny_counts<TN>(key, c);
   // the first 8 re-draw actions of this env are fetched now (only by envs that collided) and consumed after the
   // predator has been computed, so the load's latency is hidden
-  const uint8_t* __restrict__ slab = p.slab + (size_t)env * (size_t)p.K;
+  const uint8_t* __restrict__ slab = p.slab ? p.slab + (size_t)env * (size_t)p.K : nullptr;
   unsigned long long slab8 = 0ull;
   const bool slab_vec = p.slab != nullptr && p.K >= 8 && (((uintptr_t)slab) & 7) == 0;
   if (L > 0 && slab_vec) {
@@ -303,6 +313,7 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
       s_P = 0; s_Q = 0;
       float4* __restrict__ ar = p.agent_reward ? reinterpret_cast<float4*>(p.agent_reward) + base : nullptr;
       int2* __restrict__ ac = p.agent_counts ? reinterpret_cast<int2*>(p.agent_counts) + base : nullptr;
+      uint2* __restrict__ at = p.agent_terms ? reinterpret_cast<uint2*>(p.agent_terms) + base : nullptr;
 #pragma unroll
       for (int k = 0; k < TN; ++k) {
         if (k < N) {
@@ -324,6 +335,7 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
             ar[k] = make_float4((float)a_att, (float)a_rep, (float)a_ali, (float)(a_rep + a_att + a_ali));
           }
           if (ac) ac[k] = make_int2(t.rep_i, t.att_i);
+          if (at) at[k] = pack_terms(t.rep_i, t.att_i, N - 1, P, Q);
         }
       }
     } else {
@@ -370,6 +382,12 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
       for (int k = 0; k < TN; ++k)
         if (k < N) ac[k] = make_int2(0, 0);
     }
+    if (AGENT_OUT && p.agent_terms) {
+      uint2* __restrict__ at = reinterpret_cast<uint2*>(p.agent_terms) + base;
+#pragma unroll
+      for (int k = 0; k < TN; ++k)
+        if (k < N) at[k] = make_uint2(0u, 0u);
+    }
   }
   if (p.eff_action) {
     if (N == TN) {
@@ -398,25 +416,7 @@ __global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_co
   p.step_orient[env] = (uint8_t)orient;
   p.step_target[env] = step_target;
   p.consumed[env] = cur;
-  if (p.track_stats) {
-    const unsigned len = ep_len0 + 1u;
-    float4 ret = ep_ret0;
-    ret.x += (float)r_surv; ret.y += (float)r_att; ret.z += (float)r_rep; ret.w += (float)r_ali;
-    if (done) {
-      // single writer per env: the reductions are deterministic and need no read round trip
-      atomicAdd(&p.fin_count[env], 1u);
-      atomicAdd(&p.fin_len[env], len);
-      atomicAdd(&p.fin_ret[4 * env + 0], ret.x);
-      atomicAdd(&p.fin_ret[4 * env + 1], ret.y);
-      atomicAdd(&p.fin_ret[4 * env + 2], ret.z);
-      atomicAdd(&p.fin_ret[4 * env + 3], ret.w);
-      p.ep_len[env] = 0u;
-      reinterpret_cast<float4*>(p.ep_ret)[env] = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-      p.ep_len[env] = len;
-      reinterpret_cast<float4*>(p.ep_ret)[env] = ret;
-    }
-  }
+  if (p.track_stats) episode_update(p, env, ep0, done, (float)r_surv, (float)r_att, (float)r_rep, (float)r_ali);
 
   // ---- commit / auto-reset (SDE:260; reset semantics SDE:197-221) -----------------------------
   if (done) {

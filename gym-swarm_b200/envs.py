@@ -58,7 +58,8 @@ class BatchedSwarmEnv:
     def __init__(self, num_envs, num_agents=4, obs_space_size=20, attraction_thresh=5, repulsion_thresh=2,
                  predator_eat_rew=-10, device="cuda:0", auto_reset=True, track_stats=False, slab_len=None,
                  place_extra=None, pred_attempts=8, reset_slots=4, per_agent=True, debug_outputs=False,
-                 path="auto", seed=0, tape_chunk=16, device_tapes=False):
+                 path="auto", seed=0, tape_chunk=16, device_tapes=False, env_offset=0, flags=0, tiny16_min_envs=0,
+                 agent_terms=False):
         self.lib = _lib.load()                      # raises when the CUDA library is missing
         if not torch.cuda.is_available():
             raise _lib.SwarmLibraryError("no CUDA device: the swarm transition has no CPU fallback")
@@ -72,7 +73,12 @@ class BatchedSwarmEnv:
         self.PL = 2 * self.N + 2 * self.KR
         self.KP, self.R = int(pred_attempts), int(reset_slots)
         self.per_agent, self.debug_outputs = bool(per_agent), bool(debug_outputs)
-        self._rng = np.random.default_rng(seed)
+        self.with_terms = bool(agent_terms)             # compact per-agent credit int16[E,N,4] (swarm_step_out.agent_terms)
+        # env_offset = global index of this batch's env 0 (a shard's ``lo``): host tapes are drawn from a generator
+        # keyed by (seed, env_offset) so that shards do not replay each other, and the in-kernel Philox counters use
+        # env + env_offset so that a sharded device_tapes run draws exactly what the unsharded run draws
+        self.env_offset = int(env_offset)
+        self._rng = np.random.default_rng(seed if self.env_offset == 0 else [int(seed), self.env_offset])
         # device_tapes: every random draw of the transition is computed inside the kernels by Philox4x32-10 keyed with
         # ``seed`` (no tape memory, no host draws); tapes.philox_* materialise the identical values on the host
         self.device_tapes = bool(device_tapes)
@@ -89,38 +95,60 @@ class BatchedSwarmEnv:
             slab_len=self.K, place_len=self.PL, pred_attempts=self.KP, reset_slots=self.R,
             auto_reset=int(self.auto_reset), track_stats=int(self.track_stats),
             path={"auto": _lib.PATH_AUTO, "staged": _lib.PATH_STAGED, "fused": _lib.PATH_FUSED,
-                  "group": _lib.PATH_GROUP, "staged_pairwise": _lib.PATH_STAGED_PAIRWISE}[path])
+                  "group": _lib.PATH_GROUP, "staged_pairwise": _lib.PATH_STAGED_PAIRWISE}[path],
+            flags=int(flags), tiny16_min_envs=int(tiny16_min_envs), env_offset=self.env_offset & 0xFFFFFFFF, reserved=0)
         self._h = C.c_void_p()
         _lib.check(self.lib.swarm_create(C.byref(cfg), C.byref(self._h)))
         self.path_name = self.lib.swarm_path_name(self._h).decode()
 
         E, N, dev = self.E, self.N, self.device
+        # Everything a caller reads back per step -- the observation (x, y), done, the global reward and the per-agent
+        # credit -- is carved out of ONE contiguous device block ("result arena"), so that a host-side consumer fetches
+        # a step's results with a single device-to-host copy (fetch_host) instead of one per tensor.
+        arena_spec = [("x", (E, N), torch.int16), ("y", (E, N), torch.int16), ("done", (E,), torch.uint8),
+                      ("reward", (E, 5), torch.float32)]
+        if self.per_agent:
+            arena_spec.append(("agent_reward", (E, N, 4), torch.float32))
+        if self.with_terms:
+            arena_spec.append(("agent_terms", (E, N, 4), torch.int16))
+        self._arena_layout, off = [], 0
+        for name, shape, dt in arena_spec:
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            self._arena_layout.append((name, shape, dt, off, nbytes))
+            off = (off + nbytes + 255) // 256 * 256
+        self.arena = torch.zeros(off, dtype=torch.uint8, device=dev)
+        self.agent_reward = self.agent_terms = None
+        for name, shape, dt, o, nbytes in self._arena_layout:
+            setattr(self, name, self.arena[o:o + nbytes].view(dt).view(shape))
+        self._host_arena = None
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
-        # persistent state (SoA, int16 positions)
-        self.x, self.y = z((E, N), torch.int16), z((E, N), torch.int16)
+        # persistent state (SoA, int16 positions; x, y live in the arena)
         self.px, self.py = z((E,), torch.int16), z((E,), torch.int16)
         self.target = z((E,), torch.int32)
         self.pred_orient, self.frozen = z((E,), torch.uint8), z((E,), torch.uint8)
         self.err, self.reset_count = z((E,), torch.int32), z((E,), torch.int32)
+        # cell of the predator's target: state of the staged kernels only (include/swarm_abi.h, swarm_state.tcell)
+        self.tcell = z((E, 2), torch.int16) if self.path_name.startswith("staged") else None
         if self.track_stats:
-            self.ep_len, self.ep_ret = z((E,), torch.int32), z((E, 4), torch.float32)
+            # one 16-byte running-episode record per env: word 0 = length, words 1..3 = f32 bits of the running
+            # attraction / repulsion / alignment return (``ep_len`` / ``ep_ret`` below are views of it)
+            self.ep_rec = z((E, 4), torch.int32)
             self.fin_count, self.fin_len = z((E,), torch.int32), z((E,), torch.int32)
             self.fin_ret = z((E, 4), torch.float32)
         else:
-            self.ep_len = self.ep_ret = self.fin_count = self.fin_len = self.fin_ret = None
+            self.ep_rec = self.fin_count = self.fin_len = self.fin_ret = None
         st = _lib.State(x=_ptr(self.x), y=_ptr(self.y), px=_ptr(self.px), py=_ptr(self.py), target=_ptr(self.target),
                         pred_orient=_ptr(self.pred_orient), frozen=_ptr(self.frozen), err=_ptr(self.err),
-                        reset_count=_ptr(self.reset_count), ep_len=_ptr(self.ep_len), ep_ret=_ptr(self.ep_ret),
+                        reset_count=_ptr(self.reset_count), tcell=_ptr(self.tcell), ep_rec=_ptr(self.ep_rec),
                         fin_count=_ptr(self.fin_count), fin_len=_ptr(self.fin_len), fin_ret=_ptr(self.fin_ret))
         _lib.check(self.lib.swarm_bind_state(self._h, C.byref(st)), self._h)
-        # step outputs (owned by the env, overwritten by the next step)
-        self.done, self.eaten = z((E,), torch.uint8), z((E,), torch.int32)
-        self.reward, self.counts = z((E, 5), torch.float32), z((E, 2), torch.int32)
+        # remaining step outputs (owned by the env, overwritten by the next step)
+        self.eaten = z((E,), torch.int32)
+        self.counts = z((E, 2), torch.int32)
         self.pred_prev, self.pred_next = z((E, 2), torch.int16), z((E, 2), torch.int16)
         self.step_orient, self.step_target = z((E,), torch.uint8), z((E,), torch.int32)
         self.consumed = z((E,), torch.int32)
         self.term_x, self.term_y = z((E, N), torch.int16), z((E, N), torch.int16)
-        self.agent_reward = z((E, N, 4), torch.float32) if self.per_agent else None
         self.agent_counts = z((E, N, 2), torch.int32) if self.debug_outputs else None
         self.eff_action = z((E, N), torch.uint8) if self.debug_outputs else None
         self._out = _lib.StepOut(
@@ -128,7 +156,7 @@ class BatchedSwarmEnv:
             pred_prev=_ptr(self.pred_prev), pred_next=_ptr(self.pred_next), step_orient=_ptr(self.step_orient),
             step_target=_ptr(self.step_target), consumed=_ptr(self.consumed), term_x=_ptr(self.term_x),
             term_y=_ptr(self.term_y), agent_reward=_ptr(self.agent_reward), agent_counts=_ptr(self.agent_counts),
-            eff_action=_ptr(self.eff_action))
+            eff_action=_ptr(self.eff_action), agent_terms=_ptr(self.agent_terms))
         self._place = self._ptape = None
         self._nccl_ready = False
 
@@ -242,11 +270,84 @@ class BatchedSwarmEnv:
         self.step_index += 1
         self._keep = (actions, retarget, slab)      # keep inputs alive until the kernels ran
         _lib.check(self.lib.swarm_step(self._h, C.byref(sin), C.byref(self._out), self._stream()), self._h)
-        reward = {"global": self.reward, "agents": self.agent_reward, "counts": self.counts}
+        reward = {"global": self.reward, "agents": self.agent_reward, "counts": self.counts, "terms": self.agent_terms}
         info = {"predator_state": self.pred_prev, "predator_next_state": self.pred_next,
                 "predator_orientation": self.step_orient, "predator_target": self.step_target, "eaten": self.eaten,
                 "terminal_state": (self.term_x, self.term_y), "redraws": self.consumed, "errors": self.err}
         return (self.x, self.y), reward, self.done, info
+
+    # ---- host-side consumers: one packed copy per step ------------------------------------------------------
+    def fetch_host(self, sync=True):
+        """The step's results on the host with ONE device-to-host copy of the result arena into a pinned mirror
+        (allocated on first use, by the calling thread: bind the process to the GPU's NUMA node first --
+        ``sharding.bind_to_gpu_numa_node`` -- so that the pages are local to the GPU's PCIe root).  Returns
+        ``{"x", "y", "done", "reward"[, "agent_reward"][, "agent_terms"]}`` as CPU tensors viewing the mirror; they are
+        valid once the stream has been synchronised (``sync=True`` does that) and are overwritten by the next fetch."""
+        if self._host_arena is None:
+            self._host_arena = torch.empty(self.arena.numel(), dtype=torch.uint8).pin_memory()
+            self._host_views = {name: self._host_arena[o:o + nbytes].view(dt).view(shape)
+                                for name, shape, dt, o, nbytes in self._arena_layout}
+        self._host_arena.copy_(self.arena, non_blocking=True)          # a single cudaMemcpyAsync
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+        return self._host_views
+
+    def host_inputs(self, slot=0):
+        """Pinned host views ``{"actions" u8[E,N], "retarget" u8[E], "slab" u8[E,K]}`` of ONE packed input block (only
+        ``actions`` in device_tapes mode): fill them, then ``step_host(slot=...)`` moves the block with a single
+        host-to-device copy.  ``slot`` selects one of several independent blocks (a producer can fill the next block
+        while the previous step runs)."""
+        if getattr(self, "_in_host", None) is None:
+            spec = [("actions", (self.E, self.N))]
+            if not self.device_tapes:
+                spec += [("retarget", (self.E,)), ("slab", (self.E, self.K))]
+            self._in_layout, off = [], 0
+            for name, shape in spec:
+                nb = int(np.prod(shape))
+                self._in_layout.append((name, shape, off, nb))
+                off = (off + nb + 255) // 256 * 256
+            self._in_bytes = off
+            self._in_host, self._in_host_views = {}, {}
+            self._in_dev = torch.zeros(off, dtype=torch.uint8, device=self.device)
+            self._in_dev_views = {n: self._in_dev[o:o + nb].view(sh) for n, sh, o, nb in self._in_layout}
+        if slot not in self._in_host:
+            blk = torch.zeros(self._in_bytes, dtype=torch.uint8).pin_memory()
+            self._in_host[slot] = blk
+            self._in_host_views[slot] = {n: blk[o:o + nb].view(sh) for n, sh, o, nb in self._in_layout}
+        return self._in_host_views[slot]
+
+    def step_host(self, reward_type=None, slot=0):
+        """``step`` on the inputs currently in ``host_inputs(slot)``: one packed H2D copy + the step's kernels."""
+        self.host_inputs(slot)
+        self._in_dev.copy_(self._in_host[slot], non_blocking=True)     # a single cudaMemcpyAsync
+        d = self._in_dev_views
+        return self.step(d["actions"], reward_type, retarget=d.get("retarget"), slab=d.get("slab"))
+
+    @property
+    def input_bytes(self):
+        self.host_inputs()
+        return int(self._in_bytes)
+
+    @property
+    def fetch_bytes(self):
+        """Bytes one fetch_host moves (the arena, 256-byte padding between its tensors included)."""
+        return int(self.arena.numel())
+
+    def decode_agent_terms(self, terms, reward_type=None):
+        """float64[...,4] (attraction, repulsion, alignment, sum) from the compact per-agent credit (int16[...,4] =
+        rew_rep_i, rew_attr_i, U_i, Q_i; include/swarm_abi.h) for the weights of ``reward_type`` -- the same values
+        ``agent_reward`` holds, formed on the consumer's side (SDE:371-379)."""
+        rt = DEFAULT_REWARD_TYPE if reward_type is None else reward_type
+        t = terms.to(torch.float64) if isinstance(terms, torch.Tensor) else torch.as_tensor(np.asarray(terms), dtype=torch.float64)
+        inv = 1.0 / (self.N * (self.N - 1))
+        w_ali = float(rt["alignment"])
+        vf = rt.get("vf_size", None)
+        if vf is not None and vf < 0:
+            w_ali = 0.0
+        rep = float(rt["repulsion"]) * t[..., 0] * inv
+        att = float(rt["attraction"]) * t[..., 1] * inv
+        ali = -w_ali * (0.25 * t[..., 2] - 0.35355339059327376220 * t[..., 3]) * inv
+        return torch.stack([att, rep, ali, att + rep + ali], -1)
 
     def observe_visual_field(self, vf_size=2, out=None):
         """Egocentric occupancy windows of the current state: uint8[E,N,2vf+1,2vf+1], [dy+vf][dx+vf]; 0 empty / outside
@@ -273,9 +374,35 @@ class BatchedSwarmEnv:
     STAT_KEYS = ("episodes", "sum_length", "sum_return", "sum_survival", "sum_attraction", "sum_repulsion",
                  "sum_alignment", "running_steps")
 
+    @property
+    def ep_len(self):
+        """Length of every env's running episode: int32[E] view of the running-episode record."""
+        return None if self.ep_rec is None else self.ep_rec[:, 0]
+
+    @property
+    def ep_ret(self):
+        """Running attraction / repulsion / alignment return: f32[E,3] view of the running-episode record."""
+        return None if self.ep_rec is None else self.ep_rec.view(torch.float32)[:, 1:]
+
     def stats(self):
+        """Episode statistics of this batch (synchronous: reduces on the current stream and waits for the result)."""
         out = (C.c_double * 8)()
         _lib.check(self.lib.swarm_stats_read(self._h, out, self._stream()), self._h)
+        return dict(zip(self.STAT_KEYS, [float(v) for v in out]))
+
+    def stats_begin(self, allreduce=False):
+        """Asynchronous statistics for a step loop (e.g. every 64 steps): the reduction is enqueued on the current
+        stream, the optional NCCL sum all-reduce over the ranks (on the device buffer) and the copy to pinned host
+        memory run on the library's side stream.  Never blocks the host; collect with ``stats_end``."""
+        _lib.check(self.lib.swarm_stats_begin(self._h, int(bool(allreduce)), self._stream()), self._h)
+
+    def stats_end(self, wait=False):
+        """Oldest result begun and not yet collected, or None while it is still in flight (``wait=False``)."""
+        out = (C.c_double * 8)()
+        rc = self.lib.swarm_stats_end(self._h, out, int(bool(wait)))
+        if rc == _lib.E_NOT_READY:
+            return None
+        _lib.check(rc, self._h)
         return dict(zip(self.STAT_KEYS, [float(v) for v in out]))
 
     def init_nccl(self, rank, world_size, broadcast_bytes):
@@ -290,15 +417,14 @@ class BatchedSwarmEnv:
         self._nccl_ready = True
 
     def stats_allreduce(self):
-        """Sum the episode statistics over all ranks (NCCL over NVLink, 8 doubles)."""
-        st = self.stats()
-        buf = (C.c_double * 8)(*[st[k] for k in self.STAT_KEYS])
+        """Sum the episode statistics over all ranks (NCCL over NVLink, 8 doubles, on the device buffer); synchronous."""
+        buf = (C.c_double * 8)()
         _lib.check(self.lib.swarm_stats_allreduce(self._h, buf, self._stream()), self._h)
         return dict(zip(self.STAT_KEYS, [float(v) for v in buf]))
 
     # ---- checkpoint / resume (the reference's state is its attributes + the global NumPy RNG, SURVEY.md 5) ----
-    _STATE_TENSORS = ("x", "y", "px", "py", "target", "pred_orient", "frozen", "err", "reset_count",
-                      "ep_len", "ep_ret", "fin_count", "fin_len", "fin_ret")
+    _STATE_TENSORS = ("x", "y", "px", "py", "target", "pred_orient", "frozen", "err", "reset_count", "tcell",
+                      "ep_rec", "fin_count", "fin_len", "fin_ret")
 
     def state_dict(self):
         """Everything needed to continue bit-identically: device state, statistics, reset tapes, the host tape
@@ -318,7 +444,12 @@ class BatchedSwarmEnv:
     def load_state_dict(self, d):
         assert tuple(d["shape"]) == (self.E, self.N, self.S), "checkpoint is for another shape"
         for k, v in d["tensors"].items():
-            getattr(self, k).copy_(v)                   # in place: the bound device pointers stay valid
+            if getattr(self, k, None) is not None:
+                getattr(self, k).copy_(v)               # in place: the bound device pointers stay valid
+        if self.tcell is not None:                      # (a checkpoint of another kernel path carries no target cell)
+            idx = self.target.long().clamp(0, self.N - 1).unsqueeze(1)
+            self.tcell[:, 0].copy_(self.x.gather(1, idx).squeeze(1))
+            self.tcell[:, 1].copy_(self.y.gather(1, idx).squeeze(1))
         if d["place"] is not None:
             self.set_reset_tapes(d["place"], d["ptape"])
         self._rng.bit_generator.state = d["rng"]
@@ -360,6 +491,8 @@ class BatchedSwarmEnv:
             idx = np.nonzero(dn)[0]
             ag[idx, o["eaten"][idx], 0] = float(self.predator_eat_rew)
             o["agent"] = ag
+        if self.agent_terms is not None:
+            o["terms"] = self.agent_terms.cpu().numpy().astype(np.int64)
         if self.agent_counts is not None:
             o["agent_cnt"] = self.agent_counts.cpu().numpy().astype(np.int64)
             o["eff"] = self.eff_action.cpu().numpy()
@@ -428,9 +561,12 @@ class SwarmVectorEnv:
 
     def reset(self, seed=None):
         if seed is not None:
-            self.env._rng = np.random.default_rng(seed)
-            self.env._place = None
-            self.env._chunk = None
+            env = self.env
+            env._rng = np.random.default_rng(seed if env.env_offset == 0 else [int(seed), env.env_offset])
+            env._place = None
+            env._chunk = None
+            env.seed, env.step_index = int(seed), 0     # device tapes: new Philox key, streams restart
+            env._dev_reset_bound = False
         self.env.reset()
         return self._observe(), {"predator": torch.stack([self.env.px, self.env.py], 1)}
 

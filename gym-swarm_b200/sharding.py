@@ -41,6 +41,42 @@ def slice_step_tapes(st, lo: int, hi: int):
                    slab=np.ascontiguousarray(st.slab[:, lo:hi]), roll=np.ascontiguousarray(st.roll[:, lo:hi]))
 
 
+def gpu_numa_node(device_index: int) -> int:
+    """NUMA node of a CUDA device's PCIe root (from sysfs), or -1 when unknown."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        return int(open(path).read().strip())
+    except Exception:
+        return -1
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin the calling process to the CPUs of the GPU's NUMA node, so that the pinned host buffers it allocates next
+    (first touch) are local to that GPU's PCIe root.  With one process per GPU on a two-socket box this keeps half of the
+    host <-> device traffic off the socket interconnect.  Returns what was done (for the bench record); never raises."""
+    import os
+    node = gpu_numa_node(device_index)
+    info = {"numa_node": node, "bound": False}
+    if node < 0:
+        return info
+    try:
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as exc:                       # containers may hide sysfs or forbid the call: run unbound
+        info["error"] = type(exc).__name__
+    return info
+
+
 def allreduce_stats(stats: dict, group=None, device=None) -> dict:
     """Sum the episode statistics over all ranks with torch.distributed (fp64, one 8-element all-reduce)."""
     import torch
@@ -74,6 +110,9 @@ class ShardedSwarmEnv:
         self.num_envs_total = int(num_envs_total)
         self.lo, self.hi = shard_range(num_envs_total, world_size, rank)
         env_kwargs.setdefault("track_stats", True)
+        # env_offset = lo: host tape generators differ per shard, and the in-kernel Philox streams are keyed by the
+        # GLOBAL env index, so a sharded device_tapes job draws exactly what one big batch would draw
+        env_kwargs.setdefault("env_offset", self.lo)
         self.env = BatchedSwarmEnv(self.hi - self.lo, num_agents, obs_space_size, **env_kwargs)
         self._library_nccl = bool(use_library_nccl) and world_size > 1
         if self._library_nccl:

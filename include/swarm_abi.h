@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SWARM_ABI_VERSION 2
+#define SWARM_ABI_VERSION 3
 
 /* return codes */
 #define SWARM_OK 0
@@ -40,6 +40,7 @@ extern "C" {
 #define SWARM_E_CUDA (-2)      /* CUDA runtime error (message has the cudaError string) */
 #define SWARM_E_STATE (-3)     /* call order problem (state or tapes not bound) */
 #define SWARM_E_NCCL (-4)      /* NCCL unavailable or failed */
+#define SWARM_E_NOT_READY (-5) /* swarm_stats_end(wait = 0): the asynchronous statistics are still in flight */
 
 /* per-env error bits (swarm_state.err) */
 #define SWARM_ERR_SLAB_OVERFLOW 1u   /* collision re-draw slab (K) exhausted (SDE:249-255 has no cap) */
@@ -62,6 +63,11 @@ extern "C" {
                                        box-count path) */
 #define SWARM_PATH_GROUP 3   /* fused lane-group kernel even where the thread-per-env kernel (N <= 8) would be used */
 
+/* swarm_config.flags: kernel-selection switches for A/B measurements and for the parity tests that must reach every
+ * kernel variant (read once in swarm_create; the library reads no environment variables) */
+#define SWARM_FLAG_NO_FAR_BORDER 1u /* keep all four thresholds in the pair sweep (no border pass for the far ones) */
+#define SWARM_FLAG_VF_DENSE 4u      /* vf_size steps of the lane-group kernels: always the dense gate sweep */
+
 typedef struct swarm_config {
   int32_t abi_version;       /* SWARM_ABI_VERSION */
   int32_t device;            /* CUDA device ordinal */
@@ -78,6 +84,11 @@ typedef struct swarm_config {
   int32_t auto_reset;        /* 1: finished envs reset in-kernel; 0: they freeze */
   int32_t track_stats;       /* 1: maintain episode statistics (needs the stats pointers) */
   int32_t path;              /* SWARM_PATH_* */
+  uint32_t flags;            /* SWARM_FLAG_* */
+  int32_t tiny16_min_envs;   /* 9..16 agents: thread-per-env kernel from this many envs up (0: default 65,536) */
+  uint32_t env_offset;       /* global index of this handle's env 0 (its shard's `lo`): the counter-based (Philox) tapes
+                                are keyed by env + env_offset, so a sharded job draws what the unsharded one draws */
+  int32_t reserved;          /* 0 */
 } swarm_config;
 
 /* Persistent device state, all caller-allocated. SoA; positions are int16. */
@@ -91,9 +102,15 @@ typedef struct swarm_state {
   uint8_t* frozen;       /* [E]   1 = episode finished and not reset (auto_reset == 0) */
   uint32_t* err;         /* [E]   sticky SWARM_ERR_* bits */
   uint32_t* reset_count; /* [E]   number of resets performed (selects the reset slot) */
+  int16_t* tcell;        /* [E,2] (opt) cell of Predator.current_target: the agent position follow_target reads at the
+                            next step (SDE:142).  State of the STAGED path only (N > 256): its predator and reset kernels
+                            maintain it, and with it the predator kernel needs no dependent random read of the old
+                            positions; the fused kernels hold the whole env in registers and ignore it.  NULL: not kept.
+                            A caller that overwrites x / y / target itself must refresh it (or pass NULL) */
   /* episode statistics (track_stats == 1, else may be NULL) */
-  uint32_t* ep_len;      /* [E]   length of the running episode */
-  float* ep_ret;         /* [E,4] running episode return: survival, attraction, repulsion, alignment */
+  uint32_t* ep_rec;      /* [E,4] running episode, one 16-byte record: word 0 = length (u32), words 1..3 = f32 bits of
+                            the running attraction, repulsion, alignment return (the survival term is non-zero only on
+                            the terminal step, so a running episode's survival return is always 0) */
   uint32_t* fin_count;   /* [E]   finished episodes */
   uint32_t* fin_len;     /* [E]   sum of finished episode lengths */
   float* fin_ret;        /* [E,4] sum of finished episode returns per component */
@@ -132,6 +149,12 @@ typedef struct swarm_step_out {
                             survival is predator_eat_rew for agent `eaten`, 0 otherwise */
   int32_t* agent_counts; /* [E,N,2] (opt) integer rew_rep_i (SDE:372), rew_attr_i (SDE:373) */
   uint8_t* eff_action;   /* [E,N] (opt) action id each agent finally moved with (after re-draws) */
+  int16_t* agent_terms;  /* [E,N,4] (opt, N <= 4096) compact per-agent credit: the integers the per-agent floats are exact
+                            functions of -- (rew_rep_i, rew_attr_i, U_i, Q_i) with
+                              repulsion_i = w_rep * rew_rep_i / (N(N-1)),  attraction_i = w_att * rew_attr_i / (N(N-1)),
+                              alignment_i = -w_ali * (0.25 * U_i - (sqrt(2)/4) * Q_i) / (N(N-1))      (SDE:371-379);
+                            all four are 0 on a terminal step.  Half the bytes of agent_reward for callers that read
+                            rewards over PCIe; either, both or neither may be bound */
 } swarm_step_out;
 
 typedef struct swarm_ctx* swarm_handle;
@@ -168,11 +191,16 @@ int swarm_move(int32_t E, int32_t N, int32_t S, const int16_t* x, const int16_t*
 int swarm_predator(int32_t E, int32_t N, int32_t S, const int16_t* x_old, const int16_t* y_old,
                    const int16_t* x_new, const int16_t* y_new, const uint8_t* retarget, int16_t* px, int16_t* py,
                    int32_t* target, uint8_t* pred_orient, int16_t* pred_prev, uint8_t* done, int32_t* eaten,
+                   int16_t* tcell /* [E,2] in/out (opt): swarm_state.tcell; NULL: the target's old cell is read from x_old/y_old */,
                    void* stream);
 /* SDE:330-343 integer part: per-agent un-weighted rew_rep_i / rew_attr_i from a tiled O(N^2) pass.
  * out_counts: int32[E,N,2]; skip (may be NULL): uint8[E], envs with skip != 0 are not computed. */
 int swarm_pairwise(int32_t E, int32_t N, int32_t S, int32_t attraction_thresh, int32_t repulsion_thresh,
-                   const int16_t* x, const int16_t* y, const uint8_t* skip, int32_t* out_counts, void* stream);
+                   const int16_t* x, const int16_t* y, const uint8_t* skip, int32_t* out_counts, void* scratch,
+                   uint64_t scratch_bytes, void* stream);
+/* Device scratch swarm_pairwise needs for (E, N): the caller allocates it (any 256-byte aligned device block) and may
+ * reuse it between calls on one stream; calls with different scratch blocks may overlap freely. */
+uint64_t swarm_pairwise_scratch_bytes(int32_t E, int32_t N);
 /* SDE:197-221: reset the envs whose mask byte is non-zero (all if mask == NULL) from their next reset slot. */
 int swarm_autoreset(swarm_handle h, const uint8_t* mask, void* stream);
 
@@ -185,12 +213,24 @@ int swarm_observe_vf(int32_t E, int32_t N, int32_t S, int32_t vf, const int16_t*
 
 /* ---- episode statistics ---- */
 /* out[8] = episodes, sum length, sum return, sum survival, sum attraction, sum repulsion, sum alignment,
- * env-steps of running episodes.  Deterministic reduction; synchronises the stream. */
+ * env-steps of running episodes.  Deterministic two-stage reduction over the envs (multi-CTA partials, fixed order).
+ *
+ * Asynchronous form (the one a step loop uses, e.g. every 64 steps): swarm_stats_begin enqueues the reduction on
+ * `stream` (so it sees exactly the steps enqueued before it), then -- on the handle's own side stream, behind an event,
+ * off the step's critical path -- the optional NCCL sum all-reduce of the 8 doubles ON THE DEVICE BUFFER and the copy
+ * into a pinned host slot.  It never synchronises the host.  swarm_stats_end returns the oldest result begun and not
+ * yet collected: SWARM_E_NOT_READY if wait == 0 and it is still in flight.  Up to 4 results may be in flight. */
+int swarm_stats_begin(swarm_handle h, int32_t allreduce, void* stream);
+int swarm_stats_end(swarm_handle h, double out[8], int32_t wait);
+/* Synchronous conveniences: begin + end(wait = 1). */
 int swarm_stats_read(swarm_handle h, double out[8], void* stream);
-/* NCCL (dlopen'ed libnccl.so.2): communicator bootstrap + in-place sum all-reduce of the 8 statistics. */
+int swarm_stats_allreduce(swarm_handle h, double out[8], void* stream);
+/* NCCL (dlopen'ed libnccl.so.2): the library bootstraps its own communicator from a unique id the host broadcasts
+ * (swarm_nccl_init), or adopts one the caller already owns (swarm_nccl_adopt: comm is an ncclComm_t; not destroyed by
+ * swarm_destroy). */
 int swarm_nccl_unique_id(uint8_t out_id[128]);
 int swarm_nccl_init(swarm_handle h, const uint8_t id[128], int32_t nranks, int32_t rank);
-int swarm_stats_allreduce(swarm_handle h, double inout[8], void* stream);
+int swarm_nccl_adopt(swarm_handle h, void* comm);
 
 /* ---- measurement helpers ---- */
 /* INT32-pipe micro-benchmarks (independent dependent-chain kernels); returns lane-ops/s in *out.

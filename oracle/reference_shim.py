@@ -36,7 +36,12 @@ import types
 
 import numpy as _np
 
-REFERENCE_FILE = "/root/reference/gym_swarm/envs/swarm_discrete_env.py"
+# The unmodified reference file: where it lies in the authoring container, else the copy `pip install --target
+# baseline/_ref` made of it (git-ignored, travels to the GPU box with the snapshot; __graft_entry__.build()).
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = ("/root/reference/gym_swarm/envs/swarm_discrete_env.py",
+               os.path.join(_REPO, "baseline", "_ref", "gym_swarm", "envs", "swarm_discrete_env.py"))
+REFERENCE_FILE = next((c for c in _CANDIDATES if os.path.isfile(c)), _CANDIDATES[0])
 
 
 def reference_available() -> bool:

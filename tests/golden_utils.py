@@ -9,9 +9,22 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-# float rewards: north-star tolerance (1e-6 relative); counts/positions/flags: bit-exact
+# float rewards: north-star tolerance (1e-6 RELATIVE); counts/positions/flags: bit-exact
 RTOL = 1e-6
-ATOL = 1e-9
+ZERO = 1e-12    # the reference's float64 sums return its exact zeros as +-1e-16: below this a reference value IS zero
+
+
+def assert_float_parity(got, want, rtol=RTOL, err_msg=""):
+    """|got - want| <= rtol * |want| for every entry; where the reference value is (numerically) zero the result must
+    be zero as well.  No absolute slack anywhere else."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, f"{err_msg}: shape {got.shape} != {want.shape}"
+    zero = np.abs(want) < ZERO
+    bad = np.where(zero, np.abs(got) >= ZERO, np.abs(got - want) > rtol * np.abs(want))
+    if bad.any():
+        i = tuple(int(v[0]) for v in np.nonzero(bad))
+        raise AssertionError(f"{err_msg}: {int(bad.sum())} of {bad.size} entries beyond rtol={rtol}; first at {i}: "
+                             f"got {got[i]!r}, reference {want[i]!r}")
 
 
 def case_names():
@@ -53,15 +66,14 @@ def replay(impl, cfg, z, steps=None, check_agents=True, float_rtol=RTOL):
         np.testing.assert_array_equal(o["step_target"][live], z["step_target"][t][live], err_msg=ctx + " step_target")
         np.testing.assert_array_equal(o["consumed"][live], z["consumed"][t][live], err_msg=ctx + " consumed draws")
         np.testing.assert_array_equal(o["cnt"][live], z["cnt"][t][live], err_msg=ctx + " integer reward counts")
-        np.testing.assert_allclose(o["glob"][live], z["glob"][t][live], rtol=float_rtol, atol=ATOL,
-                                   err_msg=ctx + " global reward")
+        assert_float_parity(o["glob"][live], z["glob"][t][live], rtol=float_rtol, err_msg=ctx + " global reward")
         dn = (z["done"][t] == 1) & live
         np.testing.assert_array_equal(o["term_x"][dn], z["term_x"][t][dn], err_msg=ctx + " terminal x")
         np.testing.assert_array_equal(o["term_y"][dn], z["term_y"][t][dn], err_msg=ctx + " terminal y")
         if check_agents:
             np.testing.assert_array_equal(o["agent_cnt"][live], z["agent_cnt"][t][live],
                                           err_msg=ctx + " per-agent integer counts")
-            np.testing.assert_allclose(o["agent"][live], z["agent"][t][live], rtol=float_rtol, atol=ATOL,
+            assert_float_parity(o["agent"][live], z["agent"][t][live], rtol=float_rtol,
                                        err_msg=ctx + " per-agent reward")
         assert not np.any(o["err"] & ~np.uint32(16)), ctx + f" error flags {o['err']}"
     return T

@@ -37,12 +37,24 @@ def test_library_exports_every_declared_symbol(built):
     assert lib.swarm_abi_version() == _lib.ABI_VERSION
 
 
+def _header_struct_fields(name):
+    """Field names of `typedef struct <name> { ... } <name>;` in include/swarm_abi.h, in declaration order."""
+    src = open(_lib.HEADER_PATH).read()
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    return [re.search(r"(\w+)\s*$", decl.strip()).group(1) for decl in body.split(";") if decl.strip()]
+
+
 def test_struct_layout_matches_header():
-    # field counts / sizes of the ctypes mirrors (all pointers 8 bytes, int32/float 4, double 8)
-    assert ctypes.sizeof(_lib.Config) == 15 * 4
+    # the ctypes mirrors carry the header's fields in the header's order ...
+    for cname, mirror in (("swarm_config", _lib.Config), ("swarm_state", _lib.State), ("swarm_step_in", _lib.StepIn),
+                          ("swarm_step_out", _lib.StepOut)):
+        assert _header_struct_fields(cname) == [f[0] for f in mirror._fields_], cname
+    # ... and their sizes (all pointers 8 bytes, int32/uint32/float 4, double 8)
+    assert ctypes.sizeof(_lib.Config) == 19 * 4
     assert ctypes.sizeof(_lib.State) == 14 * 8
     assert ctypes.sizeof(_lib.StepIn) == 3 * 8 + 3 * 8 + 4 + 4 + 8
-    assert ctypes.sizeof(_lib.StepOut) == 14 * 8
+    assert ctypes.sizeof(_lib.StepOut) == 15 * 8
 
 
 def test_no_cpu_fallback(built):

@@ -73,9 +73,23 @@ def test_swarm_predator_matches_oracle(E, N, S):
     prev = torch.zeros((E, 2), dtype=torch.int16, device="cuda")
     done = torch.zeros(E, dtype=torch.uint8, device="cuda")
     eaten = torch.zeros(E, dtype=torch.int32, device="cuda")
+    # second run with the cached target cell (swarm_state.tcell) instead of the dependent read of the old positions
+    d2 = {k: v.clone() for k, v in d.items()}
+    ori2, prev2, done2, eaten2 = torch.zeros_like(ori), torch.zeros_like(prev), torch.zeros_like(done), torch.zeros_like(eaten)
+    ar = np.arange(E)
+    tcell = torch.from_numpy(np.stack([xo[ar, tgt], yo[ar, tgt]], 1).astype(np.int16)).cuda()
     _lib.check(lib.swarm_predator(E, N, S, _ptr(d["xo"]), _ptr(d["yo"]), _ptr(d["xn"]), _ptr(d["yn"]), _ptr(d["ret"]),
                                   _ptr(d["px"]), _ptr(d["py"]), _ptr(d["tgt"]), _ptr(ori), _ptr(prev), _ptr(done),
-                                  _ptr(eaten), _stream()))
+                                  _ptr(eaten), None, _stream()))
+    _lib.check(lib.swarm_predator(E, N, S, _ptr(d2["xo"]), _ptr(d2["yo"]), _ptr(d2["xn"]), _ptr(d2["yn"]), _ptr(d2["ret"]),
+                                  _ptr(d2["px"]), _ptr(d2["py"]), _ptr(d2["tgt"]), _ptr(ori2), _ptr(prev2), _ptr(done2),
+                                  _ptr(eaten2), _ptr(tcell), _stream()))
+    for a, b in ((d["px"], d2["px"]), (d["py"], d2["py"]), (d["tgt"], d2["tgt"]), (ori, ori2), (prev, prev2), (done, done2),
+                 (eaten, eaten2)):
+        assert torch.equal(a, b), "target-cell cache changed the predator step"
+    t_new = d2["tgt"].long().cpu().numpy()
+    np.testing.assert_array_equal(tcell.cpu().numpy(), np.stack([xn[ar, t_new], yn[ar, t_new]], 1),
+                                  err_msg="tcell must hold the target's NEW cell after the step")
     n_done = 0
     for e in range(E):
         npx, npy, t, o = so.follow_target(int(px[e]), int(py[e]), int(tgt[e]), 0, xo[e].astype(np.int64),
@@ -104,7 +118,10 @@ def test_swarm_pairwise_matches_oracle(E, N, S, att, rep):
     skip[E - 1] = 1
     dx, dy, ds = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(skip).cuda()
     out = torch.full((E, N, 2), -7, dtype=torch.int32, device="cuda")
-    _lib.check(lib.swarm_pairwise(E, N, S, att, rep, _ptr(dx), _ptr(dy), _ptr(ds), _ptr(out), _stream()))
+    nbytes = int(lib.swarm_pairwise_scratch_bytes(E, N))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.swarm_pairwise(E, N, S, att, rep, _ptr(dx), _ptr(dy), _ptr(ds), _ptr(out), _ptr(scratch), nbytes,
+                                  _stream()))
     got = out.cpu().numpy()
     eff = np.zeros(N, dtype=np.int64)
     for e in range(E):

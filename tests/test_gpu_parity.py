@@ -7,7 +7,7 @@ north-star tolerance 1e-6 relative (golden_utils.RTOL)."""
 import numpy as np
 import pytest
 
-from golden_utils import case_names, load_case, replay
+from golden_utils import assert_float_parity, case_names, load_case, replay
 
 pytestmark = pytest.mark.gpu
 
@@ -21,8 +21,8 @@ def make_env(cfg, path="auto", **kw):
 
 
 class CudaImpl:
-    def __init__(self, cfg, z, path):
-        self.env = make_env(cfg, path)
+    def __init__(self, cfg, z, path, **kw):
+        self.env = make_env(cfg, path, **kw)
         self.env.set_reset_tapes(z["place"], z["ptape"])
 
     def reset(self):
@@ -69,24 +69,25 @@ def test_golden_lane_group_kernel_small_n(name):
 
 
 @pytest.mark.parametrize("name", _small_n_cases(9, 16))
-def test_golden_thread_per_env_kernel_16(name, monkeypatch):
+def test_golden_thread_per_env_kernel_16(name):
     """Fixtures with 9..16 agents through the 16-agent thread-per-env kernel (normally reserved for huge batches)."""
-    monkeypatch.setenv("SWARM_TINY16_MIN_ENVS", "1")
     cfg, z = load_case(name)
-    impl = CudaImpl(cfg, z, "auto")
+    impl = CudaImpl(cfg, z, "auto", tiny16_min_envs=1)
     assert impl.env.path_name.startswith("tiny<16>") or cfg["vf"] is not None, impl.env.path_name
     replay(impl, cfg, z, steps=150)
     impl.env.close()
 
 
 def _oracle_lockstep(E, N, S, T, seed, path="auto", att=5, rep=2, eat=-10.0, vf=None, n_actions=8, K=None, KR=None,
-                     weights=(1.0, 1.0, 1.0), auto_reset=True, check_agents=True, agent_out=True):
+                     weights=(1.0, 1.0, 1.0), auto_reset=True, check_agents=True, agent_out=True, flags=0,
+                     tiny16_min_envs=0):
     from gym_swarm_b200 import tapes
     from gym_swarm_b200.envs import BatchedSwarmEnv
     from oracle import swarm_oracle as so
     rng = np.random.default_rng(seed)
     env = BatchedSwarmEnv(E, N, S, att, rep, eat, auto_reset=auto_reset, slab_len=K, place_extra=KR, reset_slots=3,
-                          per_agent=agent_out, debug_outputs=agent_out, path=path)
+                          per_agent=agent_out, debug_outputs=agent_out, path=path, flags=flags,
+                          tiny16_min_envs=tiny16_min_envs)
     check_agents = check_agents and agent_out
     rt = tapes.make_reset_tapes(rng, env.R, E, N, S, KR=env.KR, KP=env.KP)
     st = tapes.make_step_tapes(rng, T, E, N, K=env.K, n_actions=n_actions)
@@ -105,11 +106,10 @@ def _oracle_lockstep(E, N, S, T, seed, path="auto", att=5, rep=2, eat=-10.0, vf=
             np.testing.assert_array_equal(a[k], b[k], err_msg=f"step {t} {k}")
         for k in ("eaten", "cnt", "pred_prev", "pred_next", "pred_orient", "step_target", "consumed"):
             np.testing.assert_array_equal(a[k][live], b[k][live], err_msg=f"step {t} {k}")
-        np.testing.assert_allclose(a["glob"][live], b["glob"][live], rtol=1e-6, atol=1e-9, err_msg=f"step {t} glob")
+        assert_float_parity(a["glob"][live], b["glob"][live], err_msg=f"step {t} glob")
         if check_agents:
             np.testing.assert_array_equal(a["agent_cnt"][live], b["agent_cnt"][live], err_msg=f"step {t} agent_cnt")
-            np.testing.assert_allclose(a["agent"][live], b["agent"][live], rtol=1e-6, atol=1e-9,
-                                       err_msg=f"step {t} agent")
+            assert_float_parity(a["agent"][live], b["agent"][live], err_msg=f"step {t} agent")
             np.testing.assert_array_equal(a["eff"][live], b["eff"][live], err_msg=f"step {t} eff action")
     env.close()
 
@@ -140,12 +140,11 @@ def test_oracle_lockstep_tiny_and_group_kernels(N, S):
 
 
 @pytest.mark.parametrize("N,S", [(9, 16), (12, 7), (13, 40), (16, 32), (16, 8)])
-def test_oracle_lockstep_tiny16_kernel(N, S, monkeypatch):
+def test_oracle_lockstep_tiny16_kernel(N, S):
     """9..16 agents: the 16-agent instantiation of the thread-per-env kernel (normally chosen only for batches of
-    >= 65,536 envs; SWARM_TINY16_MIN_ENVS lowers the bar so that the oracle can follow)."""
+    >= 65,536 envs; swarm_config.tiny16_min_envs lowers the bar so that the oracle can follow)."""
     from gym_swarm_b200.envs import BatchedSwarmEnv
-    monkeypatch.setenv("SWARM_TINY16_MIN_ENVS", "1")
-    env = BatchedSwarmEnv(4, N, S)
+    env = BatchedSwarmEnv(4, N, S, tiny16_min_envs=1)
     assert env.path_name.startswith("tiny<16>"), env.path_name
     env.close()
     dense = S * S < 4 * N
@@ -184,24 +183,23 @@ def test_box_count_path_thresholds(att, rep):
     _oracle_lockstep(E=2, N=1500, S=50, T=2, seed=att + rep, n_actions=9, att=att, rep=rep, K=4096, KR=6000)
 
 
-@pytest.mark.parametrize("force", ["0", "1"])
 @pytest.mark.parametrize("N,S", [(16, 32), (24, 12), (33, 64), (64, 64), (100, 48), (128, 128), (255, 64)])
-def test_fused_reward_by_ring_sweep_and_by_box_counts(N, S, force, monkeypatch):
-    """The fused lane-group kernel computes the reward counts either by the symmetric ring sweep or from the env's
-    occupancy bitmap (box counts); SWARM_FUSED_BOX forces one or the other regardless of the cost heuristic."""
-    monkeypatch.setenv("SWARM_FUSED_BOX", force)
+def test_fused_reward_by_ring_sweep(N, S):
+    """The fused lane-group kernel's reward counts (symmetric ring sweep + border pass) on every ring shape, dense grids
+    included."""
     dense = S * S < 4 * N
-    _oracle_lockstep(E=9, N=N, S=S, T=12, seed=N * 3 + S + int(force), n_actions=9, K=512 if dense else None,
+    _oracle_lockstep(E=9, N=N, S=S, T=12, seed=N * 3 + S, n_actions=9, K=512 if dense else None,
                      KR=2000 if dense else None, weights=(0.5, 1.0, 0.25))
 
 
 @pytest.mark.parametrize("N,S", [(16, 32), (24, 12), (64, 64), (60, 11), (128, 128)])
-def test_fused_four_threshold_sweep(N, S, monkeypatch):
+def test_fused_four_threshold_sweep(N, S):
     """Default thresholds normally take the border pass for the two far thresholds + a 2-threshold ring sweep;
-    SWARM_NO_FAR_BORDER keeps all four thresholds in the sweep (the path other threshold combinations use)."""
-    monkeypatch.setenv("SWARM_NO_FAR_BORDER", "1")
+    SWARM_FLAG_NO_FAR_BORDER keeps all four thresholds in the sweep (the path other threshold combinations use)."""
+    from gym_swarm_b200 import _lib
     dense = S * S < 4 * N
-    _oracle_lockstep(E=9, N=N, S=S, T=10, seed=N + S, n_actions=9, K=512 if dense else None, KR=2000 if dense else None)
+    _oracle_lockstep(E=9, N=N, S=S, T=10, seed=N + S, n_actions=9, K=512 if dense else None, KR=2000 if dense else None,
+                     flags=_lib.FLAG_NO_FAR_BORDER)
 
 
 @pytest.mark.parametrize("att,rep", [(5, 2), (2, 5), (1, 1), (9, 3), (3, 12), (12, 12), (20, 3), (31, 31), (32, 5)])
@@ -214,10 +212,11 @@ def test_fused_far_border_pass_thresholds(att, rep):
 
 
 @pytest.mark.parametrize("att,rep", [(5, 2), (2, 5), (0, 0), (1, 1), (9, 3), (3, 12), (10, 200), (40, 3), (70, 70), (5, 60)])
-def test_fused_box_count_thresholds(att, rep, monkeypatch):
-    monkeypatch.setenv("SWARM_FUSED_BOX", "1")
-    _oracle_lockstep(E=6, N=120, S=64, T=4, seed=att * 13 + rep, n_actions=9, att=att, rep=rep, weights=(0.5, 1.0, 0.25))
-    _oracle_lockstep(E=6, N=40, S=21, T=4, seed=att + rep, n_actions=9, att=att, rep=rep)
+def test_staged_box_count_thresholds(att, rep):
+    """Box counts on the occupancy bitmap (the staged path's default reward counts): zero / all / direct / complement plans."""
+    _oracle_lockstep(E=3, N=600, S=64, T=3, seed=att * 13 + rep, n_actions=9, att=att, rep=rep, weights=(0.5, 1.0, 0.25),
+                     path="staged")
+    _oracle_lockstep(E=3, N=300, S=45, T=3, seed=att + rep, n_actions=9, att=min(att, 45), rep=min(rep, 45), path="staged")
 
 
 @pytest.mark.parametrize("E,N,S,path", [(300, 8, 6, "auto"), (64, 5, 9, "group"), (40, 16, 8, "auto"), (9, 128, 40, "auto"),
@@ -277,23 +276,23 @@ def test_oracle_lockstep_large_n16384():
 @pytest.mark.parametrize("N,S,vf", [(12, 24, 1), (16, 32, 2), (30, 40, 2), (60, 64, 5), (100, 128, 0), (128, 128, 5),
                                     (128, 200, 12), (37, 50, 4), (128, 16384, 9)])
 @pytest.mark.parametrize("dense", [False, True])
-def test_vf_sparse_and_dense_modes(N, S, vf, dense, monkeypatch):
+def test_vf_sparse_and_dense_modes(N, S, vf, dense):
     """vf_size steps on the ring-sweep shapes: the sparse mode (visible pairs recorded by the symmetric sweep, picked when
-    (2 vf + 1)^2 <= S^2 / 16) and the dense mode (every ordered pair gated; SWARM_VF_DENSE=1 forces it) both reproduce the
+    (2 vf + 1)^2 <= S^2 / 16) and the dense mode (every ordered pair gated; SWARM_FLAG_VF_DENSE forces it) both reproduce the
     oracle; att / rep far thresholds, action 8 and auto-reset included."""
-    if dense:
-        monkeypatch.setenv("SWARM_VF_DENSE", "1")
+    from gym_swarm_b200 import _lib
     for (att, rep) in ((5, 2), (2, 5)):
         _oracle_lockstep(E=37, N=N, S=S, T=6, seed=N + S + vf, vf=vf, att=att, rep=rep, weights=(0.5, 1.0, 2.0),
-                         n_actions=9)
+                         n_actions=9, flags=_lib.FLAG_VF_DENSE if dense else 0)
 
 
 @pytest.mark.parametrize("N,S", [(16, 32), (64, 64), (128, 128)])
-def test_vf_sparse_with_four_threshold_sweep(N, S, monkeypatch):
+def test_vf_sparse_with_four_threshold_sweep(N, S):
     """Sparse visual-field mode on the ring sweep that carries all four thresholds (no border pass), the variant taken
     when a far threshold is at or below S/2."""
-    monkeypatch.setenv("SWARM_NO_FAR_BORDER", "1")
-    _oracle_lockstep(E=9, N=N, S=S, T=6, seed=N + S, vf=2, n_actions=9, weights=(0.5, 1.0, 2.0))
+    from gym_swarm_b200 import _lib
+    _oracle_lockstep(E=9, N=N, S=S, T=6, seed=N + S, vf=2, n_actions=9, weights=(0.5, 1.0, 2.0),
+                     flags=_lib.FLAG_NO_FAR_BORDER)
 
 
 @pytest.mark.parametrize("vf", [-1, 2.5])

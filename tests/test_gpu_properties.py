@@ -190,6 +190,7 @@ def test_kernel_paths_agree_at_full_size(E, N, S, paths):
             continue
         for k in ref:
             if ref[k].is_floating_point():
-                assert torch.allclose(ref[k], out[k], rtol=1e-6, atol=1e-9), f"{k}: path {paths[0]} != {path}"
+                # two kernel paths form the same integers and combine them in fp64: identical up to the f32 store
+                assert torch.allclose(ref[k], out[k], rtol=1e-6, atol=0.0), f"{k}: path {paths[0]} != {path}"
             else:
                 assert torch.equal(ref[k], out[k]), f"{k}: path {paths[0]} != {path}"

@@ -148,3 +148,51 @@ def test_shard_equivalence_on_one_gpu():
     whole.close()
     for _, _, env in parts:
         env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("E,N,S,path", [(301, 8, 9, "auto"), (150, 16, 12, "auto"), (40, 100, 40, "auto"), (5, 300, 64, "staged")])
+def test_sharded_device_tapes_equal_unsharded(E, N, S, path):
+    """In-kernel (Philox) tapes are keyed by the GLOBAL env index (swarm_config.env_offset = the shard's lo): three
+    shards of a batch draw exactly what the whole batch draws -- resets, re-draws, retarget flags, auto-resets."""
+    import torch
+    from gym_swarm_b200.envs import BatchedSwarmEnv
+    T_ = 40
+    acts = np.random.default_rng(E + N).integers(0, 9, size=(T_, E, N), dtype=np.uint8)
+    kw = dict(device_tapes=True, seed=1234, track_stats=True, debug_outputs=True, path=path, place_extra=400,
+              pred_attempts=32, slab_len=256)
+    whole = BatchedSwarmEnv(E, N, S, **kw)
+    whole.reset()
+    parts = []
+    for r in range(3):
+        lo, hi = sharding.shard_range(E, 3, r)
+        env = BatchedSwarmEnv(hi - lo, N, S, env_offset=lo, **kw)
+        env.reset()
+        parts.append((lo, hi, env))
+    keys = ("x", "y", "px", "py", "target", "done", "eaten", "reward", "counts", "consumed", "agent_reward", "eff_action",
+            "reset_count")
+    n_done = 0
+    for t in range(T_):
+        whole.step(acts[t])
+        for lo, hi, env in parts:
+            env.step(acts[t, lo:hi])
+            for k in keys:
+                assert torch.equal(getattr(whole, k)[lo:hi], getattr(env, k)), f"step {t} {k} shard [{lo},{hi})"
+        n_done += int(whole.done.sum())
+    assert n_done > 0 and int(whole.reset_count.max()) >= 1
+    whole.check_errors()
+    whole.close()
+    for _, _, env in parts:
+        env.close()
+
+
+@pytest.mark.gpu
+def test_sharded_env_host_tapes_differ_per_shard():
+    """ShardedSwarmEnv passes env_offset = lo, so the shards' internal HOST tape generators are distinct streams (with
+    one shared seed every rank used to replay rank 0's placements)."""
+    a = sharding.ShardedSwarmEnv(64, 8, 16, rank=0, world_size=2, seed=5)
+    b = sharding.ShardedSwarmEnv(64, 8, 16, rank=1, world_size=2, seed=5)
+    assert (a.lo, a.hi, b.lo, b.hi) == (0, 32, 32, 64) and b.env.env_offset == 32
+    a.reset(), b.reset()
+    assert not bool((a.env.x == b.env.x).all())
+    a.close(), b.close()

@@ -67,7 +67,7 @@ def run_move(lib, dev):
             "achieved": alg / (mean * 1e-3) / 1e9, "peak": HBM, "unit": "GB/s", "frac": alg / (mean * 1e-3) / 1e9 / HBM}
 
 
-def run_predator(lib, dev, N=128, E=1 << 20, S=128):
+def run_predator(lib, dev, N=128, E=1 << 20, S=128, use_tcell=True):
     g = torch.Generator(device=dev).manual_seed(2)
     xo = torch.randint(0, S, (E, N), dtype=torch.int16, device=dev, generator=g)
     yo = torch.randint(0, S, (E, N), dtype=torch.int16, device=dev, generator=g)
@@ -81,13 +81,19 @@ def run_predator(lib, dev, N=128, E=1 << 20, S=128):
     prev = torch.zeros((E, 2), dtype=torch.int16, device=dev)
     done = torch.zeros((E,), dtype=torch.uint8, device=dev)
     eaten = torch.zeros((E,), dtype=torch.int32, device=dev)
+    # the cached cell of the current target (swarm_state.tcell), as the staged step keeps it
+    tcell = torch.stack([xo.gather(1, tgt.long().unsqueeze(1)).squeeze(1), yo.gather(1, tgt.long().unsqueeze(1)).squeeze(1)],
+                        1).contiguous() if use_tcell else None
     fn = lambda: _lib.check(lib.swarm_predator(E, N, S, ptr(xo), ptr(yo), ptr(xn), ptr(yn), ptr(ret), ptr(px), ptr(py),
-                                               ptr(tgt), ptr(ori), ptr(prev), ptr(done), ptr(eaten), stream()))
+                                               ptr(tgt), ptr(ori), ptr(prev), ptr(done), ptr(eaten),
+                                               ptr(tcell) if use_tcell else None, stream()))
     mean, best = timeit(fn)
-    # new positions always (termination test), old positions for the 10 % of envs that retarget + the target's cell,
-    # per env: px,py,target read+write (16), retarget 1, orient 1, pred_prev 4, done 1, eaten 4
-    alg = int(E * (4 * N + 0.1 * 4 * N + 4 + 27))
-    return {"kernel": "swarm_predator (predator_kernel)", "shape": f"{E} envs x {N} agents, S={S}", "bound": "hbm",
+    # new positions always (termination test), old positions for the 10 % of envs that retarget + the target's cell
+    # (4 B read; + 4 B written back with the cache), per env: px,py,target read+write (16), retarget 1, orient 1,
+    # pred_prev 4, done 1, eaten 4
+    alg = int(E * (4 * N + 0.1 * 4 * N + 4 + 27 + (4 if use_tcell else 0)))
+    return {"kernel": "swarm_predator" + (" (target cell cached)" if use_tcell else " (no tcell)"),
+            "shape": f"{E} envs x {N} agents, S={S}", "bound": "hbm",
             "algorithmic_bytes": alg, "bytes_per_env": alg / E, "ms_mean": mean, "ms_best": best,
             "achieved": alg / (mean * 1e-3) / 1e9, "peak": HBM, "unit": "GB/s", "frac": alg / (mean * 1e-3) / 1e9 / HBM}
 
@@ -123,7 +129,10 @@ def run_pairwise(lib, dev, peaks):
     x = torch.randint(0, S, (E, N), dtype=torch.int16, device=dev, generator=g)
     y = torch.randint(0, S, (E, N), dtype=torch.int16, device=dev, generator=g)
     out = torch.empty((E, N, 2), dtype=torch.int32, device=dev)
-    fn = lambda: _lib.check(lib.swarm_pairwise(E, N, S, 5, 2, ptr(x), ptr(y), None, ptr(out), stream()))
+    nbytes = int(lib.swarm_pairwise_scratch_bytes(E, N))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    fn = lambda: _lib.check(lib.swarm_pairwise(E, N, S, 5, 2, ptr(x), ptr(y), None, ptr(out), ptr(scratch), nbytes,
+                                               stream()))
     mean, best = timeit(fn, reps=5)
     pairs = E * N * (N - 1)
     ops14 = pairs * 14                              # 14 scalar INT32 lane-ops per ordered pair
@@ -159,6 +168,10 @@ def main():
         print(json.dumps(run_predator(lib, dev, N=16384, E=8192, S=1024)), flush=True)
         torch.cuda.empty_cache()
         print(json.dumps(run_predator(lib, dev, N=8, E=1 << 24, S=16)), flush=True)
+        torch.cuda.empty_cache()
+        print(json.dumps(run_predator(lib, dev, use_tcell=False)), flush=True)      # round-1 form: dependent random read
+        torch.cuda.empty_cache()
+        print(json.dumps(run_predator(lib, dev, N=8, E=1 << 24, S=16, use_tcell=False)), flush=True)
         torch.cuda.empty_cache()
     if "pairwise" in which:
         print(json.dumps(run_pairwise(lib, dev, peaks)), flush=True)

@@ -39,9 +39,7 @@ def main():
     run(9, 40, 9, 4, slab_len=2048, place_extra=4000, pred_attempts=64)   # fused<16,4>, dense
     run(6, 128, 64, 3)                                 # fused<32,4>
     run(6, 128, 64, 3, vf=3)                           # fused<32,4, vf>
-    os.environ["SWARM_FUSED_BOX"] = "1"
-    run(6, 120, 64, 3)                                 # fused box counts
-    del os.environ["SWARM_FUSED_BOX"]
+    run(6, 120, 64, 3, flags=_lib.FLAG_NO_FAR_BORDER)  # fused<32,4>, all four thresholds in the ring sweep
     run(4, 200, 300, 3)                                # fused<32,8>, no bitmap (all-pairs collision counts)
     run(3, 300, 96, 3)                                 # staged + box
     run(3, 300, 96, 2, path="staged_pairwise")         # staged symmetric pairwise
@@ -67,9 +65,11 @@ def main():
         done = torch.zeros(E, dtype=torch.uint8, device=dev)
         eat = torch.zeros(E, dtype=torch.int32, device=dev)
         _lib.check(lib.swarm_predator(E, N, S, p(x), p(y), p(ox), p(oy), p(ret), p(px), p(py), p(tg), p(ori), p(prev),
-                                      p(done), p(eat), s))
+                                      p(done), p(eat), None, s))
         out = torch.zeros((E, N, 2), dtype=torch.int32, device=dev)
-        _lib.check(lib.swarm_pairwise(E, N, S, 5, 2, p(x), p(y), None, p(out), s))
+        nb = int(lib.swarm_pairwise_scratch_bytes(E, N))
+        scr = torch.empty(nb, dtype=torch.uint8, device=dev)
+        _lib.check(lib.swarm_pairwise(E, N, S, 5, 2, p(x), p(y), None, p(out), p(scr), nb, s))
     torch.cuda.synchronize()
     print("sanitize case done", flush=True)
 
