@@ -449,6 +449,7 @@ def main():
     ap.add_argument("--no-subconfigs", action="store_true", help="skip the sub-records of the other named configs")
     ap.add_argument("--path", default="auto", choices=["auto", "fused", "group", "staged", "staged_pairwise"])
     ap.add_argument("--vf", type=int, default=None, help="reward_type['vf_size'] (default None)")
+    ap.add_argument("--flags", type=int, default=0, help="swarm_config.flags (kernel A/B switches, include/swarm_abi.h)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="time the HBM-resident loop as CUDA-graph replays of --tape-steps steps (auto: when a step has "
                          "fewer than 1M agents and the host launch cost would dominate)")
@@ -482,7 +483,7 @@ def main():
     rng = np.random.default_rng(sorted(CONFIGS).index(args.config) * 1000 + rank)
     env = BatchedSwarmEnv(E, N, S, device=f"cuda:{local_rank}", auto_reset=True, track_stats=True, reset_slots=4,
                           per_agent=per_agent, debug_outputs=False, path=args.path,
-                          place_extra=cfg.get("place_extra"),
+                          place_extra=cfg.get("place_extra"), flags=args.flags,
                           env_offset=rank * E if (args.scaling == "strong" and world > 1) else 0)
     K = env.K
     place = torch.from_numpy(rng.integers(0, S, size=(env.R, E, env.PL), dtype=np.int16))

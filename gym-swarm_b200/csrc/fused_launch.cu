@@ -15,7 +15,10 @@ void choose_fused_shape(int N, int& lpe, int& apl) {
 
 template <int LPE, int APL>
 static cudaError_t prepare(const StepParams& p) {
-  return smem_opt_in(fused_step_kernel<LPE, APL, 0>, fused_smem_bytes<LPE, APL>(p, 0));
+  cudaError_t e = smem_opt_in(fused_step_kernel<LPE, APL, 0, 0>, fused_smem_bytes<LPE, APL>(p, 0));
+  if (e == cudaSuccess) e = smem_opt_in(fused_step_kernel<LPE, APL, 0, 1>, fused_smem_bytes<LPE, APL>(p, 0));
+  if (e == cudaSuccess) e = smem_opt_in(fused_step_kernel<LPE, APL, 0, 2>, fused_smem_bytes<LPE, APL>(p, 0));
+  return e;
 }
 
 template <int LPE, int APL>
@@ -23,7 +26,22 @@ static cudaError_t launch_step(const StepParams& p, cudaStream_t s) {
   using C = FusedCfg<LPE, APL>;
   const int envs_per_cta = C::WARPS * C::EPW;
   const int grid = (p.E + envs_per_cta - 1) / envs_per_cta;
-  fused_step_kernel<LPE, APL, 0><<<grid, C::WARPS * 32, fused_smem_bytes<LPE, APL>(p, 0), s>>>(p);
+  const int smem = fused_smem_bytes<LPE, APL>(p, 0);
+  if (p.split) {
+    fused_step_kernel<LPE, APL, 0, 1><<<grid, C::WARPS * 32, smem, s>>>(p);
+    fused_step_kernel<LPE, APL, 0, 2><<<grid, C::WARPS * 32, smem, s>>>(p);
+  } else {
+    fused_step_kernel<LPE, APL, 0, 0><<<grid, C::WARPS * 32, smem, s>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+template <int LPE, int APL>
+static cudaError_t launch_transition(const StepParams& p, cudaStream_t s) {
+  using C = FusedCfg<LPE, APL>;
+  const int envs_per_cta = C::WARPS * C::EPW;
+  const int grid = (p.E + envs_per_cta - 1) / envs_per_cta;
+  fused_step_kernel<LPE, APL, 0, 1><<<grid, C::WARPS * 32, fused_smem_bytes<LPE, APL>(p, 0), s>>>(p);
   return cudaGetLastError();
 }
 
@@ -49,6 +67,14 @@ cudaError_t fused_step_launch(int lpe, int apl, const StepParams& p, cudaStream_
   if (p.t_vf >= 0) return fused_vf_step_launch(lpe, apl, p, s);
   cudaError_t e = cudaSuccess;
 #define CALL(L, A) e = launch_step<L, A>(p, s)
+  FUSED_DISPATCH(lpe, apl, CALL);
+#undef CALL
+  return e;
+}
+
+cudaError_t fused_transition_launch(int lpe, int apl, const StepParams& p, cudaStream_t s) {
+  cudaError_t e = cudaSuccess;
+#define CALL(L, A) e = launch_transition<L, A>(p, s)
   FUSED_DISPATCH(lpe, apl, CALL);
 #undef CALL
   return e;

@@ -18,8 +18,12 @@
 #define FUSED_WARPS 4    // warps per CTA of the fused kernels
 #endif
 #ifndef FUSED_MINB
-#define FUSED_MINB 6     // minimum resident CTAs per SM the step kernel is compiled for (caps registers at 80:
-                         // measured on cfg3: 8 warps x 2 CTAs 0.339 ms, 4 x 5 0.328 ms, 4 x 6 0.316 ms per step)
+#define FUSED_MINB 8     // minimum resident CTAs per SM the step kernel is compiled for (caps registers at 64; measured
+                         // on cfg3, ms per step: round 1 8 warps x 2 CTAs 0.339, 4 x 5 0.328, 4 x 6 0.316; round 2 (per-env
+                         // scalars stored before the pair sweep) 4 x 6 0.283, 4 x 7 0.280, 4 x 8 0.272)
+#endif
+#ifndef FUSED_P1_MINB
+#define FUSED_P1_MINB 8  // the same for the transition launch of the two-launch step
 #endif
 #ifndef FUSED_VF_MINB
 #define FUSED_VF_MINB 5  // the same for the sparse visual-field variant (hit bookkeeping needs a few more registers)
@@ -468,6 +472,54 @@ __device__ __forceinline__ void vf_sparse_accumulate(const Seg<LPE>& g, const un
   }
 }
 
+// ---- near thresholds from the env's occupancy bitmap (reward launch of the two-launch step) ------------------------
+// After the collision rounds the N cells are distinct, so #{j : D_ij < t} (self included) is the popcount of the S x S
+// occupancy bitmap over the (2t-1)^2 box around agent i, clipped to the grid (plain Chebyshev, no wrap).  The reward
+// launch rebuilds the bitmap in a PADDED layout: rB = max radius zero rows above and below the grid and one zero word
+// after every row (stride S/32 + 1 words, S % 32 == 0), so that a row's box columns always sit in the 32-bit window
+// obtained by a funnel shift of two consecutive words and no row or word needs a range check.  Per (row, agent):
+// 2 LDS + SHF + LOP + POPC + 2 IADD, against ~9 instructions per PAIR WORD of the ring sweep: 9 rows x 4 agents per lane
+// instead of 136 word evaluations at N = S = 128, att = 5.  (In the single-launch kernel a box variant bought nothing
+// while the instruction cache was the limit -- round 1 measured 0.270 vs 0.275 ms; in the reward launch, which is issue
+// bound, instructions are time.)  The odd row stride also spreads the gathers over the banks.
+template <int APL>
+__device__ __forceinline__ void box_near_counts(const unsigned* __restrict__ bits, int S, int rR, int rA,
+                                                const int (&x)[APL], const int (&y)[APL], unsigned (&cR)[APL],
+                                                unsigned (&cA)[APL]) {
+  const int rB = max(max(rR, rA), 0), rS = min(rR, rA);   // uniform over the warp (kernel parameters); rB = layout radius
+  const int stride = (S >> 5) + 1;
+  const unsigned* ptr[APL];
+  unsigned sh[APL], mB[APL], mS[APL], cB[APL], cS[APL];
+#pragma unroll
+  for (int k = 0; k < APL; ++k) {
+    const int lo_c = max(x[k] - rB, 0);
+    sh[k] = (unsigned)(lo_c & 31);
+    ptr[k] = bits + y[k] * stride + (lo_c >> 5);         // padded row y = grid row y - rB: the first row of the box
+    // the boxes' columns inside the window that starts at column lo_c (a radius of -1 is the empty box of t = 0)
+    const int hB = min(x[k] + rB, S - 1), lS = max(x[k] - rS, 0), hS = min(x[k] + rS, S - 1);
+    mB[k] = max(rR, rA) >= 0 ? (0xFFFFFFFFu >> (31 - (hB - lo_c))) : 0u;
+    mS[k] = rS >= 0 ? ((0xFFFFFFFFu >> (31 - (hS - lS))) << (lS - lo_c)) : 0u;
+    cB[k] = 0u;
+    cS[k] = 0u;
+  }
+#pragma unroll 1
+  for (int i = 0; i <= 2 * rB; ++i) {
+    const bool small = i >= rB - rS && i <= rB + rS;     // uniform: rows that belong to the smaller box as well
+#pragma unroll
+    for (int k = 0; k < APL; ++k) {
+      const unsigned win = __funnelshift_r(ptr[k][0], ptr[k][1], sh[k]);
+      cB[k] += __popc(win & mB[k]);
+      if (small) cS[k] += __popc(win & mS[k]);
+      ptr[k] += stride;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < APL; ++k) {
+    cA[k] = rA >= rR ? cB[k] : cS[k];
+    cR[k] = rA >= rR ? cS[k] : cB[k];
+  }
+}
+
 // ---- far thresholds from the border agents only ------------------------------------------------------------------
 // For a threshold t > S/2 a pair with D >= t needs |dx| >= t or |dy| >= t, i.e. one agent within b = S - t cells of a
 // border and the other within b cells of the OPPOSITE border.  So #{j : D_ij < t} = N-1 for every agent outside the
@@ -508,11 +560,15 @@ __device__ __forceinline__ void far_border_counts(const StepParams& p, const Seg
   }
   g.sync();
   const int nLX = (int)sfar[0], nHX = (int)sfar[1], nLY = (int)sfar[2], nHY = (int)sfar[3];
-  const int totX = nLX * nHX, tot = totX + nLY * nHY;
+  // candidate (ii, jj) of a pass = (q >> sh, q & (2^sh - 1)) with 2^sh >= its high-band list (no division; at most half
+  // of the slots of a pass are padding)
+  const int shX = 32 - __clz(max(nHX, 1) - 1), shY = 32 - __clz(max(nHY, 1) - 1);
+  const int totX = nHX ? nLX << shX : 0, tot = totX + (nHY ? nLY << shY : 0);
   for (int q = g.li; q < tot; q += LPE) {
     const bool yp = q >= totX;
-    const int qq = yp ? q - totX : q, nh = yp ? nHY : nHX;
-    const int ii = qq / nh, jj = qq - ii * nh;
+    const int qq = yp ? q - totX : q, sh = yp ? shY : shX, nh = yp ? nHY : nHX;
+    const int ii = qq >> sh, jj = qq & ((1 << sh) - 1);
+    if (jj >= nh) continue;
     const unsigned short* __restrict__ lst = yp ? yl : xl;
     const int a = lst[ii], c = lst[NMAX - 1 - jj];
     // agent n sits in half n % 2 of pair word (n % APL / 2) * LPE + n / APL (the ring sweep's [word][lane] layout)
@@ -603,9 +659,17 @@ __device__ __noinline__ void terminal_step(const StepParams& p, const Seg<LPE>& 
   }
 }
 
-template <int LPE, int APL, int VFM>
+// PHASE 0: the whole step in one launch.  PHASE 1 / 2: the same step as two launches -- 1 = transition (move, collision
+// re-draws, predator, termination, commit, terminal step + auto-reset), 2 = reward of the running episodes, reading the
+// committed positions and the effective actions phase 1 left in p.eff_buf.  One launch is the shorter latency (small
+// batches, CUDA-graph rollouts); for batches of many waves the split wins because the step's straight-line code
+// (~48 KB executed per env) no longer fits the SM's 32 KB instruction cache when 32 resident warps sit in unrelated
+// phases of it (ncu on the fused kernel at cfg3: "no instruction" was the top stall reason, 3.1 of 7.2 warps per
+// scheduler), while each half does.
+template <int LPE, int APL, int VFM, int PHASE>
 __global__ void __launch_bounds__(FusedCfg<LPE, APL>::WARPS * 32,
-                                  (APL == 8 || VFM == 1) ? 3 : (VFM == 2 ? FUSED_VF_MINB : FUSED_MINB))
+                                  PHASE == 1 ? (APL == 8 ? 4 : FUSED_P1_MINB)
+                                             : (APL == 8 || VFM == 1) ? 3 : (VFM == 2 ? FUSED_VF_MINB : FUSED_MINB))
 fused_step_kernel(const __grid_constant__ StepParams p) {
   using C = FusedCfg<LPE, APL>;
   constexpr bool HAS_VF = VFM != 0;
@@ -631,8 +695,8 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
   unsigned* sfar = reinterpret_cast<unsigned*>(wbase + C::pair_bytes() + C::vf_bytes(VFM)) + g.seg * C::far_env_words();
   unsigned* sbit = reinterpret_cast<unsigned*>(wbase + C::pair_bytes() + C::vf_bytes(VFM) + C::far_bytes()) +
                    g.seg * p.bitmap_words;
-  if (p.bitmap_words) {
-    for (int w = g.li; w < p.bitmap_words; w += LPE) sbit[w] = 0u;
+  if ((PHASE != 2 || (VFM == 0 && p.box_near)) && p.bitmap_words) {   // (a multiple of 4 words, 16-byte aligned)
+    for (int w = g.li; w < (p.bitmap_words >> 2); w += LPE) reinterpret_cast<uint4*>(sbit)[w] = make_uint4(0u, 0u, 0u, 0u);
   }
   if (env >= p.E) return;
   g.sync();
@@ -640,7 +704,10 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
   const int i0 = g.li * APL;
   const size_t base = (size_t)env * (size_t)N;
   const bool vec = (N % APL) == 0;
+  int nx[APL], ny[APL];
+  unsigned effp = 0u;                                  // the effective actions of the owned agents, 4 bits each
 
+  if constexpr (PHASE != 2) {
   // every load the first phases need is issued here, before the first dependent branch, so that one DRAM round trip
   // covers all of it
   const int is_frozen = p.frozen[env];
@@ -650,6 +717,12 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
   load_u8<APL>(p.actions + base, i0, N, vec, act);
   int px = p.px[env], py = p.py[env];
   int target = p.target[env];
+  // the first 16 re-draw actions of the env (one broadcast LDG.128) ride on the same round trip: a colliding env
+  // (~45 % of them at cfg3, ~1 draw each) would otherwise pay a second, dependent trip to DRAM in the middle of the step
+  const uint8_t* __restrict__ slab = p.slab ? p.slab + (size_t)env * (size_t)p.K : nullptr;
+  const bool slab_pre = slab != nullptr && p.K >= 16 && (((uintptr_t)slab) & 15) == 0;
+  uint4 slab16 = make_uint4(0u, 0u, 0u, 0u);
+  if (slab_pre) slab16 = *reinterpret_cast<const uint4*>(slab);
 
   if (is_frozen) {                          // SDE:233-234: finished episode, auto-reset off: nothing moves, every output
     if (g.li == 0) {                        // of the step is defined (zero reward, the predator where it stands)
@@ -681,7 +754,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
   unsigned err = 0;
 
   // ---- move + collision re-draw rounds (SDE:237-255) --------------------------------------------
-  int eff[APL], nx[APL], ny[APL];
+  int eff[APL];
   {
     bool bad = false;
 #pragma unroll
@@ -689,7 +762,6 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
     if (g.any(bad)) err |= SWARM_ERR_BAD_ACTION;
   }
   int cur = 0;
-  const uint8_t* __restrict__ slab = p.slab ? p.slab + (size_t)env * (size_t)p.K : nullptr;
   for (;;) {
 #pragma unroll
     for (int k = 0; k < APL; ++k) {
@@ -712,7 +784,10 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
     for (int k = 0; k < APL; ++k) {
       const int e = c[k] - 1;
-      if (e > 0) eff[k] = tape_slab(p, slab, env, cur + off + e - 1);   // SDE:250-252: last of its c-1 draws wins
+      if (e > 0) {                                       // SDE:250-252: last of its c-1 draws wins
+        const int d = cur + off + e - 1;
+        eff[k] = (slab_pre && d < 16) ? (int)((word_of(slab16, d >> 2) >> (8 * (d & 3))) & 7u) : tape_slab(p, slab, env, d);
+      }
       off += e;
     }
     cur += L;
@@ -769,15 +844,28 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
     p.target[env] = target;
     p.orient[env] = (uint8_t)orient;
   }
+  if constexpr (PHASE == 1) {                          // hand the effective actions to the reward launch
+    if (p.eff_buf != p.eff_action) store_u8<APL>(p.eff_buf + base, i0, N, vec, eff);
+    return;
+  } else {
+#pragma unroll
+    for (int k = 0; k < APL; ++k) effp |= (unsigned)eff[k] << (4 * k);
+  }
+  } else {                                             // PHASE 2: the reward launch picks the running episodes up
+    if (p.done[env]) return;                           // finished (or frozen): phase 1 wrote the terminal outputs
+    int e2[APL];
+    load_i16<APL>(p.x + base, i0, N, vec, nx);         // committed NEW positions
+    load_i16<APL>(p.y + base, i0, N, vec, ny);
+    load_u8<APL>(p.eff_buf + base, i0, N, vec, e2);
+#pragma unroll
+    for (int k = 0; k < APL; ++k) effp |= (unsigned)e2[k] << (4 * k);
+  }
 
   // ---- reward (SDE:330-379) ---------------------------------------------------------------------
   unsigned aR[APL], aA[APL], aRf[APL], aAf[APL];       // threshold counts of each owned agent, self included
   unsigned aV[APL], accA[APL], accD[APL];
 #pragma unroll
   for (int k = 0; k < APL; ++k) aR[k] = aA[k] = aRf[k] = aAf[k] = aV[k] = accA[k] = accD[k] = 0u;
-  unsigned effp = 0u;                                  // the effective actions, 4 bits each (eff[] dies here)
-#pragma unroll
-  for (int k = 0; k < APL; ++k) effp |= (unsigned)eff[k] << (4 * k);
   {
     // stage the env's positions as packed pair words {x2, y2, -x2, -y2}; padding agents sit at x=-S
     unsigned XI[APL], YI[APL], NXI[APL], NYI[APL];
@@ -807,7 +895,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
       if constexpr (HAS_VF) {
 #pragma unroll
         for (int k = 0; k < APL; ++k) {
-          const int a = eff[k];
+          const int a = (int)((effp >> (4 * k)) & 15u);
           const bool mover = (i0 + k < N) && a < 8;
           const int mx = mover ? move_dx(a) : 0, my = mover ? move_dy(a) : 0;
           const bool diag = (a & 1) != 0;
@@ -835,7 +923,20 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
       // ALU pipe to the DPX ops.
       const unsigned one = (unsigned)p.one, c256 = (unsigned)p.one << 8;
       int nhit = 0;
-      if (p.far_border)      // both far thresholds > S/2: they come from the border pass below, the sweep carries {rep, att}
+      if (PHASE == 2 && VFM == 0 && p.box_near) {
+        // reward launch: {rep, att} from box popcounts on the rebuilt (padded) occupancy bitmap; far thresholds below
+        const int rB = max(max(p.t_rep, p.t_att) - 1, 0), bstride = (S >> 5) + 1;
+        int bx[APL], by[APL];
+#pragma unroll
+        for (int k = 0; k < APL; ++k) {
+          const bool v = i0 + k < N;
+          bx[k] = v ? nx[k] : 0;             // padding agents read (in-range) rows too: the row loop stays convergent
+          by[k] = v ? ny[k] : 0;
+          if (v) atomicOr(&sbit[(ny[k] + rB) * bstride + (nx[k] >> 5)], 1u << (nx[k] & 31));
+        }
+        g.sync();
+        box_near_counts<APL>(sbit, S, p.t_rep - 1, p.t_att - 1, bx, by, aR, aA);
+      } else if (p.far_border)      // both far thresholds > S/2: they come from the border pass below, the sweep carries {rep, att}
         ring_sweep<LPE, APL, false, VF_SPARSE>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf, TV, shits, nhit);
       else
         ring_sweep<LPE, APL, true, VF_SPARSE>(g, spw, XI, YI, NXI, NYI, TR, TA, TRf, TAf, one, c256, aR, aA, aRf, aAf, TV, shits, nhit);
@@ -918,9 +1019,9 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
     if (v) {
       s_rep += t.rep_i; s_att += t.att_i; s_P += P; s_Q += Q; s_vis += vis;
       if (p.agent_reward) {                                 // SDE:371-379
-        const double a_rep = p.w_rep * (double)t.rep_i * p.inv_nn;
-        const double a_att = p.w_att * (double)t.att_i * p.inv_nn;
-        const double a_ali = p.w_ali * (-t.una) * p.inv_nn;
+        const double a_rep = (p.w_rep * (double)t.rep_i) * p.inv_nn;
+        const double a_att = (p.w_att * (double)t.att_i) * p.inv_nn;
+        const double a_ali = (p.w_ali * (-t.una)) * p.inv_nn;
         reinterpret_cast<float4*>(p.agent_reward)[base + i0 + k] =
             make_float4((float)a_att, (float)a_rep, (float)a_ali, (float)(a_rep + a_att + a_ali));
       }

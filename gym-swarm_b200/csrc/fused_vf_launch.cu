@@ -16,9 +16,11 @@ static int vf_mode(const StepParams& p) {
 
 template <int LPE, int APL>
 static cudaError_t prepare(const StepParams& p) {
-  cudaError_t e = smem_opt_in(fused_step_kernel<LPE, APL, 1>, fused_smem_bytes<LPE, APL>(p, 1));
+  cudaError_t e = smem_opt_in(fused_step_kernel<LPE, APL, 1, 0>, fused_smem_bytes<LPE, APL>(p, 1));
+  if (e == cudaSuccess) e = smem_opt_in(fused_step_kernel<LPE, APL, 1, 2>, fused_smem_bytes<LPE, APL>(p, 1));
   if constexpr (FusedCfg<LPE, APL>::ring_ok()) {
-    if (e == cudaSuccess) e = smem_opt_in(fused_step_kernel<LPE, APL, 2>, fused_smem_bytes<LPE, APL>(p, 2));
+    if (e == cudaSuccess) e = smem_opt_in(fused_step_kernel<LPE, APL, 2, 0>, fused_smem_bytes<LPE, APL>(p, 2));
+    if (e == cudaSuccess) e = smem_opt_in(fused_step_kernel<LPE, APL, 2, 2>, fused_smem_bytes<LPE, APL>(p, 2));
   }
   return e;
 }
@@ -30,8 +32,15 @@ static cudaError_t launch_step(const StepParams& p, cudaStream_t s) {
   const int grid = (p.E + envs_per_cta - 1) / envs_per_cta;
   const int vfm = vf_mode<LPE, APL>(p);
   const int smem = fused_smem_bytes<LPE, APL>(p, vfm);
-  if (vfm == 1) fused_step_kernel<LPE, APL, 1><<<grid, C::WARPS * 32, smem, s>>>(p);
-  else if constexpr (C::ring_ok()) fused_step_kernel<LPE, APL, 2><<<grid, C::WARPS * 32, smem, s>>>(p);
+  if (p.split) {                                   // transition launch (no visual-field code in it), then the reward
+    const cudaError_t e = fused_transition_launch(LPE, APL, p, s);
+    if (e != cudaSuccess) return e;
+    if (vfm == 1) fused_step_kernel<LPE, APL, 1, 2><<<grid, C::WARPS * 32, smem, s>>>(p);
+    else if constexpr (C::ring_ok()) fused_step_kernel<LPE, APL, 2, 2><<<grid, C::WARPS * 32, smem, s>>>(p);
+    return cudaGetLastError();
+  }
+  if (vfm == 1) fused_step_kernel<LPE, APL, 1, 0><<<grid, C::WARPS * 32, smem, s>>>(p);
+  else if constexpr (C::ring_ok()) fused_step_kernel<LPE, APL, 2, 0><<<grid, C::WARPS * 32, smem, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -35,6 +35,7 @@ void choose_fused_shape(int N, int& lpe, int& apl);
 // of every step kernel of the shape (both files) once per handle, so that swarm_step itself only launches.
 cudaError_t fused_prepare(int lpe, int apl, const StepParams& p);
 cudaError_t fused_step_launch(int lpe, int apl, const StepParams& p, cudaStream_t s);   // forwards vf_size steps
+cudaError_t fused_transition_launch(int lpe, int apl, const StepParams& p, cudaStream_t s);   // first of two launches (p.split)
 cudaError_t fused_reset_launch(int lpe, int apl, const StepParams& p, const uint8_t* mask, int zero_counts, cudaStream_t s);
 
 // fused_vf_launch.cu: vf_size steps (dense and sparse visual-field modes)

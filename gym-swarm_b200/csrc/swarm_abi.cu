@@ -29,6 +29,9 @@ struct Ctx {
   bool tiny = false;          // thread-per-env kernel (steps without a visual-field gate)
   int tiny_n = 8;             // its register capacity: 8 or 16 agents
   bool force_pairwise = false;  // SWARM_PATH_STAGED_PAIRWISE: never use the box-count reward path
+  bool split = false;         // lane-group kernels: two launches per step (transition, reward), see fused_step_kernel
+  bool box_near = false;      // ... and its reward launch may count {rep, att} by box popcounts
+  uint8_t* eff_scratch = nullptr;   // [E,N] effective actions between the two launches (when the caller binds no eff_action)
   int lpe = 0, apl = 0;
   int bitmap_words = 0;
   int launches = 0;
@@ -57,6 +60,7 @@ struct Ctx {
   bool nccl_owned = false;
   ~Ctx() {                     // owns only the library scratch; state / tapes / outputs belong to the caller
     if (scratch_block) cudaFree(scratch_block);
+    if (eff_scratch) cudaFree(eff_scratch);
     if (d_stats) cudaFree(d_stats);
     if (d_partial) cudaFree(d_partial);
     if (h_stats) cudaFreeHost(h_stats);
@@ -398,6 +402,19 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
     const long long cells = (long long)cfg->grid_size * cfg->grid_size;
     const long long words = ((cells + 31) / 32 + 3) / 4 * 4;
     c->bitmap_words = (words <= 2048 && cfg->num_agents >= 16) ? (int)words : 0;
+    {
+      // the reward launch of the two-launch step counts {rep, att} by box popcounts on a padded copy of the bitmap
+      // (fused_step.cuh, box_near_counts) when rows are word aligned, both radii fit a 32-bit window and the far
+      // thresholds come from the border pass; the per-env region is sized for the larger of the two layouts
+      StepParams tp;
+      memset(&tp, 0, sizeof(tp));
+      fill_thresholds(tp, cfg->num_agents, cfg->grid_size, cfg->attraction_thresh, cfg->repulsion_thresh, cfg->flags);
+      const int S = cfg->grid_size;
+      const int bw = box_near_words(S, std::max(std::max(tp.t_rep, tp.t_att) - 1, 0));
+      c->box_near = c->bitmap_words > 0 && (S % 32) == 0 && tp.t_rep <= 16 && tp.t_att <= 16 && tp.far_border && bw <= 2048 &&
+                    !(cfg->flags & SWARM_FLAG_NO_BOX_NEAR);
+      if (c->box_near) c->bitmap_words = std::max(c->bitmap_words, bw);
+    }
     // (A box-count variant of the reward on this per-env bitmap was measured for the lane-group kernels in round 1:
     // 0.42-0.45 ms / step at cfg3 against 0.275 for the ring sweep -- the shared-memory gathers of 32 lanes into random
     // bitmap rows serialise on bank conflicts.  It pays off from N ~ 1000 up, which is the staged path; removed here.)
@@ -416,6 +433,17 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
     else if (c->coll_bm_words > 0) c->path_name = "staged+bitmap";
   }
   if (c->fused) {
+    // One launch per step for small batches (latency, graph rollouts); two launches once the batch is many waves deep
+    // and the instruction-cache footprint of the whole step is what limits the SMs (measured at cfg3).
+    const long long agents = (long long)cfg->num_envs * cfg->num_agents;
+    c->split = agents >= (1LL << 22);   // measured: 1 M agents (8,192 x 128) 0.042 ms in one launch vs 0.046 in two; 8.4 M 0.272 vs 0.248
+    if (cfg->flags & SWARM_FLAG_FUSED_SPLIT) c->split = true;
+    if (cfg->flags & SWARM_FLAG_FUSED_ONE_LAUNCH) c->split = false;
+    if (c->split) {
+      const cudaError_t ae = cudaMalloc(&c->eff_scratch, (size_t)agents + 16);
+      if (ae != cudaSuccess) { delete c; return fail(nullptr, SWARM_E_CUDA, "swarm_create: cudaMalloc (effective actions)"); }
+      if (!c->tiny) c->path_name += " x2 launches";
+    }
     const StepParams p0 = base_params(c);
     const cudaError_t pe = fused_prepare(c->lpe, c->apl, p0);
     if (pe != cudaSuccess) {
@@ -575,8 +603,11 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     return SWARM_OK;
   }
   if (c->fused) {
+    p.split = c->split ? 1 : 0;
+    p.eff_buf = out->eff_action ? out->eff_action : c->eff_scratch;
+    p.box_near = (c->split && c->box_near && !vf) ? 1 : 0;
     CUDA_TRY(c, fused_step_launch(c->lpe, c->apl, p, s));
-    c->launches = 1;
+    c->launches = c->split ? 2 : 1;
     return SWARM_OK;
   }
   // ---- staged path -------------------------------------------------------------------------------

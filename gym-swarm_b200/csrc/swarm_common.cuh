@@ -34,6 +34,10 @@ struct BoxPlan {
 };
 
 
+// words of the padded per-env bitmap the fused reward launch counts boxes on (fused_step.cuh, box_near_counts):
+// rB zero rows above and below the grid, one zero word after every row
+__host__ __device__ inline int box_near_words(int S, int rB) { return ((S + 2 * rB) * ((S >> 5) + 1) + 3) / 4 * 4; }
+
 // ----------------------------------------------------------------------------------------------
 // Kernel parameter block (by-value kernel argument).
 // ----------------------------------------------------------------------------------------------
@@ -59,6 +63,8 @@ struct StepParams {
   unsigned env_offset;                 // added to the env index in every Philox counter (swarm_config.env_offset)
   int one;           // runtime 1: `v * one + acc` compiles to IMAD (FMA pipe) instead of IADD3 (ALU pipe)
   int vf_dense;      // SWARM_FLAG_VF_DENSE
+  int split;         // lane-group kernels: the step as two launches (transition, reward); see fused_step_kernel
+  int box_near;      // reward launch: {rep, att} counts from box popcounts on the occupancy bitmap (fused_step.cuh)
   // state
   int16_t *x, *y, *px, *py;
   int32_t* target;
@@ -83,6 +89,8 @@ struct StepParams {
   int32_t* agent_counts;
   uint8_t* eff_action;
   int16_t* agent_terms;   // [E,N,4] (rew_rep_i, rew_attr_i, U_i = 2 vis - P, Q_i)
+  uint8_t* eff_buf;       // two-launch fused step: effective actions from the transition launch to the reward launch
+                          // (= eff_action when the caller binds it, else library scratch)
 };
 
 // ----------------------------------------------------------------------------------------------

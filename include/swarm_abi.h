@@ -67,6 +67,10 @@ extern "C" {
  * kernel variant (read once in swarm_create; the library reads no environment variables) */
 #define SWARM_FLAG_NO_FAR_BORDER 1u /* keep all four thresholds in the pair sweep (no border pass for the far ones) */
 #define SWARM_FLAG_VF_DENSE 4u      /* vf_size steps of the lane-group kernels: always the dense gate sweep */
+#define SWARM_FLAG_FUSED_SPLIT 8u   /* lane-group kernels: always two launches per step (transition, then reward); the default
+                                       does that from 2^22 agents per handle up (instruction-cache footprint) */
+#define SWARM_FLAG_FUSED_ONE_LAUNCH 16u /* lane-group kernels: always the single fused launch */
+#define SWARM_FLAG_NO_BOX_NEAR 32u  /* reward launch of the two-launch step: ring sweep even where box popcounts apply */
 
 typedef struct swarm_config {
   int32_t abi_version;       /* SWARM_ABI_VERSION */

@@ -80,14 +80,14 @@ def test_golden_thread_per_env_kernel_16(name):
 
 def _oracle_lockstep(E, N, S, T, seed, path="auto", att=5, rep=2, eat=-10.0, vf=None, n_actions=8, K=None, KR=None,
                      weights=(1.0, 1.0, 1.0), auto_reset=True, check_agents=True, agent_out=True, flags=0,
-                     tiny16_min_envs=0):
+                     tiny16_min_envs=0, KP=8):
     from gym_swarm_b200 import tapes
     from gym_swarm_b200.envs import BatchedSwarmEnv
     from oracle import swarm_oracle as so
     rng = np.random.default_rng(seed)
     env = BatchedSwarmEnv(E, N, S, att, rep, eat, auto_reset=auto_reset, slab_len=K, place_extra=KR, reset_slots=3,
                           per_agent=agent_out, debug_outputs=agent_out, path=path, flags=flags,
-                          tiny16_min_envs=tiny16_min_envs)
+                          tiny16_min_envs=tiny16_min_envs, pred_attempts=KP)
     check_agents = check_agents and agent_out
     rt = tapes.make_reset_tapes(rng, env.R, E, N, S, KR=env.KR, KP=env.KP)
     st = tapes.make_step_tapes(rng, T, E, N, K=env.K, n_actions=n_actions)
@@ -190,6 +190,36 @@ def test_fused_reward_by_ring_sweep(N, S):
     dense = S * S < 4 * N
     _oracle_lockstep(E=9, N=N, S=S, T=12, seed=N * 3 + S, n_actions=9, K=512 if dense else None,
                      KR=2000 if dense else None, weights=(0.5, 1.0, 0.25))
+
+
+@pytest.mark.parametrize("N,S,att,rep", [(16, 32, 5, 2), (24, 12, 5, 2), (33, 64, 5, 2), (64, 64, 9, 3), (100, 96, 16, 1),
+                                         (128, 128, 5, 2), (128, 128, 2, 5), (128, 128, 0, 0), (128, 128, 17, 2),
+                                         (255, 64, 5, 2), (200, 300, 5, 2), (12, 5, 3, 1), (128, 256, 16, 16)])
+@pytest.mark.parametrize("ring", [False, True])
+def test_two_launch_step(N, S, att, rep, ring):
+    """The lane-group step as two launches (transition, then reward; the default from 2^22 agents per handle up, forced
+    here by SWARM_FLAG_FUSED_SPLIT): reward counts by box popcounts on the rebuilt occupancy bitmap where they apply
+    (word-aligned rows, radii <= 15, far thresholds from the border pass) and by the ring sweep otherwise / when
+    SWARM_FLAG_NO_BOX_NEAR asks for it; terminal steps and auto-resets come from the transition launch."""
+    from gym_swarm_b200 import _lib
+    dense = S * S < 4 * N
+    _oracle_lockstep(E=11, N=N, S=S, T=12, seed=N * 5 + S + att, n_actions=9, att=att, rep=rep, K=512 if dense else None,
+                     KR=2000 if dense else None, KP=64 if dense else 8, weights=(0.5, 1.0, 0.25),
+                     flags=_lib.FLAG_FUSED_SPLIT | (_lib.FLAG_NO_BOX_NEAR if ring else 0))
+
+
+@pytest.mark.parametrize("N,S,vf", [(16, 32, 2), (60, 64, 5), (128, 128, 5), (37, 50, 4)])
+@pytest.mark.parametrize("dense", [False, True])
+def test_two_launch_step_with_vf(N, S, vf, dense):
+    from gym_swarm_b200 import _lib
+    _oracle_lockstep(E=13, N=N, S=S, T=6, seed=N + S + vf, vf=vf, weights=(0.5, 1.0, 2.0), n_actions=9,
+                     flags=_lib.FLAG_FUSED_SPLIT | (_lib.FLAG_VF_DENSE if dense else 0))
+
+
+def test_two_launch_step_without_debug_outputs():
+    """No eff_action bound: the effective actions travel between the two launches in the library's own scratch."""
+    from gym_swarm_b200 import _lib
+    _oracle_lockstep(E=40, N=128, S=128, T=8, seed=3, n_actions=9, flags=_lib.FLAG_FUSED_SPLIT, agent_out=False)
 
 
 @pytest.mark.parametrize("N,S", [(16, 32), (24, 12), (64, 64), (60, 11), (128, 128)])
