@@ -620,13 +620,17 @@ __device__ __forceinline__ void predator_frozen(const PredIO& io, int env) {
   if (io.step_target) io.step_target[env] = io.target[env];
 }
 
+// element e (0..7) of a packed vector pair as a cell word (x | y << 16)
+__device__ __forceinline__ unsigned cell8(const uint4& xv, const uint4& yv, int e) {
+  const int h = e >> 1;
+  const unsigned wx = h == 0 ? xv.x : (h == 1 ? xv.y : (h == 2 ? xv.z : xv.w));
+  const unsigned wy = h == 0 ? yv.x : (h == 1 ? yv.y : (h == 2 ? yv.z : yv.w));
+  const int sh = 16 * (e & 1);
+  return ((wx >> sh) & 0xFFFFu) | (((wy >> sh) & 0xFFFFu) << 16);
+}
 __device__ __forceinline__ void predator_write(const PredIO& io, int env, int ppx, int ppy, int px, int py, int target,
                                                int orient, unsigned hit) {
   const bool done = hit != 0xFFFFFFFFu;
-  if (io.tcell) {   // the target's NEW cell = what the next step pursues; the line was just streamed (L1 hit)
-    const size_t t = (size_t)env * (size_t)io.N + (size_t)target;
-    reinterpret_cast<unsigned*>(io.tcell)[env] = pack2(io.xn[t], io.yn[t]);
-  }
   io.px[env] = (int16_t)px;
   io.py[env] = (int16_t)py;
   io.target[env] = target;
@@ -644,10 +648,16 @@ __device__ __forceinline__ void predator_write(const PredIO& io, int env, int pp
 // registers, so that more envs are in flight per SM).  N % 8 == 0.  Round trip 1 is the predator's state (tiny, coalesced over envs);
 // round trip 2 issues the bulk together: NEW positions, the stored target's OLD cell, and -- for the envs that
 // retarget -- the OLD positions.
-constexpr int PRED_VPL = 4;
+#ifndef PRED_VPL_DEFAULT
+#define PRED_VPL_DEFAULT 4
+#endif
+constexpr int PRED_VPL = PRED_VPL_DEFAULT;
 
+#ifndef PRED_THREADS
+#define PRED_THREADS 64    // measured at 1 M x 128: 256 threads 0.159 ms, 128 0.153, 64 0.147 (finer CTAs fill the SMs more evenly)
+#endif
 template <int LPE, int VPL = PRED_VPL>
-__global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
+__global__ void __launch_bounds__(PRED_THREADS) predator_group_kernel(const PredIO io) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int env = gtid / LPE;
   const int li = threadIdx.x % LPE;
@@ -665,10 +675,14 @@ __global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
   const uint4* __restrict__ yn4 = reinterpret_cast<const uint4*>(io.yn) + vbase;
   const uint4* __restrict__ xo4 = reinterpret_cast<const uint4*>(io.xo) + vbase;
   const uint4* __restrict__ yo4 = reinterpret_cast<const uint4*>(io.yo) + vbase;
+  // ONE round trip for everything that does not depend on the retarget draw: the predator's state, the cached target
+  // cell (4 B, read even by the ~10 % of envs that will retarget: cheaper than a dependent second trip for all the
+  // others) and the NEW positions
   int px = io.px[env], py = io.py[env];
   int target = io.target[env];
   const int retarget = pred_retarget(io, env);
-  target = min(max(target, 0), N - 1);
+  unsigned tc = 0u;
+  if (io.tcell) tc = reinterpret_cast<const unsigned*>(io.tcell)[env];
   uint4 xn[VPL], yn[VPL];
 #pragma unroll
   for (int q = 0; q < VPL; ++q) {
@@ -676,29 +690,38 @@ __global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
     if (v < NV) { xn[q] = __ldg(xn4 + v); yn[q] = __ldg(yn4 + v); }
     else { xn[q] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu); yn[q] = xn[q]; }
   }
-  int tx = 0, ty = 0;
-  if (!retarget) {
-    if (io.tcell) {                                            // coalesced over envs, no dependent random read
-      const unsigned tc = reinterpret_cast<const unsigned*>(io.tcell)[env];
-      tx = (int)(int16_t)(tc & 0xFFFFu); ty = (int)(int16_t)(tc >> 16);
-    } else {
-      tx = io.xo[(size_t)env * N + target];
-      ty = io.yo[(size_t)env * N + target];
-    }
+  target = min(max(target, 0), N - 1);
+  int tx = (int)(int16_t)(tc & 0xFFFFu), ty = (int)(int16_t)(tc >> 16);
+  if (!retarget && !io.tcell) {
+    tx = io.xo[(size_t)env * N + target];
+    ty = io.yo[(size_t)env * N + target];
   }
   const int ppx = px, ppy = py;
-  if (retarget) {                                              // SDE:138-140
+  if (retarget) {                                              // SDE:138-140: second trip, the OLD positions
     unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;
-#pragma unroll 4
-    for (int v = li; v < NV; v += LPE) nn_keys8(__ldg(xo4 + v), __ldg(yo4 + v), px, py, v * 8, klo, khi);
+    if constexpr (LPE == 1 && VPL <= 2) {                      // the whole env sits in this thread's registers
+      uint4 xo[VPL], yo[VPL];
 #pragma unroll
-    for (int d = LPE / 2; d > 0; d >>= 1) {
-      klo = min(klo, __shfl_xor_sync(gmask, klo, d));
-      khi = min(khi, __shfl_xor_sync(gmask, khi, d));
+      for (int q = 0; q < VPL; ++q) { xo[q] = __ldg(xo4 + q); yo[q] = __ldg(yo4 + q); }
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) nn_keys8(xo[q], yo[q], px, py, q * 8, klo, khi);
+      target = nn_pick(klo, khi, S);
+      unsigned cell = cell8(xo[0], yo[0], target & 7);         // the new target's cell, selected from the registers
+      if constexpr (VPL == 2) { if (target >= 8) cell = cell8(xo[1], yo[1], target & 7); }
+      tx = (int)(int16_t)(cell & 0xFFFFu);
+      ty = (int)(int16_t)(cell >> 16);
+    } else {
+#pragma unroll 4
+      for (int v = li; v < NV; v += LPE) nn_keys8(__ldg(xo4 + v), __ldg(yo4 + v), px, py, v * 8, klo, khi);
+#pragma unroll
+      for (int d = LPE / 2; d > 0; d >>= 1) {
+        klo = min(klo, __shfl_xor_sync(gmask, klo, d));
+        khi = min(khi, __shfl_xor_sync(gmask, khi, d));
+      }
+      target = nn_pick(klo, khi, S);
+      tx = io.xo[(size_t)env * N + target];                    // L1/L2 hit: the line was just streamed
+      ty = io.yo[(size_t)env * N + target];
     }
-    target = nn_pick(klo, khi, S);
-    tx = io.xo[(size_t)env * N + target];                      // L1/L2 hit: the line was just streamed
-    ty = io.yo[(size_t)env * N + target];
   }
   int orient;
   pursue(px, py, tx, ty, S, px, py, orient);
@@ -710,6 +733,10 @@ __global__ void __launch_bounds__(256) predator_group_kernel(const PredIO io) {
   for (int v = li + VPL * LPE; v < NV; v += LPE) hit8(__ldg(xn4 + v), __ldg(yn4 + v), kx, ky, v * 8, hit);
 #pragma unroll
   for (int d = LPE / 2; d > 0; d >>= 1) hit = min(hit, __shfl_xor_sync(gmask, hit, d));
+  if (io.tcell && li == 0) {   // the target's NEW cell = what the next step pursues; the line was just streamed (L1 hit)
+    const size_t t = (size_t)env * (size_t)N + (size_t)target;   // (selecting it from the prefetched registers instead
+    reinterpret_cast<unsigned*>(io.tcell)[env] = pack2(io.xn[t], io.yn[t]);   // pushed the vectors into local memory)
+  }
   if (li == 0) predator_write(io, env, ppx, ppy, px, py, target, orient, hit);
 }
 
@@ -730,8 +757,11 @@ __global__ void __launch_bounds__(256) predator_block_kernel(const PredIO io) {
     const uint4* __restrict__ yo4 = reinterpret_cast<const uint4*>(io.yo) + vbase;
     int px = io.px[env], py = io.py[env];
     int target = io.target[env];
+    unsigned tc = 0u;
+    if (io.tcell) tc = reinterpret_cast<const unsigned*>(io.tcell)[env];
     const int ppx = px, ppy = py;
-    if (pred_retarget(io, env)) {
+    const int retarget = pred_retarget(io, env);
+    if (retarget) {
       unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu;
 #pragma unroll 4
       for (int v = threadIdx.x; v < NV; v += blockDim.x) nn_keys8(__ldg(xo4 + v), __ldg(yo4 + v), px, py, v * 8, klo, khi);
@@ -740,12 +770,23 @@ __global__ void __launch_bounds__(256) predator_block_kernel(const PredIO io) {
       target = nn_pick(klo, khi, S);
     }
     target = min(max(target, 0), N - 1);
+    int tx = (int)(int16_t)(tc & 0xFFFFu), ty = (int)(int16_t)(tc >> 16);
+    if (retarget || !io.tcell) {                               // (the cached cell spares the dependent read otherwise)
+      tx = (int)io.xo[(size_t)env * N + target];
+      ty = (int)io.yo[(size_t)env * N + target];
+    }
     int orient;
-    pursue(px, py, (int)io.xo[(size_t)env * N + target], (int)io.yo[(size_t)env * N + target], S, px, py, orient);
+    pursue(px, py, tx, ty, S, px, py, orient);
     unsigned hit = 0xFFFFFFFFu;
     const unsigned kx = rep2(px), ky = rep2(py);
+    const int tv = target >> 3;
+    if (io.tcell) __syncthreads();          // every thread has read the cached cell before one of them replaces it
 #pragma unroll 4
-    for (int v = threadIdx.x; v < NV; v += blockDim.x) hit8(__ldg(xn4 + v), __ldg(yn4 + v), kx, ky, v * 8, hit);
+    for (int v = threadIdx.x; v < NV; v += blockDim.x) {
+      const uint4 xv = __ldg(xn4 + v), yv = __ldg(yn4 + v);
+      hit8(xv, yv, kx, ky, v * 8, hit);
+      if (v == tv && io.tcell) reinterpret_cast<unsigned*>(io.tcell)[env] = cell8(xv, yv, target & 7);   // next step's cell
+    }
     hit = block_umin(hit, bs);
     if (threadIdx.x == 0) predator_write(io, env, ppx, ppy, px, py, target, orient, hit);
     __syncthreads();   // outputs of this env are written before the state reads of the next iteration
@@ -782,7 +823,10 @@ __global__ void __launch_bounds__(256) predator_kernel(const PredIO io) {
   for (int i = lane; i < N; i += 32)
     if ((int)io.xn[base + i] == px && (int)io.yn[base + i] == py) hit = min(hit, (unsigned)i);
   hit = warp_umin(hit);
-  if (lane == 0) predator_write(io, env, ppx, ppy, px, py, target, orient, hit);
+  if (lane == 0) {
+    if (io.tcell) reinterpret_cast<unsigned*>(io.tcell)[env] = pack2(io.xn[base + target], io.yn[base + target]);
+    predator_write(io, env, ppx, ppy, px, py, target, orient, hit);
+  }
 }
 
 // host-side dispatch (used by swarm_step's staged path and by swarm_predator)
@@ -800,16 +844,16 @@ static inline void launch_predator(const PredIO& io, int num_sms, cudaStream_t s
   }
   int lpe = 1;
   while (lpe < 32 && lpe * PRED_VPL < nv) lpe <<= 1;
-  const int grid = (int)((E * lpe + 255) / 256);
-  if (nv == 1) { predator_group_kernel<1, 1><<<grid, 256, 0, s>>>(io); return; }
-  if (nv == 2) { predator_group_kernel<1, 2><<<grid, 256, 0, s>>>(io); return; }
+  const int grid = (int)((E * lpe + PRED_THREADS - 1) / PRED_THREADS);
+  if (nv == 1) { predator_group_kernel<1, 1><<<grid, PRED_THREADS, 0, s>>>(io); return; }
+  if (nv == 2) { predator_group_kernel<1, 2><<<grid, PRED_THREADS, 0, s>>>(io); return; }
   switch (lpe) {
-    case 1: predator_group_kernel<1><<<grid, 256, 0, s>>>(io); break;
-    case 2: predator_group_kernel<2><<<grid, 256, 0, s>>>(io); break;
-    case 4: predator_group_kernel<4><<<grid, 256, 0, s>>>(io); break;
-    case 8: predator_group_kernel<8><<<grid, 256, 0, s>>>(io); break;
-    case 16: predator_group_kernel<16><<<grid, 256, 0, s>>>(io); break;
-    default: predator_group_kernel<32><<<grid, 256, 0, s>>>(io); break;
+    case 1: predator_group_kernel<1><<<grid, PRED_THREADS, 0, s>>>(io); break;
+    case 2: predator_group_kernel<2><<<grid, PRED_THREADS, 0, s>>>(io); break;
+    case 4: predator_group_kernel<4><<<grid, PRED_THREADS, 0, s>>>(io); break;
+    case 8: predator_group_kernel<8><<<grid, PRED_THREADS, 0, s>>>(io); break;
+    case 16: predator_group_kernel<16><<<grid, PRED_THREADS, 0, s>>>(io); break;
+    default: predator_group_kernel<32><<<grid, PRED_THREADS, 0, s>>>(io); break;
   }
 }
 

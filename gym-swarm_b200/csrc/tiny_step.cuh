@@ -23,6 +23,9 @@
 namespace swarm {
 
 constexpr int TINY_THREADS = 128;
+#ifndef TINY_MINB
+#define TINY_MINB 1      // minimum resident CTAs per SM the 8-agent step kernel is compiled for (register cap)
+#endif
 
 // c[k] = number of agents on agent k's cell (SDE:269-292); keys of padding agents are unique. Returns sum(c-1).
 template <int TN>
@@ -124,7 +127,7 @@ __device__ __forceinline__ void tiny_reset(const StepParams& p, int env, unsigne
 // AGENT_OUT: per-agent rewards / counts are written (otherwise only the env totals are formed, from the packed
 // counters, without ever unpacking a per-agent value).
 template <int TN, bool AGENT_OUT>
-__global__ void __launch_bounds__(TINY_THREADS) tiny_step_kernel(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(TINY_THREADS, TN == 8 ? TINY_MINB : 1) tiny_step_kernel(const __grid_constant__ StepParams p) {
   const int env = blockIdx.x * TINY_THREADS + threadIdx.x;
   if (env >= p.E) return;
   const int N = p.N, S = p.S;
