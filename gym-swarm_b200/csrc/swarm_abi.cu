@@ -351,6 +351,8 @@ __global__ void __launch_bounds__(256) int32_peak_kernel(int iters, unsigned see
 
 using namespace swarm;
 
+typedef int (*nccl_allreduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+
 extern "C" {
 
 int swarm_abi_version(void) { return SWARM_ABI_VERSION; }
@@ -783,8 +785,6 @@ int swarm_observe_vf(int32_t E, int32_t N, int32_t S, int32_t vf, const int16_t*
 
 // ---- statistics -----------------------------------------------------------------------------------------
 
-typedef int (*nccl_allreduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
-
 int swarm_stats_begin(swarm_handle h, int32_t allreduce, void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(h);
   if (!c) return fail(c, SWARM_E_INVALID, "swarm_stats_begin: null handle");
@@ -886,6 +886,14 @@ int swarm_nccl_init(swarm_handle h, const uint8_t id[128], int32_t nranks, int32
   const int rc = f(&c->nccl_comm, nranks, u, rank);
   if (rc != 0) return fail(c, SWARM_E_NCCL, "ncclCommInitRank failed, code " + std::to_string(rc));
   c->nccl_owned = true;
+  // NCCL connects its channels lazily, inside the first collective (hundreds of milliseconds): pay that here, on the
+  // side stream, so that the first swarm_stats_begin of a step loop costs what every later one costs
+  nccl_allreduce_t ar = (nccl_allreduce_t)dlsym(c->nccl_lib, "ncclAllReduce");
+  if (!ar) return fail(c, SWARM_E_NCCL, "ncclAllReduce missing");
+  CUDA_TRY(c, cudaMemsetAsync(c->d_partial, 0, 8 * sizeof(double), c->side));
+  const int wrc = ar(c->d_partial, c->d_partial, 8, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl_comm, c->side);
+  if (wrc != 0) return fail(c, SWARM_E_NCCL, "ncclAllReduce (warm-up) failed, code " + std::to_string(wrc));
+  CUDA_TRY(c, cudaStreamSynchronize(c->side));
   return SWARM_OK;
 }
 
