@@ -3,10 +3,14 @@
 captured with --import-source on (regions are delimited by marker comments in the embedded source)."""
 import csv, io, subprocess, sys
 MARKERS = [("helpers (Seg, ld/st)", "struct Seg {"), ("occupancy_counts", "void occupancy_counts("), ("bitmap_counts", "bool bitmap_counts("),
-           ("closest_target", "int closest_target("), ("reset_group", "void reset_group("), ("ring sweep", "void ring_sweep("), ("visual-field hits -> sums", "void vf_sparse_accumulate("), ("far-threshold border pass", "void far_border_counts("), ("kernel prologue + loads", "fused_step_kernel(const __grid_constant__"),
-           ("move + collision rounds", "// ---- move + collision"), ("predator", "// ---- predator (SDE"), ("termination", "// ---- termination"),
-           ("stage pair words", "// ---- reward (SDE"), ("pair sweep", "const unsigned TR = rep2"), ("alignment + epilogue", "// alignment sums"),
-           ("per-env outputs + stats", "// ---- per-env outputs"), ("commit / auto-reset", "// ---- commit / auto-reset"), ("reset kernel", "fused_reset_kernel(")]
+           ("closest_target", "int closest_target("), ("reset_group", "void reset_group("), ("ring sweep", "void ring_sweep("),
+           ("visual-field hits -> sums", "void vf_sparse_accumulate("), ("box counts (near thresholds)", "void box_near_counts("),
+           ("far-threshold border pass", "void far_border_counts("), ("FusedCfg", "struct FusedCfg {"),
+           ("terminal step (out of line)", "void terminal_step("), ("kernel prologue + loads", "fused_step_kernel(const __grid_constant__"),
+           ("move + collision rounds", "// ---- move + collision"), ("predator", "// ---- predator (SDE"),
+           ("termination + early per-env stores + commit", "// ---- termination"), ("stage pair words", "// ---- reward (SDE"),
+           ("sweep / box dispatch", "const unsigned TR = rep2"), ("alignment + epilogue + outputs", "// the running-episode record is fetched"),
+           ("reset kernel", "fused_reset_kernel(")]
 src = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 cur, per_file = None, {}
 for r in csv.reader(io.StringIO(src)):
