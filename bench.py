@@ -635,7 +635,7 @@ def main():
         configs = {}
         configs["cfg2"] = run_sub(job, "cfg2", steps=800, warmup=40, strong=False, graph=True)
         configs["cfg3_strong"] = run_sub(job, "cfg3", steps=100, warmup=10, strong=True)
-        configs["cfg4"] = run_sub(job, "cfg4", steps=100, warmup=10, strong=True)
+        configs["cfg4"] = run_sub(job, "cfg4", steps=96, warmup=16, strong=True, graph=True)
         configs["cfg5"] = run_sub(job, "cfg5", steps=3 * STATS_EVERY, warmup=10, strong=True, stats_every=STATS_EVERY)
         if not args.no_e2e:
             configs["cfg3_e2e_terms"] = run_e2e_terms(job, cfg, h_actions, h_retarget, h_slab, T, numa)

@@ -183,25 +183,18 @@ class BatchedSwarmEnv:
         assert tuple(place.shape) == (self.R, self.E, self.PL), (tuple(place.shape), (self.R, self.E, self.PL))
         assert tuple(ptape.shape) == (self.R, self.E, self.KP, 2), tuple(ptape.shape)
         self._place, self._ptape = place, ptape
+        self._dev_reset_bound = False
         _lib.check(self.lib.swarm_bind_reset_tapes(self._h, _ptr(place), _ptr(ptape)), self._h)
 
     def _ensure_reset_tapes(self):
-        if self.device_tapes and self._place is None:
-            if not getattr(self, "_dev_reset_bound", False):
-                _lib.check(self.lib.swarm_set_device_reset_tapes(self._h, C.c_uint64(self.reset_seed)), self._h)
-                self._dev_reset_bound = True
-            return
-        if self._place is None:
-            if self.R * self.E * self.PL <= (1 << 24):
-                rt = _tapes.make_reset_tapes(self._rng, self.R, self.E, self.N, self.S, KR=self.KR, KP=self.KP)
-                self.set_reset_tapes(rt.place, rt.ptape)
-            else:                                       # large batches: draw the reset tapes on the device
-                g = torch.Generator(device=self.device)
-                g.manual_seed(int(self._rng.integers(0, 2 ** 62)))
-                place = torch.randint(0, self.S, (self.R, self.E, self.PL), dtype=torch.int16, device=self.device, generator=g)
-                ptape = torch.randint(0, self.S, (self.R, self.E, self.KP, 2), dtype=torch.int16, device=self.device,
-                                      generator=g)
-                self.set_reset_tapes(place, ptape)
+        """Reset tapes for callers that bind none: the in-kernel counter streams (Philox keyed by ``seed``, stream index =
+        the env's reset count).  They never wrap, so an env that resets for the n-th time gets a fresh placement -- a
+        materialised tape with ``reset_slots`` slots would cycle through ``reset_slots`` placements per env -- and the
+        only bounds left are the attempts per reset (``place_extra`` re-draws, ``pred_attempts``).  Explicit tapes
+        (``set_reset_tapes``: parity runs, the reference-compatible single env) take precedence."""
+        if self._place is None and not getattr(self, "_dev_reset_bound", False):
+            _lib.check(self.lib.swarm_set_device_reset_tapes(self._h, C.c_uint64(self.reset_seed)), self._h)
+            self._dev_reset_bound = True
 
     def _next_step_tapes(self):
         """Tapes for callers that do not bring their own: drawn in chunks of ``tape_chunk`` steps.  Small batches draw
@@ -450,11 +443,14 @@ class BatchedSwarmEnv:
             idx = self.target.long().clamp(0, self.N - 1).unsqueeze(1)
             self.tcell[:, 0].copy_(self.x.gather(1, idx).squeeze(1))
             self.tcell[:, 1].copy_(self.y.gather(1, idx).squeeze(1))
-        if d["place"] is not None:
-            self.set_reset_tapes(d["place"], d["ptape"])
         self._rng.bit_generator.state = d["rng"]
         self.seed, self.step_index = d.get("seed", self.seed), d.get("step_index", self.step_index)
-        self._dev_reset_bound = False
+        if d["place"] is not None:
+            self.set_reset_tapes(d["place"], d["ptape"])
+        else:                                           # in-kernel reset streams: re-key them with the restored seed
+            self._place = self._ptape = None
+            self._dev_reset_bound = False
+            self._ensure_reset_tapes()
         self._chunk = None if d["chunk"] is None else tuple(t.to(self.device) for t in d["chunk"])
         self._chunk_pos = d["chunk_pos"]
 
