@@ -1,0 +1,369 @@
+// predator_async.cuh -- the predator step for N <= 256 as a persistent, software-pipelined stream (sm_100a).
+//
+// SDE:111-165 (closest_target / follow_target) and SDE:307-309 (termination test), same arithmetic as the kernels in
+// staged.cuh.  What differs is how the bytes travel: predator_group_kernel lands its loads in REGISTERS, so the bytes in
+// flight per SM are bounded by the register file times the share of a warp's life spent waiting (ncu: 23 warps x 4 KB,
+// half of them computing -> ~46 KB in flight, 0.65 of the HBM peak), and an env that retargets (SDE:138-140) pays a
+// second, dependent DRAM round trip.  Here every warp owns a ring of SHARED-memory buffers and fills them with
+// cp.async (LDGSTS) W+1 tiles ahead of the tile it computes on:
+//
+//   state(k)  px, py, target, cached target cell, retarget flags of the warp tile's 32/LPE envs (4-byte pieces)
+//   main(k)   the NEW positions of the tile (16-byte pieces, each lane copies exactly the vectors it will read)
+//   rows(k)   the OLD positions of the envs whose retarget flag is set -- issued together with main(k), because
+//             state(k) travels W+1 tiles further ahead and has landed by then: no dependent round trip
+//
+// One commit group per iteration; cp.async groups complete in order, so `wait_group W` at the top of iteration `it`
+// guarantees main(it), rows(it) and state(it + W + 1).  Nothing is shared between warps and nothing waits on an
+// mbarrier: a lane reads another lane's slot only after wait_group + __syncwarp.  Shared memory, not the register file,
+// bounds the bytes in flight (~100 KB per SM), and the compute of a tile overlaps the flight of the next W+1.
+#pragma once
+#include "swarm_common.cuh"
+
+namespace swarm {
+
+#ifndef PA_THREADS
+#define PA_THREADS 64
+#endif
+#ifndef PA_W
+#define PA_W 1
+#endif
+
+template <int LPE, int V, int W>
+struct PredAsyncCfg {
+  static constexpr int EW = 32 / LPE;          // envs of one warp tile
+  static constexpr int FW = (EW + 3) / 4;      // 4-byte words of the u8-per-env retarget flags
+  // state buffer (bytes): px int16[EW] | py int16[EW] | target i32[EW] | target cell u32[EW] | retarget u8[EW]
+  static constexpr int O_PX = 0, O_PY = 2 * EW, O_TG = 4 * EW, O_TC = 8 * EW, O_FL = 12 * EW;
+  static constexpr int SB = (13 * EW + 15) / 16 * 16;
+  static constexpr int SW = 3 * EW + FW;       // the same buffer in 4-byte words (ragged last tile)
+  // row slots per warp tile (binomial(EW, 0.1) exceeds them in < 0.5 % of the tiles: those envs read global memory)
+  static constexpr int RMAX = EW >= 32 ? 8 : (EW >= 16 ? 5 : (EW >= 8 ? 3 : 2));
+  static constexpr int DM = W + 1, DS = 2 * W + 2;              // tiles ahead: main / rows, state
+  static constexpr int NMAIN = DM + 1, NROWS = DM + 1, NSTATE = DS + 1;
+  static constexpr int MAIN_U4 = 2 * V * 32;                    // [x|y][V][32 lanes]
+  static constexpr int ROWS_U4 = RMAX * 2 * V * LPE;            // [slot][x|y][V][LPE]
+  static constexpr int WARP_BYTES = (NMAIN * MAIN_U4 + NROWS * ROWS_U4) * 16 + NSTATE * SB;
+  static constexpr int CTA_BYTES = WARP_BYTES * (PA_THREADS / 32);
+  // pieces of one state(k): 16-byte copies where a segment is a multiple of 16 bytes, 4-byte copies otherwise
+  static constexpr int PS_PX = (2 * EW) % 16 == 0 ? 16 : 4, PS_TG = (4 * EW) % 16 == 0 ? 16 : 4, PS_FL = EW % 16 == 0 ? 16 : 4;
+  static constexpr int NP_PX = 2 * EW / PS_PX, NP_TG = 4 * EW / PS_TG, NP_FL = EW / PS_FL;
+  static constexpr int NPIECES = 2 * NP_PX + 2 * NP_TG + NP_FL;   // <= 32: one cp.async per lane
+};
+
+__device__ __forceinline__ void cp_async16(unsigned dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Chebyshev distance of two packed agents to the predator, per halfword: max(x-px, px-x, y-py, py-y).
+//   NP = rep2(-px), P1 = rep2(px+1) (so that ~x + P1 = px - x), same for y.   4 DPX + 2 LOP per word.
+__device__ __forceinline__ unsigned cheb2_pred(unsigned xw, unsigned yw, unsigned NP, unsigned P1, unsigned NQ, unsigned Q1) {
+  unsigned d = __vadd2(xw, NP);
+  d = __viaddmax_s16x2(~xw, P1, d);
+  d = __viaddmax_s16x2(yw, NQ, d);
+  d = __viaddmax_s16x2(~yw, Q1, d);
+  return d;
+}
+// Nearest-neighbour keys of one vector (8 agents) in packed 16-bit form, (d << 5) | c with d < 2048 and the local index
+// l = 8 q + e < 32 of the agent in its lane: c = l selects the LOWEST index at the minimum distance (HI = false),
+// c = 31 - l the HIGHEST (SDE:121-129 under the stable-sort rule, see nn_pick).
+template <int Q, bool HI>
+__device__ __forceinline__ void nn_keys8_packed(const uint4& xv, const uint4& yv, unsigned NP, unsigned P1, unsigned NQ,
+                                                unsigned Q1, unsigned& acc) {
+  const unsigned xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+  unsigned k[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const unsigned d = cheb2_pred(xs[h], ys[h], NP, P1, NQ, Q1);
+    const unsigned l0 = (unsigned)(Q * 8 + 2 * h);
+    k[h] = (d << 5) + (HI ? (((31u - (l0 + 1u)) << 16) | (31u - l0)) : (((l0 + 1u) << 16) | l0));
+  }
+  acc = __vimin3_u16x2(acc, k[0], k[1]);
+  acc = __vimin3_u16x2(acc, k[2], k[3]);
+}
+// running packed minimum of (x ^ kx) | (y ^ ky): a zero halfword <=> an agent of the vector stands on the cell
+__device__ __forceinline__ void hit8_packed(const uint4& xv, const uint4& yv, unsigned kx, unsigned ky, unsigned& acc) {
+  acc = __vimin3_u16x2(acc, (xv.x ^ kx) | (yv.x ^ ky), (xv.y ^ kx) | (yv.y ^ ky));
+  acc = __vimin3_u16x2(acc, (xv.z ^ kx) | (yv.z ^ ky), (xv.w ^ kx) | (yv.w ^ ky));
+}
+
+// EXACT: N == 8 * LPE * V (no lane ever holds a padding vector)
+template <int LPE, int V, int W, bool EXACT>
+__global__ void __launch_bounds__(PA_THREADS) predator_async_kernel(const PredIO io, int tiles) {
+  using C = PredAsyncCfg<LPE, V, W>;
+  constexpr int EW = C::EW;
+  extern __shared__ uint4 pa_smem[];
+  const int wic = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPE, li = lane % LPE;
+  const unsigned gmask = (LPE == 32) ? 0xFFFFFFFFu : (((1u << LPE) - 1u) << (g * LPE));
+  // the warp's ring, as shared-window byte addresses
+  const unsigned mainb = (unsigned)__cvta_generic_to_shared(pa_smem) + (unsigned)wic * C::WARP_BYTES;
+  const unsigned rowsb = mainb + C::NMAIN * C::MAIN_U4 * 16;
+  const unsigned stateb = rowsb + C::NROWS * C::ROWS_U4 * 16;
+  const unsigned char* const gen0 = reinterpret_cast<const unsigned char*>(pa_smem) + (size_t)wic * C::WARP_BYTES;
+  const unsigned char* const gen_rows = gen0 + C::NMAIN * C::MAIN_U4 * 16;
+  const unsigned char* const gen_state = gen_rows + C::NROWS * C::ROWS_U4 * 16;
+  const int nwarps = gridDim.x * (PA_THREADS / 32);
+  const int w0 = blockIdx.x * (PA_THREADS / 32) + wic;
+  const int my = w0 < tiles ? (tiles - w0 + nwarps - 1) / nwarps : 0;   // warp tiles w0, w0 + nwarps, ...
+  const int N = io.N, S = io.S, NV = N >> 3, E = io.E;
+  const uint4* __restrict__ xn4 = reinterpret_cast<const uint4*>(io.xn);
+  const uint4* __restrict__ yn4 = reinterpret_cast<const uint4*>(io.yn);
+  const uint4* __restrict__ xo4 = reinterpret_cast<const uint4*>(io.xo);
+  const uint4* __restrict__ yo4 = reinterpret_cast<const uint4*>(io.yo);
+
+  // ---- this lane's piece of every state(k): source array, bytes per env, offsets (fixed for the whole launch)
+  const unsigned char* role_src = nullptr;
+  unsigned role_bpe = 0, role_dst = 0;
+  bool role16 = false;
+  {
+    int j = lane;
+    auto seg = [&](const void* base, int bpe, int off_smem, int npieces, int psize) {
+      if (j >= 0 && j < npieces) {
+        role_src = reinterpret_cast<const unsigned char*>(base) + j * psize;
+        role_bpe = (unsigned)bpe;
+        role_dst = (unsigned)(off_smem + j * psize);
+        role16 = psize == 16;
+      }
+      j -= npieces;
+    };
+    seg(io.px, 2, C::O_PX, C::NP_PX, C::PS_PX);
+    seg(io.py, 2, C::O_PY, C::NP_PX, C::PS_PX);
+    seg(io.target, 4, C::O_TG, C::NP_TG, C::PS_TG);
+    seg(io.tcell, 4, C::O_TC, C::NP_TG, C::PS_TG);
+    seg(io.retarget, 1, C::O_FL, C::NP_FL, C::PS_FL);
+  }
+
+  // ---- state(tile) into state slot `slot`
+  auto issue_state = [&](int tile, int slot) {
+    const int e0 = tile * EW;
+    const unsigned st = stateb + (unsigned)slot * C::SB;
+    if (e0 + EW <= E) {                          // whole tile: one piece per lane
+      if (role_src) {
+        const unsigned char* src = role_src + (size_t)e0 * role_bpe;
+        if (role16) cp_async16(st + role_dst, src);
+        else cp_async4(st + role_dst, src);
+      }
+    } else {                                     // ragged last tile (E % 4 == 0): 4-byte words, each inside the arrays
+#pragma unroll
+      for (int r = 0; r < (C::SW + 31) / 32; ++r) {
+        const int j = lane + 32 * r;
+        if (j >= C::SW) break;
+        const void* src;
+        int env;
+        if (j < EW / 2) { env = e0 + 2 * j; src = io.px + env; }
+        else if (j < EW) { env = e0 + 2 * (j - EW / 2); src = io.py + env; }
+        else if (j < 2 * EW) { env = e0 + (j - EW); src = io.target + env; }
+        else if (j < 3 * EW) { env = e0 + (j - 2 * EW); src = io.tcell + 2 * (size_t)env; }
+        else { env = e0 + 4 * (j - 3 * EW); src = io.retarget + env; }
+        if (env < E) cp_async4(st + 4u * (unsigned)j, src);
+      }
+    }
+  };
+  // ---- main(tile) + rows(tile); needs the flags of state(tile) in state slot `sslot`
+  auto issue_main_rows = [&](int tile, int sslot, int mslot) {
+    const int env = tile * EW + g;
+    const bool valid = env < E;
+    const bool ret = valid && gen_state[sslot * C::SB + C::O_FL + g] != 0;
+    const unsigned rb = __ballot_sync(0xFFFFFFFFu, ret && li == 0);
+    if (valid) {
+      const unsigned voff = (unsigned)env * (unsigned)NV + (unsigned)li;      // vector index: E * N / 8 < 2^32
+      const unsigned mb = mainb + (unsigned)mslot * (C::MAIN_U4 * 16) + (unsigned)lane * 16u;
+      const uint4* xs = xn4 + voff;
+      const uint4* ys = yn4 + voff;
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        if (EXACT || li + q * LPE < NV) {
+          cp_async16(mb + q * 512, xs + q * LPE);
+          cp_async16(mb + (V + q) * 512, ys + q * LPE);
+        }
+      }
+      if (ret) {
+        const int rank = __popc(rb & ((1u << (g * LPE)) - 1u));
+        if (rank < C::RMAX) {
+          const unsigned rw = rowsb + (unsigned)mslot * (C::ROWS_U4 * 16) + (unsigned)(rank * (2 * V * LPE) + li) * 16u;
+          const uint4* xos = xo4 + voff;
+          const uint4* yos = yo4 + voff;
+#pragma unroll
+          for (int q = 0; q < V; ++q) {
+            if (EXACT || li + q * LPE < NV) {
+              cp_async16(rw + q * (LPE * 16), xos + q * LPE);
+              cp_async16(rw + (V + q) * (LPE * 16), yos + q * LPE);
+            }
+          }
+        }
+      }
+    }
+  };
+
+  // ---- prologue: the first DS states land before the first main / rows are issued
+#pragma unroll
+  for (int k = 0; k < C::DS; ++k)
+    if (k < my) issue_state(w0 + k * nwarps, k % C::NSTATE);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < C::DM; ++k) {
+    if (k < my) issue_main_rows(w0 + k * nwarps, k % C::NSTATE, k % C::NMAIN);
+    cp_async_commit();
+  }
+
+  int cs = 0, cm = 0;                            // it % NSTATE, it % NMAIN
+  int tile = w0;
+  for (int it = 0; it < my; ++it, tile += nwarps) {
+    cp_async_wait<W>();          // main(it), rows(it), state(it + DM) have landed
+    __syncwarp();                // ... for every lane of the warp; and every lane is done with tile it - 1
+    {
+      const int ss = cs == 0 ? C::NSTATE - 1 : cs - 1;                        // (it + DS) % NSTATE
+      const int ms = cs + C::DM >= C::NSTATE ? cs + C::DM - C::NSTATE : cs + C::DM;   // (it + DM) % NSTATE
+      const int im = cm == 0 ? C::NMAIN - 1 : cm - 1;                         // (it + DM) % NMAIN
+      if (it + C::DS < my) issue_state(tile + C::DS * nwarps, ss);
+      if (it + C::DM < my) issue_main_rows(tile + C::DM * nwarps, ms, im);
+      cp_async_commit();
+    }
+    const int env = tile * EW + g;
+    const unsigned char* st = gen_state + cs * C::SB;
+    const uint4* mb = reinterpret_cast<const uint4*>(gen0) + cm * C::MAIN_U4;
+    const uint4* rwb = reinterpret_cast<const uint4*>(gen_rows) + cm * C::ROWS_U4;
+    cs = cs + 1 == C::NSTATE ? 0 : cs + 1;
+    cm = cm + 1 == C::NMAIN ? 0 : cm + 1;
+    const bool valid = env < E;
+    const bool ret = valid && st[C::O_FL + g] != 0;
+    const unsigned rb = __ballot_sync(0xFFFFFFFFu, ret && li == 0);
+    if (!valid) continue;        // whole lane groups leave; the warp meets again at the __syncwarp of the next iteration
+    int px = reinterpret_cast<const int16_t*>(st + C::O_PX)[g];
+    int py = reinterpret_cast<const int16_t*>(st + C::O_PY)[g];
+    int target = min(max(reinterpret_cast<const int*>(st + C::O_TG)[g], 0), N - 1);
+    const unsigned tc = reinterpret_cast<const unsigned*>(st + C::O_TC)[g];
+    int tx = (int)(int16_t)(tc & 0xFFFFu), ty = (int)(int16_t)(tc >> 16);
+    const int ppx = px, ppy = py;
+    if (ret) {                                                   // SDE:138-140 on the OLD positions
+      const unsigned NP = rep2(-px), P1 = rep2(px + 1), NQ = rep2(-py), Q1 = rep2(py + 1);
+      const int rank = __popc(rb & ((1u << (g * LPE)) - 1u));
+      const bool staged = rank < C::RMAX;
+      const uint4* rw = rwb + (staged ? rank : 0) * (2 * V * LPE);
+      const unsigned voff = (unsigned)env * (unsigned)NV + (unsigned)li;
+      auto keys = [&](auto hi_tag) -> unsigned {
+        constexpr bool HI = decltype(hi_tag)::value;
+        unsigned acc = 0xFFFFFFFFu;
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+          if (EXACT || li + q * LPE < NV) {
+            const uint4 xv = staged ? rw[q * LPE + li] : __ldg(xo4 + voff + q * LPE);
+            const uint4 yv = staged ? rw[(V + q) * LPE + li] : __ldg(yo4 + voff + q * LPE);
+            if (q == 0) nn_keys8_packed<0, HI>(xv, yv, NP, P1, NQ, Q1, acc);
+            if (q == 1) nn_keys8_packed<1, HI>(xv, yv, NP, P1, NQ, Q1, acc);
+            if (q == 2) nn_keys8_packed<2, HI>(xv, yv, NP, P1, NQ, Q1, acc);
+            if (q == 3) nn_keys8_packed<3, HI>(xv, yv, NP, P1, NQ, Q1, acc);
+          }
+        }
+        // lane minimum -> 32-bit key (d << 16) | c' with the GLOBAL agent index (or 0xFFFF - index for HI)
+        const unsigned m16 = min(acc & 0xFFFFu, acc >> 16);
+        const unsigned l = HI ? 31u - (m16 & 31u) : (m16 & 31u);
+        const unsigned idx = ((unsigned)(li + (int)(l >> 3) * LPE) << 3) | (l & 7u);
+        unsigned key = ((m16 >> 5) << 16) | (HI ? 0xFFFFu - idx : idx);
+        if (!EXACT && li >= NV) key = 0xFFFFFFFFu;               // a lane without a single vector of the env
+#pragma unroll
+        for (int d = LPE / 2; d > 0; d >>= 1) key = min(key, __shfl_xor_sync(gmask, key, d));
+        return key;
+      };
+      const unsigned klo = keys(std::false_type{});
+      target = (int)(klo & 0xFFFFu);
+      if (2 * (int)(klo >> 16) >= S) {                           // ties go to the HIGHEST index only at d_min >= S/2 (nn_pick)
+        const unsigned khi = keys(std::true_type{});
+        target = nn_pick(klo, khi, S);
+      }
+      if (staged) {                                              // the new target's OLD cell, from the staged rows
+        const int v = target >> 3, e = target & 7;
+        tx = reinterpret_cast<const int16_t*>(rw + v)[e];        // rows are [q][li]: vector v = li + q LPE sits at index v
+        ty = reinterpret_cast<const int16_t*>(rw + V * LPE + v)[e];
+      } else {
+        const size_t a = (size_t)env * (size_t)N + (size_t)target;
+        tx = io.xo[a];
+        ty = io.yo[a];
+      }
+    }
+    int orient;
+    pursue(px, py, tx, ty, S, px, py, orient);                   // SDE:142-165
+    const unsigned kx = rep2(px), ky = rep2(py);
+    unsigned acc = 0xFFFFFFFFu;                                  // SDE:307-309 on the NEW positions
+#pragma unroll
+    for (int q = 0; q < V; ++q)
+      if (EXACT || li + q * LPE < NV) hit8_packed(mb[q * 32 + lane], mb[(V + q) * 32 + lane], kx, ky, acc);
+#pragma unroll
+    for (int d = LPE / 2; d > 0; d >>= 1) acc = __vminu2(acc, __shfl_xor_sync(gmask, acc, d));
+    unsigned hit = 0xFFFFFFFFu;
+    if (zero_half(acc) != 0u) {                                  // rare: resolve the lowest index standing on the cell
+#pragma unroll
+      for (int q = 0; q < V; ++q)
+        if (EXACT || li + q * LPE < NV) hit8(mb[q * 32 + lane], mb[(V + q) * 32 + lane], kx, ky, (li + q * LPE) * 8, hit);
+#pragma unroll
+      for (int d = LPE / 2; d > 0; d >>= 1) hit = min(hit, __shfl_xor_sync(gmask, hit, d));
+    }
+    if (li == 0) {
+      const int v = target >> 3, e = target & 7;                 // the target's NEW cell = what the next step pursues
+      const int slot = (v / LPE) * 32 + g * LPE + (v % LPE);
+      const int nx = reinterpret_cast<const int16_t*>(mb + slot)[e];
+      const int ny = reinterpret_cast<const int16_t*>(mb + V * 32 + slot)[e];
+      reinterpret_cast<unsigned*>(io.tcell)[env] = pack2(nx, ny);
+      predator_write(io, env, ppx, ppy, px, py, target, orient, hit);
+    }
+  }
+}
+
+// shapes <LPE, V> by N (N % 8 == 0, N <= 256)
+template <int LPE, int V, bool EXACT>
+static cudaError_t predator_async_launch_x(const PredIO& io, int num_sms, cudaStream_t s) {
+  using C = PredAsyncCfg<LPE, V, PA_W>;
+  static_assert(C::NPIECES <= 32, "one state piece per lane");
+  static bool opted[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!opted[dev]) {
+    e = cudaFuncSetAttribute(predator_async_kernel<LPE, V, PA_W, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::CTA_BYTES);
+    if (e != cudaSuccess) return e;
+    opted[dev] = true;
+  }
+  const int tiles = (io.E + C::EW - 1) / C::EW;
+  const int per_sm = std::max(1, std::min(32, (int)((227 * 1024) / (C::CTA_BYTES + 1024))));
+  // a warp keeps at least 6 tiles (the pipeline's depth plus its prologue) before another CTA is added
+  const long long want = ((long long)tiles + 6 * (PA_THREADS / 32) - 1) / (6 * (PA_THREADS / 32));
+  const int grid = (int)std::min<long long>(want, (long long)num_sms * per_sm);
+  predator_async_kernel<LPE, V, PA_W, EXACT><<<grid, PA_THREADS, C::CTA_BYTES, s>>>(io, tiles);
+  return cudaGetLastError();
+}
+template <int LPE, int V>
+static cudaError_t predator_async_launch_t(const PredIO& io, int num_sms, cudaStream_t s) {
+  return io.N == 8 * LPE * V ? predator_async_launch_x<LPE, V, true>(io, num_sms, s)
+                             : predator_async_launch_x<LPE, V, false>(io, num_sms, s);
+}
+
+// true: launched (or failed with *err set); false: shape not covered, the caller uses the register kernels
+static inline bool predator_async_try(const PredIO& io, int num_sms, cudaStream_t s, cudaError_t* err) {
+  const int N = io.N;
+  // (the standalone entry point's case: tapes bound, no frozen mask -- swarm_step reaches the predator kernels only
+  // with N > 256)
+  if ((N & 7) || N > 256 || !io.tcell || !io.retarget || io.frozen || (io.E & 3) || io.S > 2048) return false;
+  if (((uintptr_t)io.px | (uintptr_t)io.py | (uintptr_t)io.target | (uintptr_t)io.tcell | (uintptr_t)io.retarget |
+       (uintptr_t)io.xo | (uintptr_t)io.yo | (uintptr_t)io.xn | (uintptr_t)io.yn) & 15)
+    return false;                                              // 16-byte cp.async pieces
+  const int nv = N >> 3;
+  if (nv == 1) *err = predator_async_launch_t<1, 1>(io, num_sms, s);
+  else if (nv == 2) *err = predator_async_launch_t<1, 2>(io, num_sms, s);
+  else if (nv <= 4) *err = predator_async_launch_t<1, 4>(io, num_sms, s);
+  else if (nv <= 8) *err = predator_async_launch_t<2, 4>(io, num_sms, s);
+  else if (nv <= 16) *err = predator_async_launch_t<4, 4>(io, num_sms, s);
+  else *err = predator_async_launch_t<8, 4>(io, num_sms, s);
+  return true;
+}
+
+}  // namespace swarm

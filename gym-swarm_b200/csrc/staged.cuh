@@ -829,10 +829,18 @@ __global__ void __launch_bounds__(256) predator_kernel(const PredIO io) {
   }
 }
 
+}  // namespace swarm
+#include "predator_async.cuh"
+namespace swarm {
+
 // host-side dispatch (used by swarm_step's staged path and by swarm_predator)
 static inline void launch_predator(const PredIO& io, int num_sms, cudaStream_t s) {
   const int N = io.N;
   const long long E = io.E;
+  {                                                            // N <= 256 with the cached target cell: cp.async stream
+    cudaError_t ae = cudaSuccess;
+    if (predator_async_try(io, num_sms, s, &ae) && ae == cudaSuccess) return;
+  }
   if ((N & 7) != 0) {
     predator_kernel<<<(int)((E * 32 + 255) / 256), 256, 0, s>>>(io);
     return;

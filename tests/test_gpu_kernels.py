@@ -35,7 +35,12 @@ def test_swarm_move_matches_reference_rule(E, N, S):
 
 
 @pytest.mark.parametrize("E,N,S", [(200, 2, 4), (300, 8, 16), (100, 16, 8), (50, 37, 50), (64, 40, 9), (40, 128, 128),
-                                   (9, 200, 64), (5, 512, 100), (3, 4096, 256), (2, 16384, 1024), (700, 16384, 300)])
+                                   (9, 200, 64), (5, 512, 100), (3, 4096, 256), (2, 16384, 1024), (700, 16384, 300),
+                                   # the cp.async stream (N <= 256, E % 4 == 0): every <LPE, V> shape, ragged last tiles,
+                                   # several tiles per warp, more retargeting envs than row slots (50 % retarget here)
+                                   (3004, 8, 16), (1500, 16, 12), (900, 24, 16), (644, 32, 20), (420, 48, 30),
+                                   (372, 64, 33), (204, 104, 64), (260, 128, 128), (124, 136, 90), (100, 256, 200),
+                                   (52, 248, 2048)])
 def test_swarm_predator_matches_oracle(E, N, S):
     """Every dispatch of the predator kernel (lane groups 1..32, CTA per env, scalar fallback): retarget tie rule,
     pursuit on the OLD positions, wrap, termination test on the NEW positions."""

@@ -22,8 +22,11 @@ KEYS = [
     "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_atom.sum",
-    "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.max",
-]
+    "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.max", "smsp__warps_eligible.avg.per_cycle_active",
+] + [f"smsp__average_warps_issue_stalled_{r}_per_issue_active.ratio" for r in (
+    "long_scoreboard", "short_scoreboard", "wait", "barrier", "math_pipe_throttle", "no_instruction", "not_selected",
+    "lg_throttle", "mio_throttle", "branch_resolving", "dispatch_stall", "drain", "membar", "sleeping", "tex_throttle",
+    "imc_miss")]
 
 
 def launches(path):
