@@ -366,4 +366,216 @@ static inline bool predator_async_try(const PredIO& io, int num_sms, cudaStream_
   return true;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Large environments (N >= 4096): a CTA streams one env after another through the same kind of ring, one thread = one
+// landing slot of PB_U x + PB_U y vectors per stage.  The chunk sequence of a CTA is
+//     for each of its envs:  [old positions, only if the env retargets]  then  new positions
+// and the loads of the next PB_W + 1 chunks are always in flight, across pass and env boundaries, while the CTA computes
+// on the current chunk or sits in the block reduction that ends a pass (arg-min of the retarget, termination test).
+// predator_block_kernel (staged.cuh) instead pays per env: one trip for the state, one per unrolled batch of loads and
+// the reductions, with nothing in flight in between (0.67 of the HBM peak at 8,192 x 16,384).
+// Per-env state travels 8 envs ahead through a 16-slot ring of 4-byte cp.async pieces (aligned-down words for the int16 /
+// u8 arrays: E % 4 == 0).
+// ------------------------------------------------------------------------------------------------
+#ifndef PB_U
+#define PB_U 2
+#endif
+#ifndef PB_W
+#define PB_W 1
+#endif
+constexpr int PB_THREADS = 256;
+constexpr int PB_NST = PB_W + 2;                       // stages of the landing ring
+constexpr int PB_LEAD = 8, PB_RING = 16, PB_SWORDS = 8;  // state ring: {px pair, py pair, target, tcell, retarget quad, frozen quad}
+constexpr int PB_SMEM = PB_NST * 2 * PB_U * PB_THREADS * 16 + PB_RING * PB_SWORDS * 4;
+
+__global__ void __launch_bounds__(PB_THREADS) predator_block_async_kernel(const PredIO io) {
+  extern __shared__ uint4 pb_smem[];
+  __shared__ unsigned red[2][2][PB_THREADS / 32];        // [parity][value][warp]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int N = io.N, S = io.S, NV = N >> 3, E = io.E;
+  const int CPE = (NV + PB_THREADS * PB_U - 1) / (PB_THREADS * PB_U);   // chunks per pass
+  const int b = blockIdx.x, G = gridDim.x;
+  const int my = b < E ? (E - b + G - 1) / G : 0;        // envs b, b + G, ...
+  uint4* const ring = pb_smem;                           // [stage][x|y][u][thread]
+  unsigned* const sring = reinterpret_cast<unsigned*>(pb_smem + PB_NST * 2 * PB_U * PB_THREADS);
+  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)t * 16u;
+  const unsigned sring_s = (unsigned)__cvta_generic_to_shared(sring);
+  int rpar = 0;
+  // one __syncthreads per reduction: warp minima into red[parity], everyone folds the 8 warp values
+  auto block_min2 = [&](unsigned& a, unsigned& c) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      a = min(a, __shfl_xor_sync(0xFFFFFFFFu, a, d));
+      c = min(c, __shfl_xor_sync(0xFFFFFFFFu, c, d));
+    }
+    if (lane == 0) { red[rpar][0][warp] = a; red[rpar][1][warp] = c; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < PB_THREADS / 32; ++w) { a = min(a, red[rpar][0][w]); c = min(c, red[rpar][1][w]); }
+    rpar ^= 1;
+  };
+  auto issue_state = [&](int j) {                        // threads 0..5, one piece each
+    if (j >= my || t >= 6) return;
+    const int env = b + j * G;
+    const unsigned dst = sring_s + (unsigned)((j & (PB_RING - 1)) * PB_SWORDS + t) * 4u;
+    if (t == 0) cp_async4(dst, io.px + (env & ~1));
+    else if (t == 1) cp_async4(dst, io.py + (env & ~1));
+    else if (t == 2) cp_async4(dst, io.target + env);
+    else if (t == 3) { if (io.tcell) cp_async4(dst, io.tcell + 2 * (size_t)env); }
+    else if (t == 4) {
+      if (io.retarget) cp_async4(dst, io.retarget + (env & ~3));
+      else sring[(j & (PB_RING - 1)) * PB_SWORDS + 4] =
+          (unsigned)philox_retarget(io.rng_seed_lo, io.rng_seed_hi, io.rng_step, env + (int)io.env_offset) << (8 * (env & 3));
+    } else if (io.frozen) cp_async4(dst, io.frozen + (env & ~3));
+  };
+  auto sword = [&](int j, int w) -> unsigned { return sring[(j & (PB_RING - 1)) * PB_SWORDS + w]; };
+  auto frozen_of = [&](int j) -> bool { return io.frozen && ((sword(j, 5) >> (8 * ((b + j * G) & 3))) & 0xFFu) != 0u; };
+  auto first_pass = [&](int j) -> int {                  // 0: old positions first (retarget), 1: new positions only
+    return (!frozen_of(j) && ((sword(j, 4) >> (8 * ((b + j * G) & 3))) & 0xFFu) != 0u) ? 0 : 1;
+  };
+  struct Cur { int j, pass, c; };
+  auto advance = [&](Cur& q) {
+    if (++q.c < CPE) return;
+    q.c = 0;
+    if (q.pass == 0) { q.pass = 1; return; }
+    ++q.j;
+    q.pass = q.j < my ? first_pass(q.j) : 1;
+  };
+  auto issue_chunk = [&](const Cur& q, int stage) {
+    if (q.j >= my) return;
+    const size_t vb = (size_t)(b + q.j * G) * (size_t)NV;
+    const uint4* xs = reinterpret_cast<const uint4*>(q.pass == 0 ? io.xo : io.xn) + vb;
+    const uint4* ys = reinterpret_cast<const uint4*>(q.pass == 0 ? io.yo : io.yn) + vb;
+    const unsigned dst = ring_s + (unsigned)stage * (2 * PB_U * PB_THREADS * 16);
+#pragma unroll
+    for (int u = 0; u < PB_U; ++u) {
+      const int v = (q.c * PB_U + u) * PB_THREADS + t;
+      if (v < NV) {
+        cp_async16(dst + u * (PB_THREADS * 16), xs + v);
+        cp_async16(dst + (PB_U + u) * (PB_THREADS * 16), ys + v);
+      }
+    }
+  };
+
+  if (my == 0) return;
+#pragma unroll
+  for (int j = 0; j < PB_LEAD; ++j) issue_state(j);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  Cur iss = {0, first_pass(0), 0}, con = iss;
+#pragma unroll
+  for (int d = 0; d <= PB_W; ++d) {
+    issue_chunk(iss, d);
+    cp_async_commit();
+    advance(iss);
+  }
+  int stage = 0;
+  // per-env registers
+  int px = 0, py = 0, ppx = 0, ppy = 0, target = 0, orient = 0, tv = 0;
+  unsigned klo = 0xFFFFFFFFu, khi = 0xFFFFFFFFu, hit = 0xFFFFFFFFu, kx = 0u, ky = 0u;
+  unsigned NP = 0u, P1 = 0u, NQ = 0u, Q1 = 0u;
+  bool frz = false;
+  while (con.j < my) {
+    cp_async_wait<PB_W>();                               // this thread's slots of the current chunk have landed
+    {
+      int is = stage + PB_W + 1;
+      if (is >= PB_NST) is -= PB_NST;
+      issue_chunk(iss, is);
+      if (con.c == 0 && con.pass == 1) issue_state(con.j + PB_LEAD);   // once per env, 8 envs ahead
+      cp_async_commit();
+      advance(iss);
+    }
+    const int env = b + con.j * G;
+    const uint4* slot = ring + stage * (2 * PB_U * PB_THREADS) + t;
+    if (con.c == 0 && (con.pass == 0 || first_pass(con.j) == 1)) {     // first chunk of the env: its state
+      px = (int)(int16_t)((sword(con.j, 0) >> (16 * (env & 1))) & 0xFFFFu);
+      py = (int)(int16_t)((sword(con.j, 1) >> (16 * (env & 1))) & 0xFFFFu);
+      ppx = px; ppy = py;
+      target = min(max((int)sword(con.j, 2), 0), N - 1);
+      frz = frozen_of(con.j);
+      klo = khi = hit = 0xFFFFFFFFu;
+      if (con.pass == 0) {
+        NP = rep2(-px); P1 = rep2(px + 1); NQ = rep2(-py); Q1 = rep2(py + 1);
+      } else {                                           // no retarget: pursue the cached cell (or read it: legacy callers)
+        int tx, ty;
+        if (io.tcell) { const unsigned tc = sword(con.j, 3); tx = (int)(int16_t)(tc & 0xFFFFu); ty = (int)(int16_t)(tc >> 16); }
+        else { const size_t a = (size_t)env * (size_t)N + (size_t)target; tx = io.xo[a]; ty = io.yo[a]; }
+        pursue(px, py, tx, ty, S, px, py, orient);
+        kx = rep2(px); ky = rep2(py); tv = target >> 3;
+      }
+    }
+    if (con.pass == 0) {                                 // SDE:111-131 on the OLD positions
+#pragma unroll
+      for (int u = 0; u < PB_U; ++u) {
+        const int v = (con.c * PB_U + u) * PB_THREADS + t;
+        if (v < NV) {
+          unsigned lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu;
+          const uint4 xv = slot[u * PB_THREADS], yv = slot[(PB_U + u) * PB_THREADS];
+          nn_keys8_packed<0, false>(xv, yv, NP, P1, NQ, Q1, lo);
+          nn_keys8_packed<0, true>(xv, yv, NP, P1, NQ, Q1, hi);
+          const unsigned l16 = min(lo & 0xFFFFu, lo >> 16), h16 = min(hi & 0xFFFFu, hi >> 16);
+          klo = min(klo, ((l16 >> 5) << 16) | ((unsigned)v * 8u + (l16 & 7u)));
+          khi = min(khi, ((h16 >> 5) << 16) | (0xFFFFu - ((unsigned)v * 8u + (7u - (h16 & 7u)))));
+        }
+      }
+      if (con.c == CPE - 1) {                            // arg-min over the env, then the pursuit (SDE:138-165)
+        block_min2(klo, khi);
+        target = nn_pick(klo, khi, S);
+        const size_t a = (size_t)env * (size_t)N + (size_t)target;
+        pursue(px, py, (int)io.xo[a], (int)io.yo[a], S, px, py, orient);
+        kx = rep2(px); ky = rep2(py); tv = target >> 3;
+      }
+    } else {                                             // SDE:307-309 on the NEW positions
+#pragma unroll
+      for (int u = 0; u < PB_U; ++u) {
+        const int v = (con.c * PB_U + u) * PB_THREADS + t;
+        if (v < NV) {
+          const uint4 xv = slot[u * PB_THREADS], yv = slot[(PB_U + u) * PB_THREADS];
+          unsigned acc = 0xFFFFFFFFu;
+          hit8_packed(xv, yv, kx, ky, acc);
+          if (zero_half(acc) != 0u) hit8(xv, yv, kx, ky, v * 8, hit);
+          if (v == tv && io.tcell && !frz) reinterpret_cast<unsigned*>(io.tcell)[env] = cell8(xv, yv, target & 7);
+        }
+      }
+      if (con.c == CPE - 1) {
+        unsigned dummy = 0xFFFFFFFFu;
+        block_min2(hit, dummy);
+        if (t == 0) {
+          if (frz) predator_frozen(io, env);
+          else predator_write(io, env, ppx, ppy, px, py, target, orient, hit);
+        }
+      }
+    }
+    advance(con);
+    if (++stage == PB_NST) stage = 0;
+  }
+}
+
+// true: launched (ok or *err set); false: shape not covered
+static inline bool predator_block_async_try(const PredIO& io, int num_sms, cudaStream_t s, cudaError_t* err) {
+  const int N = io.N;
+  if ((N & 7) || N < 4096 || N > 65528 || (io.E & 3) || io.S > 2048) return false;
+  if (((uintptr_t)io.px | (uintptr_t)io.py | (uintptr_t)io.target | (uintptr_t)io.tcell | (uintptr_t)io.retarget |
+       (uintptr_t)io.frozen) & 3)
+    return false;
+  if (((uintptr_t)io.xo | (uintptr_t)io.yo | (uintptr_t)io.xn | (uintptr_t)io.yn) & 15) return false;
+  static bool opted[64] = {};
+  int dev = 0;
+  *err = cudaGetDevice(&dev);
+  if (*err != cudaSuccess) return true;
+  if (dev < 0 || dev >= 64) return false;
+  if (!opted[dev]) {
+    *err = cudaFuncSetAttribute(predator_block_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM);
+    if (*err != cudaSuccess) return true;
+    opted[dev] = true;
+  }
+  const int per_sm = std::max(1, std::min(8, (227 * 1024) / (PB_SMEM + 1024 + 256)));
+  const int grid = (int)std::min<long long>(io.E, (long long)num_sms * per_sm);
+  predator_block_async_kernel<<<grid, PB_THREADS, PB_SMEM, s>>>(io);
+  *err = cudaGetLastError();
+  return true;
+}
+
 }  // namespace swarm

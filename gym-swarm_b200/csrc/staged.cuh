@@ -840,6 +840,7 @@ static inline void launch_predator(const PredIO& io, int num_sms, cudaStream_t s
   {                                                            // N <= 256 with the cached target cell: cp.async stream
     cudaError_t ae = cudaSuccess;
     if (predator_async_try(io, num_sms, s, &ae) && ae == cudaSuccess) return;
+    if (predator_block_async_try(io, num_sms, s, &ae) && ae == cudaSuccess) return;   // N >= 4096: CTA-per-env stream
   }
   if ((N & 7) != 0) {
     predator_kernel<<<(int)((E * 32 + 255) / 256), 256, 0, s>>>(io);

@@ -40,7 +40,10 @@ def test_swarm_move_matches_reference_rule(E, N, S):
                                    # several tiles per warp, more retargeting envs than row slots (50 % retarget here)
                                    (3004, 8, 16), (1500, 16, 12), (900, 24, 16), (644, 32, 20), (420, 48, 30),
                                    (372, 64, 33), (204, 104, 64), (260, 128, 128), (124, 136, 90), (100, 256, 200),
-                                   (52, 248, 2048)])
+                                   (52, 248, 2048),
+                                   # the CTA-per-env cp.async stream (N >= 4096, E % 4 == 0): one chunk per pass, several,
+                                   # a ragged last chunk, more envs than CTAs in flight
+                                   (8, 4096, 256), (12, 16384, 1024), (4, 40000, 2048), (900, 4096, 100)])
 def test_swarm_predator_matches_oracle(E, N, S):
     """Every dispatch of the predator kernel (lane groups 1..32, CTA per env, scalar fallback): retarget tie rule,
     pursuit on the OLD positions, wrap, termination test on the NEW positions."""
