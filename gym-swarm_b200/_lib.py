@@ -19,6 +19,7 @@ PATH_AUTO, PATH_STAGED, PATH_FUSED, PATH_GROUP, PATH_STAGED_PAIRWISE = 0, 1, 2, 
 
 E_NOT_READY = -5
 FLAG_NO_FAR_BORDER, FLAG_VF_DENSE, FLAG_FUSED_SPLIT, FLAG_FUSED_ONE_LAUNCH, FLAG_NO_BOX_NEAR = 1, 4, 8, 16, 32
+FLAG_TINY_SCALAR = 64
 
 ERR_SLAB_OVERFLOW = 1
 ERR_PLACE_OVERFLOW = 2

@@ -60,38 +60,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// Chebyshev distance of two packed agents to the predator, per halfword: max(x-px, px-x, y-py, py-y).
-//   NP = rep2(-px), P1 = rep2(px+1) (so that ~x + P1 = px - x), same for y.   4 DPX + 2 LOP per word.
-__device__ __forceinline__ unsigned cheb2_pred(unsigned xw, unsigned yw, unsigned NP, unsigned P1, unsigned NQ, unsigned Q1) {
-  unsigned d = __vadd2(xw, NP);
-  d = __viaddmax_s16x2(~xw, P1, d);
-  d = __viaddmax_s16x2(yw, NQ, d);
-  d = __viaddmax_s16x2(~yw, Q1, d);
-  return d;
-}
-// Nearest-neighbour keys of one vector (8 agents) in packed 16-bit form, (d << 5) | c with d < 2048 and the local index
-// l = 8 q + e < 32 of the agent in its lane: c = l selects the LOWEST index at the minimum distance (HI = false),
-// c = 31 - l the HIGHEST (SDE:121-129 under the stable-sort rule, see nn_pick).
-template <int Q, bool HI>
-__device__ __forceinline__ void nn_keys8_packed(const uint4& xv, const uint4& yv, unsigned NP, unsigned P1, unsigned NQ,
-                                                unsigned Q1, unsigned& acc) {
-  const unsigned xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
-  unsigned k[4];
-#pragma unroll
-  for (int h = 0; h < 4; ++h) {
-    const unsigned d = cheb2_pred(xs[h], ys[h], NP, P1, NQ, Q1);
-    const unsigned l0 = (unsigned)(Q * 8 + 2 * h);
-    k[h] = (d << 5) + (HI ? (((31u - (l0 + 1u)) << 16) | (31u - l0)) : (((l0 + 1u) << 16) | l0));
-  }
-  acc = __vimin3_u16x2(acc, k[0], k[1]);
-  acc = __vimin3_u16x2(acc, k[2], k[3]);
-}
-// running packed minimum of (x ^ kx) | (y ^ ky): a zero halfword <=> an agent of the vector stands on the cell
-__device__ __forceinline__ void hit8_packed(const uint4& xv, const uint4& yv, unsigned kx, unsigned ky, unsigned& acc) {
-  acc = __vimin3_u16x2(acc, (xv.x ^ kx) | (yv.x ^ ky), (xv.y ^ kx) | (yv.y ^ ky));
-  acc = __vimin3_u16x2(acc, (xv.z ^ kx) | (yv.z ^ ky), (xv.w ^ kx) | (yv.w ^ ky));
-}
-
 // EXACT: N == 8 * LPE * V (no lane ever holds a padding vector)
 template <int LPE, int V, int W, bool EXACT>
 __global__ void __launch_bounds__(PA_THREADS) predator_async_kernel(const PredIO io, int tiles) {

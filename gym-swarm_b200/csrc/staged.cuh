@@ -594,20 +594,6 @@ __device__ __forceinline__ void nn_keys8(const uint4& xv, const uint4& yv, int p
     khi = min(khi, nn_key_hi(d, i0 + e));
   }
 }
-// 8 packed agents against the predator's NEW cell (kx, ky = cell replicated in both halves): lowest hit index.
-// z has a zero halfword iff that agent stands on the cell; the exact index is only resolved on the rare hit.
-__device__ __forceinline__ unsigned zero_half(unsigned z) { return (z - 0x00010001u) & ~z & 0x80008000u; }
-__device__ __forceinline__ void hit8(const uint4& xv, const uint4& yv, unsigned kx, unsigned ky, int i0, unsigned& hit) {
-  const unsigned z[4] = {(xv.x ^ kx) | (yv.x ^ ky), (xv.y ^ kx) | (yv.y ^ ky), (xv.z ^ kx) | (yv.z ^ ky),
-                         (xv.w ^ kx) | (yv.w ^ ky)};
-  if ((zero_half(z[0]) | zero_half(z[1]) | zero_half(z[2]) | zero_half(z[3])) == 0u) return;
-#pragma unroll
-  for (int hh = 3; hh >= 0; --hh) {
-    if ((z[hh] >> 16) == 0u) hit = min(hit, (unsigned)(i0 + 2 * hh + 1));
-    if ((z[hh] & 0xFFFFu) == 0u) hit = min(hit, (unsigned)(i0 + 2 * hh));
-  }
-}
-
 // finished episode, auto-reset off (SDE:233-234): nothing moves, the step's predator outputs are the standing state
 __device__ __forceinline__ void predator_frozen(const PredIO& io, int env) {
   io.err[env] |= SWARM_ERR_STEP_WHEN_DONE;

@@ -144,6 +144,7 @@ static StepParams base_params(const Ctx* c) {
   p.t_vf = -1;
   p.env_offset = g.env_offset;
   p.vf_dense = (g.flags & SWARM_FLAG_VF_DENSE) ? 1 : 0;
+  p.tiny_scalar = (g.flags & SWARM_FLAG_TINY_SCALAR) ? 1 : 0;
   p.w_att = p.w_rep = p.w_ali = 1.0;
   p.eat = g.predator_eat_rew;
   p.K = g.slab_len; p.PL = g.place_len; p.KP = g.pred_attempts; p.R = g.reset_slots;

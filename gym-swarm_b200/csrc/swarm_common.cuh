@@ -64,6 +64,7 @@ struct StepParams {
   int one;           // runtime 1: `v * one + acc` compiles to IMAD (FMA pipe) instead of IADD3 (ALU pipe)
   int vf_dense;      // SWARM_FLAG_VF_DENSE
   int split;         // lane-group kernels: the step as two launches (transition, reward); see fused_step_kernel
+  int tiny_scalar;   // SWARM_FLAG_TINY_SCALAR: the scalar thread-per-env kernel even where the packed one applies
   int box_near;      // reward launch: {rep, att} counts from box popcounts on the occupancy bitmap (fused_step.cuh)
   // state
   int16_t *x, *y, *px, *py;
@@ -217,6 +218,57 @@ __device__ __forceinline__ AgentTerms agent_terms(const StepParams& p, int cR, i
   t.una = 0.5 * (double)vis - 0.25 * (double)P - 0.35355339059327376220 * (double)Q;
   return t;
 }
+
+// ----------------------------------------------------------------------------------------------
+// Packed predator arithmetic shared by the predator kernels (staged.cuh, predator_async.cuh) and the packed
+// thread-per-env step (tiny_packed.cuh): positions stay two agents per 32-bit word.
+// ----------------------------------------------------------------------------------------------
+// 8 packed agents against the predator's NEW cell (kx, ky = cell replicated in both halves): lowest hit index.
+// z has a zero halfword iff that agent stands on the cell; the exact index is only resolved on the rare hit.
+__device__ __forceinline__ unsigned zero_half(unsigned z) { return (z - 0x00010001u) & ~z & 0x80008000u; }
+__device__ __forceinline__ void hit8(const uint4& xv, const uint4& yv, unsigned kx, unsigned ky, int i0, unsigned& hit) {
+  const unsigned z[4] = {(xv.x ^ kx) | (yv.x ^ ky), (xv.y ^ kx) | (yv.y ^ ky), (xv.z ^ kx) | (yv.z ^ ky),
+                         (xv.w ^ kx) | (yv.w ^ ky)};
+  if ((zero_half(z[0]) | zero_half(z[1]) | zero_half(z[2]) | zero_half(z[3])) == 0u) return;
+#pragma unroll
+  for (int hh = 3; hh >= 0; --hh) {
+    if ((z[hh] >> 16) == 0u) hit = min(hit, (unsigned)(i0 + 2 * hh + 1));
+    if ((z[hh] & 0xFFFFu) == 0u) hit = min(hit, (unsigned)(i0 + 2 * hh));
+  }
+}
+
+// Chebyshev distance of two packed agents to the predator, per halfword: max(x-px, px-x, y-py, py-y).
+//   NP = rep2(-px), P1 = rep2(px+1) (so that ~x + P1 = px - x), same for y.   4 DPX + 2 LOP per word.
+__device__ __forceinline__ unsigned cheb2_pred(unsigned xw, unsigned yw, unsigned NP, unsigned P1, unsigned NQ, unsigned Q1) {
+  unsigned d = __vadd2(xw, NP);
+  d = __viaddmax_s16x2(~xw, P1, d);
+  d = __viaddmax_s16x2(yw, NQ, d);
+  d = __viaddmax_s16x2(~yw, Q1, d);
+  return d;
+}
+// Nearest-neighbour keys of one vector (8 agents) in packed 16-bit form, (d << 5) | c with d < 2048 and the local index
+// l = 8 q + e < 32 of the agent in its lane: c = l selects the LOWEST index at the minimum distance (HI = false),
+// c = 31 - l the HIGHEST (SDE:121-129 under the stable-sort rule, see nn_pick).
+template <int Q, bool HI>
+__device__ __forceinline__ void nn_keys8_packed(const uint4& xv, const uint4& yv, unsigned NP, unsigned P1, unsigned NQ,
+                                                unsigned Q1, unsigned& acc) {
+  const unsigned xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+  unsigned k[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const unsigned d = cheb2_pred(xs[h], ys[h], NP, P1, NQ, Q1);
+    const unsigned l0 = (unsigned)(Q * 8 + 2 * h);
+    k[h] = (d << 5) + (HI ? (((31u - (l0 + 1u)) << 16) | (31u - l0)) : (((l0 + 1u) << 16) | l0));
+  }
+  acc = __vimin3_u16x2(acc, k[0], k[1]);
+  acc = __vimin3_u16x2(acc, k[2], k[3]);
+}
+// running packed minimum of (x ^ kx) | (y ^ ky): a zero halfword <=> an agent of the vector stands on the cell
+__device__ __forceinline__ void hit8_packed(const uint4& xv, const uint4& yv, unsigned kx, unsigned ky, unsigned& acc) {
+  acc = __vimin3_u16x2(acc, (xv.x ^ kx) | (yv.x ^ ky), (xv.y ^ kx) | (yv.y ^ ky));
+  acc = __vimin3_u16x2(acc, (xv.z ^ kx) | (yv.z ^ ky), (xv.w ^ kx) | (yv.w ^ ky));
+}
+
 
 // number of set bits in the bit range [lo, hi] (inclusive, lo <= hi) of a word array
 __device__ __forceinline__ int range_popc(const unsigned* __restrict__ bits, int lo, int hi) {

@@ -70,6 +70,7 @@ extern "C" {
 #define SWARM_FLAG_FUSED_SPLIT 8u   /* lane-group kernels: always two launches per step (transition, then reward); the default
                                        does that from 2^22 agents per handle up (instruction-cache footprint) */
 #define SWARM_FLAG_FUSED_ONE_LAUNCH 16u /* lane-group kernels: always the single fused launch */
+#define SWARM_FLAG_TINY_SCALAR 64u  /* thread-per-env path: the scalar kernel even for N == 8 without per-agent outputs */
 #define SWARM_FLAG_NO_BOX_NEAR 32u  /* reward launch of the two-launch step: ring sweep even where box popcounts apply */
 
 typedef struct swarm_config {

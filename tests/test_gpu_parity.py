@@ -139,6 +139,26 @@ def test_oracle_lockstep_tiny_and_group_kernels(N, S):
                          K=512 if dense else None, KR=2000 if dense else None, weights=(0.5, 1.0, 0.25))
 
 
+@pytest.mark.parametrize("S", [16, 5, 4, 40, 300])
+def test_oracle_lockstep_packed_tiny_kernel(S):
+    """Exactly 8 agents without per-agent outputs: tiny8_packed_kernel (positions never unpacked; PRMT action table,
+    packed wrap, nibble collision counters) against the oracle -- action 8, dense grids with several re-draw rounds,
+    every threshold plan, frozen envs without auto-reset -- and the scalar kernel it replaces (FLAG_TINY_SCALAR)."""
+    from gym_swarm_b200 import _lib
+    from gym_swarm_b200.envs import BatchedSwarmEnv
+    dense = S * S < 32
+    kw = dict(K=512 if dense else None, KR=4000 if dense else None, KP=64 if dense else 8)
+    for flags in (0, _lib.FLAG_TINY_SCALAR):
+        _oracle_lockstep(E=300, N=8, S=S, T=40, seed=S * 13 + flags, n_actions=9, agent_out=False, flags=flags,
+                         weights=(0.5, 1.0, 0.25), **kw)
+    for (att, rep) in ((5, 2), (2, 5), (0, 0), (30, 3), (10, 200), (1, 1)):
+        _oracle_lockstep(E=100, N=8, S=S, T=12, seed=S + att, n_actions=9, att=att, rep=rep, agent_out=False, **kw)
+    _oracle_lockstep(E=200, N=8, S=S, T=60, seed=S + 5, n_actions=8, agent_out=False, auto_reset=False, **kw)
+    env = BatchedSwarmEnv(64, 8, 16)
+    assert env.path_name.startswith("tiny<8>"), env.path_name
+    env.close()
+
+
 @pytest.mark.parametrize("N,S", [(9, 16), (12, 7), (13, 40), (16, 32), (16, 8)])
 def test_oracle_lockstep_tiny16_kernel(N, S):
     """9..16 agents: the 16-agent instantiation of the thread-per-env kernel (normally chosen only for batches of
