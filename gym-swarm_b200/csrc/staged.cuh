@@ -1737,4 +1737,145 @@ __global__ void __launch_bounds__(OBS_CHUNK) observe_vf_kernel(int E, int N, int
   }
 }
 
+
+// Warp-per-env variant for the lane-group shapes (N <= 256, N % APL == 0, a bitmap of a few KB; e.g. cfg3): no
+// __syncthreads, no clearing passes.  A warp keeps ONE clean, row-padded occupancy bitmap (VF empty rows above and below the
+// grid: no range checks; stored as 50 % overlapping words so that a window row is always inside ONE word) and one staging area in shared memory and walks envs env, env + stride, ... with the next env's
+// positions already in flight.  Lane l owns the APL consecutive agents l APL .. l APL + APL - 1, i.e. APL (2 VF + 1)^2
+// CONTIGUOUS, 4-byte aligned output bytes: every window row is one bitmap word and a shift, a multiply spreads
+// four cells into four code bytes, and the rows are streamed into whole 32-bit words with PRMT (all byte positions are
+// compile-time constants once the loops are unrolled) -- no byte stores, no window clear.  The env's N (2 VF + 1)^2 bytes
+// leave as coalesced 128-bit stores.  observe_vf_kernel above pays three __syncthreads, a bitmap clear and a window clear
+// per 128 agents and sets its cells with byte stores (0.29 of the HBM peak at 262,144 x 128).
+constexpr int OBSW_WARPS = 4;
+
+template <int VF, int APL>
+__global__ void __launch_bounds__(OBSW_WARPS * 32) observe_vf_warp_kernel(int E, int N, int S, int bm_words, int warp_bytes,
+                                                                          const int16_t* __restrict__ x,
+                                                                          const int16_t* __restrict__ y,
+                                                                          const int16_t* __restrict__ px,
+                                                                          const int16_t* __restrict__ py,
+                                                                          uint8_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char obs_smem[];
+  constexpr int W = 2 * VF + 1, WW = W * W, NJ = (W + 3) / 4;
+  constexpr int LW = APL * WW / 4;                               // output words of one lane (APL % 4 == 0)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned* sbit = reinterpret_cast<unsigned*>(obs_smem + (size_t)warp * warp_bytes);   // [(S + 2 VF) rows], clean between envs
+  unsigned* swin = sbit + ((bm_words + 3) & ~3);                                          // [N * WW / 4] words
+  for (int w = lane; w < bm_words; w += 32) sbit[w] = 0u;
+  __syncwarp();
+  const int nbytes = N * WW;
+  const bool own = lane * APL < N;
+  const int stride = gridDim.x * OBSW_WARPS;
+  int env = blockIdx.x * OBSW_WARPS + warp;
+  // raw positions of the lane's agents (APL int16 = APL / 2 words per axis) and the predator, one env ahead
+  unsigned xr[APL / 2], yr[APL / 2];
+  int pxe = 0, pye = 0;
+  auto load_env = [&](int e) {
+    if (e < E) {
+      if (own) {
+        const size_t o = ((size_t)e * (size_t)N + (size_t)lane * APL) >> 1;     // in 32-bit words
+#pragma unroll
+        for (int q = 0; q < APL / 4; ++q) {
+          const uint2 a = reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned*>(x) + o)[q];
+          const uint2 b = reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned*>(y) + o)[q];
+          xr[2 * q] = a.x; xr[2 * q + 1] = a.y; yr[2 * q] = b.x; yr[2 * q + 1] = b.y;
+        }
+      }
+      pxe = px[e]; pye = py[e];
+    }
+  };
+  load_env(env);
+  for (; env < E; env += stride) {
+    int xs[APL], ys[APL];
+#pragma unroll
+    for (int k = 0; k < APL; ++k) {
+      xs[k] = (int)(int16_t)((xr[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
+      ys[k] = (int)(int16_t)((yr[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
+    }
+    const int cpx = pxe, cpy = pye;
+    load_env(env + stride);                                      // in flight while this env is built
+    if (own) {
+#pragma unroll
+      for (int k = 0; k < APL; ++k) {
+        const int cell = (ys[k] + VF) * S + xs[k];            // overlapped words: word v holds the bits [16 v - 16, 16 v + 16)
+        atomicOr(&sbit[(cell >> 4) + 1], 1u << (cell & 15));
+        atomicOr(&sbit[cell >> 4], 1u << ((cell & 15) + 16));
+      }
+    }
+    __syncwarp();
+    if (own) {
+      unsigned* ow = swin + lane * LW;
+      // the lane's byte stream: the `have` (< 4) bytes hold[hs .. hs + have) are waiting for the rest of their word
+      unsigned hold = 0u;
+      int hs = 0, have = 0, m = 0;                               // compile-time constants once the loops are unrolled
+#pragma unroll
+      for (int k = 0; k < APL; ++k) {
+        const int xi = xs[k], yi = ys[k];
+        const int x0 = max(xi - VF, 0), x1 = min(xi + VF, S - 1);
+        const unsigned cmask = 0xFFFFFFFFu >> (31 - (x1 - x0));
+        const int cshift = x0 - (xi - VF);                       // window columns cut off at the left border
+        int lo = yi * S + x0;                                    // padded rows: row yi - VF of the grid is row yi here
+#pragma unroll
+        for (int r = 0; r < W; ++r, lo += S) {
+          unsigned bits = ((sbit[(lo >> 4) + 1] >> (lo & 15)) & cmask) << cshift;   // <= 11 + 15 bits: one word
+          if (r == VF) bits &= ~(1u << VF);                      // the centre gets code 1 below
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int nb = (W - 4 * j) < 4 ? (W - 4 * j) : 4;    // valid bytes of this source word (the others are 0)
+            unsigned e;                                          // four cells -> four bytes of code 2
+            if (nb == 1) e = (bits >> (4 * j - 1)) & 2u;         // (j >= 1)
+            else e = (((bits >> (4 * j)) & 0xFu) * 0x00408102u) & 0x02020202u;
+            if (r == VF && j == VF / 4) e |= 1u << (8 * (VF % 4));
+            unsigned sel = 0u;
+            if (have + nb >= 4) {                                // a word completes: pending bytes, then e[0 .. 4 - have)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) sel |= (unsigned)(q < have ? hs + q : 4 + (q - have)) << (4 * q);
+              ow[m] = have == 0 ? e : __byte_perm(hold, e, sel);
+              ++m;
+              hold = e;
+              hs = 4 - have;
+              have = have + nb - 4;
+            } else {                                             // (last word of a row, W % 4 != 0): keep collecting
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                sel |= (unsigned)(q < have ? hs + q : (q < have + nb ? 4 + (q - have) : 7)) << (4 * q);   // e[3] == 0 here
+              hold = have == 0 ? e : __byte_perm(hold, e, sel);
+              hs = 0;
+              have = have + nb;
+            }
+          }
+        }
+      }
+      // predator: code 3 wins over everything (byte stores into the lane's own words, behind its word stores)
+#pragma unroll
+      for (int k = 0; k < APL; ++k) {
+        const int dx = cpx - xs[k], dy = cpy - ys[k];
+        if (iabs(dx) <= VF && iabs(dy) <= VF)
+          reinterpret_cast<unsigned char*>(ow)[k * WW + (dy + VF) * W + dx + VF] = 3;
+      }
+    }
+    __syncwarp();
+    if (own) {
+#pragma unroll
+      for (int k = 0; k < APL; ++k) {                            // leave the bitmap clean
+        const int v = ((ys[k] + VF) * S + xs[k]) >> 4;
+        sbit[v] = 0u;
+        sbit[v + 1] = 0u;
+      }
+    }
+    uint8_t* __restrict__ o = out + (size_t)env * (size_t)nbytes;
+    if ((((uintptr_t)o) & 15) == 0) {
+      const uint4* s16 = reinterpret_cast<const uint4*>(swin);
+      uint4* o16 = reinterpret_cast<uint4*>(o);
+      const int n16 = nbytes >> 4;
+      for (int q = lane; q < n16; q += 32) o16[q] = s16[q];
+      for (int q = (n16 << 4) + lane; q < nbytes; q += 32) o[q] = reinterpret_cast<const unsigned char*>(swin)[q];
+    } else {
+      for (int q = lane; q < nbytes; q += 32) o[q] = reinterpret_cast<const unsigned char*>(swin)[q];
+    }
+    __syncwarp();                                                // staging and bitmap are free for the next env
+  }
+}
+
 }  // namespace swarm

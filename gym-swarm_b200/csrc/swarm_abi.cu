@@ -776,6 +776,38 @@ int swarm_observe_vf(int32_t E, int32_t N, int32_t S, int32_t vf, const int16_t*
     else CUDA_TRY(nullptr, smem_opt_in(observe_vf_kernel<false>, smem));
     if (devi >= 0 && devi < 64) opted[devi][bitmap] = true;
   }
+  {                                                                // lane-group shapes: a warp per env, no block barriers
+    const int apl = N <= 128 ? 4 : 8;
+    const long long pwords = ((long long)(S + 2 * vf) * S + 15) / 16 + 2;          // row-padded bitmap, overlapping words
+    const int warp_bytes = (int)((pwords + 3) / 4 * 4) * 4 + (N * W * W + 15) / 16 * 16;
+    const int wsmem = warp_bytes * OBSW_WARPS;
+    if (N <= 256 && (N % apl) == 0 && vf >= 1 && vf <= 5 && pwords * 4 <= 16 * 1024 && wsmem <= 200 * 1024 &&
+        ((((uintptr_t)x) | ((uintptr_t)y)) & 7) == 0) {
+      static bool wopted[64][8][2] = {};
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devi);
+      const int per_sm = std::max(1, std::min(16, (220 * 1024) / (wsmem + 1024)));
+      const int wgrid = (int)std::min<long long>(((long long)E + OBSW_WARPS - 1) / OBSW_WARPS, (long long)sms * per_sm);
+#define OBSW_LAUNCH(V, A)                                                                                              \
+  do {                                                                                                                 \
+    if (wsmem > 48 * 1024 && (devi < 0 || devi >= 64 || !wopted[devi][V][A == 8])) {                                   \
+      CUDA_TRY(nullptr, smem_opt_in(observe_vf_warp_kernel<V, A>, wsmem));                                             \
+      if (devi >= 0 && devi < 64) wopted[devi][V][A == 8] = true;                                                      \
+    }                                                                                                                  \
+    observe_vf_warp_kernel<V, A><<<wgrid, OBSW_WARPS * 32, wsmem, (cudaStream_t)stream>>>(E, N, S, (int)pwords, warp_bytes, \
+                                                                                          x, y, px, py, out);          \
+  } while (0)
+#define OBSW_CASE(V)                                                                                                   \
+  case V:                                                                                                              \
+    if (apl == 4) OBSW_LAUNCH(V, 4); else OBSW_LAUNCH(V, 8);                                                           \
+    break;
+      switch (vf) { OBSW_CASE(1) OBSW_CASE(2) OBSW_CASE(3) OBSW_CASE(4) OBSW_CASE(5) }
+#undef OBSW_CASE
+#undef OBSW_LAUNCH
+      CUDA_TRY(nullptr, cudaGetLastError());
+      return SWARM_OK;
+    }
+  }
   const long long grid = (long long)E * ((N + OBS_CHUNK - 1) / OBS_CHUNK);
   if (grid > 0x7FFFFFFFLL) return fail(nullptr, SWARM_E_INVALID, "swarm_observe_vf: too many agent chunks");
   if (bitmap) observe_vf_kernel<true><<<(int)grid, OBS_CHUNK, smem, (cudaStream_t)stream>>>(E, N, S, vf, bm_words, x, y, px, py, out);

@@ -168,7 +168,7 @@ __device__ __forceinline__ int nn_pick(unsigned klo, unsigned khi, int S) {
 //   m = min(xj-xi, xi-xj, yj-yi, yi-yj) = -D per half          (1 VIADD.16x2 + 3 VIADDMNMX.S16x2)
 //   [D < t] = clamp(t + m, 0, 1) per half                       (1 VIADDMNMX.S16x2.RELU)
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned rep2(int v) { return ((unsigned)v & 0xFFFFu) * 0x10001u; }
+__device__ __forceinline__ unsigned rep2(int v) { return __byte_perm((unsigned)v, 0u, 0x1010); }   // one PRMT
 __device__ __forceinline__ unsigned pack2(int lo, int hi) { return ((unsigned)lo & 0xFFFFu) | ((unsigned)hi << 16); }
 
 __device__ __forceinline__ unsigned neg_cheb2(unsigned XI, unsigned YI, unsigned NXI, unsigned NYI, const uint4& w) {

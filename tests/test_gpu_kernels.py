@@ -142,7 +142,9 @@ def test_swarm_pairwise_matches_oracle(E, N, S, att, rep):
 
 
 @pytest.mark.parametrize("E,N,S,vf", [(5, 9, 12, 2), (3, 4, 20, 0), (7, 8, 6, 1), (4, 128, 40, 2), (2, 300, 30, 3), (2, 130, 16, 7),
-                                      (1, 2048, 128, 2), (2, 50, 1500, 3), (3, 37, 50, 4)])
+                                      (1, 2048, 128, 2), (2, 50, 1500, 3), (3, 37, 50, 4),
+                                      # warp-per-env kernel (N <= 256, small bitmap): several envs per warp, every vf
+                                      (70, 128, 128, 2), (41, 256, 64, 5), (33, 100, 128, 6), (50, 16, 32, 3), (90, 64, 33, 1)])
 def test_visual_field_observation(E, N, S, vf):
     """swarm_observe_vf / BatchedSwarmEnv.observe_visual_field against the oracle's definition (parity unpinned: the
     reference tree has only the README figure for this output)."""

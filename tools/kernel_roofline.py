@@ -109,7 +109,7 @@ def run_observe(lib, dev, E=1 << 18, N=128, S=128, vf=2):
     fn = lambda: _lib.check(lib.swarm_observe_vf(E, N, S, vf, ptr(x), ptr(y), ptr(px), ptr(py), ptr(out), stream()))
     mean, best = timeit(fn)
     alg = E * N * (4 + W * W) + E * 4                 # positions in, windows out
-    return {"kernel": "swarm_observe_vf (observe_vf_kernel)", "shape": f"{E} envs x {N} agents, S={S}, vf={vf}", "bound": "hbm",
+    return {"kernel": "swarm_observe_vf (observe_vf_warp_kernel)", "shape": f"{E} envs x {N} agents, S={S}, vf={vf}", "bound": "hbm",
             "algorithmic_bytes": alg, "ms_mean": mean, "ms_best": best, "achieved": alg / (mean * 1e-3) / 1e9, "peak": HBM,
             "unit": "GB/s", "frac": alg / (mean * 1e-3) / 1e9 / HBM}
 

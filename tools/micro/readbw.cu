@@ -38,6 +38,21 @@ __global__ void copy_kernel(const uint4* __restrict__ a, uint4* __restrict__ b, 
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) b[i] = __ldg(a + i);
 }
+__global__ void write_kernel(uint4* __restrict__ b, size_t n, unsigned v) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const uint4 w = make_uint4(v, v + 1, v + 2, v + 3);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) b[i] = w;
+}
+// one read stream, W write streams' worth of bytes (read 1 : write R, like the visual-field windows: 1 : 6)
+template <int R>
+__global__ void expand_kernel(const uint4* __restrict__ a, uint4* __restrict__ b, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint4 v = __ldg(a + i);
+#pragma unroll
+    for (int r = 0; r < R; ++r) b[i * R + r] = make_uint4(v.x + r, v.y, v.z, v.w);
+  }
+}
 template <typename F>
 float timeit(F f) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -61,6 +76,10 @@ int main() {
     float t8 = timeit([&] { read_kernel<8><<<grid, tpb>>>(a, n, out); });
     float t24 = timeit([&] { read2_kernel<4><<<grid, tpb>>>(a, b, n / 2, out); });
     float tc = timeit([&] { copy_kernel<<<grid, tpb>>>(a, b, n); });
+    float tw = timeit([&] { write_kernel<<<grid, tpb>>>(b, n, 7u); });
+    float te = timeit([&] { expand_kernel<6><<<grid, tpb>>>(a, b, n / 6); });
+    printf("tpb %4d cta/sm %2d : write-only %.0f  read1:write6 %.0f GB/s\n", tpb, cps, bytes / tw / 1e6,
+           (n / 6) * 16.0 * 7 / te / 1e6);
     printf("tpb %4d cta/sm %2d : read U1 %.0f  U4 %.0f  U8 %.0f  read2 U4 %.0f  copy(r+w) %.0f GB/s\n", tpb, cps,
            bytes / t1 / 1e6, bytes / t4 / 1e6, bytes / t8 / 1e6, bytes / t24 / 1e6, 2.0 * bytes / tc / 1e6);
   }
@@ -69,6 +88,7 @@ int main() {
     float t = timeit([&] { read_kernel<1><<<grid, 256>>>(a, n, out); });
     printf("one LDG.128 per thread, %d CTAs: %.0f GB/s\n", grid, bytes / t / 1e6);
   }
+  { float t = timeit([&] { cudaMemsetAsync(b, 3, bytes); }); printf("cudaMemsetAsync: %.0f GB/s\n", bytes / t / 1e6); }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
