@@ -27,12 +27,13 @@ B3="python bench.py --config cfg3 --steps 2 --warmup 3 --no-e2e --no-cpu-baselin
 full cfg3_fused fused_step 6 2 $B3
 [ -s gpurun_out/${R}_cfg3_fused.ncu-rep ] && python tools/ncu_regions.py gpurun_out/${R}_cfg3_fused.ncu-rep > gpurun_out/${R}_cfg3_fused_regions.txt
 full cfg3_vf5 fused_step 6 2 $B3 --vf 5
-full cfg5_tiny tiny_step 3 1 python bench.py --config cfg5 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-subconfigs --graph off
+full cfg5_tiny "tiny8_packed|tiny_step" 3 1 python bench.py --config cfg5 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-subconfigs --graph off
 full cfg4_staged "collide_bitmap|boxcount|predator_block" 6 3 python bench.py --config cfg4 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-subconfigs --graph off
-KR="python tools/kernel_roofline.py move predator"
+KR="python tools/kernel_roofline.py move predator observe"
 full move move_kernel 5 1 $KR
-full predator_n128 predator_group 5 1 $KR
-full predator_n16384 predator_block 5 1 $KR
-full predator_n8 predator_group 25 1 $KR
+full predator_n128 predator_async_kernel 5 1 $KR
+full predator_n16384 predator_block_async 5 1 $KR
+full predator_n8 predator_async_kernel 18 1 $KR
+full observe_vf observe_vf_warp 4 1 $KR
 rm -f gpurun_out/${R}_*.ncu-rep
 du -sh gpurun_out
