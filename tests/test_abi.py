@@ -123,3 +123,43 @@ def test_null_arguments(built):
     lib.swarm_destroy(None)                                   # destroying a null handle is a no-op
     assert lib.swarm_path_name(None) == b""
     assert lib.swarm_last_launch_count(None) == 0
+
+
+def _stub_gym(monkeypatch):
+    """A stand-in for the gym registry (gym is not in this image): records register() calls and resolves entry points
+    the way gym.make does ("module:Class")."""
+    import importlib
+    import sys
+    import types
+    registry = {}
+    gym = types.ModuleType("gym")
+    envs = types.ModuleType("gym.envs")
+    reg = types.ModuleType("gym.envs.registration")
+
+    def register(id, entry_point, **kw):
+        registry[id] = entry_point
+
+    def make(id, **kw):
+        mod, cls = registry[id].split(":")
+        return getattr(importlib.import_module(mod), cls)(**kw)
+
+    reg.register = register
+    gym.make = make
+    gym.envs = envs
+    envs.registration = reg
+    for name, m in (("gym", gym), ("gym.envs", envs), ("gym.envs.registration", reg)):
+        monkeypatch.setitem(sys.modules, name, m)
+    return gym, registry
+
+
+def test_register_gym_ids_and_entry_points(monkeypatch):
+    """register_gym() registers the two ids of gym_swarm/__init__.py:6-14 and their entry points resolve to the drop-in
+    classes (construction needs a GPU: tests/test_gpu_parity.py::test_gym_make_roundtrip)."""
+    import importlib
+    from gym_swarm_b200 import envs
+    _, registry = _stub_gym(monkeypatch)
+    assert envs.register_gym() == ["Discrete-Swarm-v0", "Continuous-Swarm-v0"]
+    assert set(registry) == {"Discrete-Swarm-v0", "Continuous-Swarm-v0"}
+    for id_, cls in (("Discrete-Swarm-v0", envs.DiscreteSwarmEnv), ("Continuous-Swarm-v0", envs.ContinuousSwarmEnv)):
+        mod, name = registry[id_].split(":")
+        assert getattr(importlib.import_module(mod), name) is cls

@@ -428,6 +428,25 @@ def test_compat_surface_matches_reference_tests():
         env.close()
 
 
+def test_gym_make_roundtrip(monkeypatch):
+    """gym.make(id) -> the drop-in env (through a stand-in registry: gym itself is not in the image), one reference-style
+    episode fragment through the registered entry point."""
+    from test_abi import _stub_gym
+    from gym_swarm_b200 import envs
+    gym, _ = _stub_gym(monkeypatch)
+    envs.register_gym()
+    for id_ in ("Discrete-Swarm-v0", "Continuous-Swarm-v0"):
+        env = gym.make(id_)
+        state = env.reset()
+        assert len(state) == env.num_agents == 4
+        for _ in range(5):
+            if env.done:
+                env.reset()
+            state, reward, done, info = env.step({0: 0, 1: 1, 2: 2, 3: 3})
+            assert set(reward.keys()) == {0, 1, 2, 3, "global"}
+        env.close()
+
+
 def test_compat_env_lockstep_with_oracle():
     """SwarmEnv (dict API) reproduces the oracle step by step when fed the same tapes."""
     from gym_swarm_b200 import tapes
