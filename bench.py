@@ -53,6 +53,9 @@ CONFIGS = {
                  desc="configs[3]: 16 envs x 16,384 agents, 1024x1024 grid, pairwise dominated"),
     "cfg5": dict(E=1048576, N=8, S=16, per_agent=False, curriculum=False, place_extra=64,
                  desc="configs[4]: 1,048,576 envs x 8 agents, 16x16 grid, auto-reset + episode statistics"),
+    # not a BASELINE config: the 8-agents-per-lane shape of the lane-group kernels (N = 129 .. 256)
+    "n256": dict(E=32768, N=256, S=128, per_agent=True, curriculum=True,
+                 desc="32,768 envs x 256 agents, 128x128 grid, per-agent reward dict + curriculum (N = 129..256 kernel shape)"),
     # streaming shape for an honest DRAM number: 16 M envs x 8 agents
     "stream": dict(E=16777216, N=8, S=16, per_agent=False, curriculum=False, place_extra=64,
                    desc="streaming shape: 16,777,216 envs x 8 agents, 16x16 grid (>= 1 GB of traffic per launch)"),

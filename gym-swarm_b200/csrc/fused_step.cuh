@@ -533,7 +533,7 @@ __device__ __forceinline__ void box_near_counts(const unsigned* __restrict__ bit
 // (#far(t_repf) | #far(t_attf) << 16); then two u16 arrays of NMAX entries: the X lists (LX grows from the front, HX
 // from the back -- an agent is in at most one of them) and the Y lists.
 // Outputs aRf / aAf in the sweep's convention (self included): N - #{j != i : D_ij >= t}.
-template <int LPE, int APL>
+template <int LPE, int APL, bool RING_LAYOUT = true>
 __device__ __forceinline__ void far_border_counts(const StepParams& p, const Seg<LPE>& g, const uint4* __restrict__ spw,
                                                   unsigned* __restrict__ sfar, int N, int S, int i0,
                                                   const unsigned (&XI)[APL], const unsigned (&YI)[APL],
@@ -571,8 +571,10 @@ __device__ __forceinline__ void far_border_counts(const StepParams& p, const Seg
     if (jj >= nh) continue;
     const unsigned short* __restrict__ lst = yp ? yl : xl;
     const int a = lst[ii], c = lst[NMAX - 1 - jj];
-    // agent n sits in half n % 2 of pair word (n % APL / 2) * LPE + n / APL (the ring sweep's [word][lane] layout)
-    const uint4 wa = spw[((a % APL) >> 1) * LPE + a / APL], wc = spw[((c % APL) >> 1) * LPE + c / APL];
+    // agent n sits in half n % 2 of pair word (n % APL / 2) * LPE + n / APL (the ring sweep's [word][lane] layout) or of
+    // pair word n / 2 (the row sweep's linear layout)
+    const uint4 wa = spw[RING_LAYOUT ? ((a % APL) >> 1) * LPE + a / APL : a >> 1];
+    const uint4 wc = spw[RING_LAYOUT ? ((c % APL) >> 1) * LPE + c / APL : c >> 1];
     const int sa = 16 * (a & 1), sc = 16 * (c & 1);
     const int xa = (int)((wa.x >> sa) & 0xFFFFu), ya = (int)((wa.y >> sa) & 0xFFFFu);
     const int xc = (int)((wc.x >> sc) & 0xFFFFu), yc = (int)((wc.y >> sc) & 0xFFFFu);
@@ -608,7 +610,7 @@ struct FusedCfg {
   }
   __host__ __device__ static constexpr int vf_bytes(int vfm) { return EPW * vf_env_bytes(vfm); }
   // scratch of the far-threshold border pass (ring kernels): 4 list lengths + NMAX counters + 2 x NMAX u16 list entries
-  __host__ __device__ static constexpr int far_env_words() { return ring_ok() ? 4 + 2 * NMAX : 0; }
+  __host__ __device__ static constexpr int far_env_words() { return (ring_ok() || APL == 8) ? 4 + 2 * NMAX : 0; }
   __host__ __device__ static constexpr int far_bytes() { return EPW * far_env_words() * 4; }
 };
 
@@ -948,6 +950,22 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
         for (int k = 0; k < APL; ++k) { aV[k] = sacc[i0 + k]; accA[k] = sacc[C::NMAX + i0 + k]; accD[k] = sacc[2 * C::NMAX + i0 + k]; }
       }
       if (p.far_border) far_border_counts<LPE, APL>(p, g, spw, sfar, N, S, i0, XI, YI, aRf, aAf);
+    } else if (PHASE == 2 && VFM == 0 && APL == 8 && p.box_near && p.far_border) {
+      // N = 129 .. 256 (8 agents per lane, no ring sweep): in the reward launch all four counts come without a pair sweep --
+      // {rep, att} from box popcounts on the rebuilt (padded) occupancy bitmap, the far thresholds from the border pass
+      // (72 + ~30 instead of 8 x 128 word evaluations per lane at N = 256)
+      const int rB = max(max(p.t_rep, p.t_att) - 1, 0), bstride = (S >> 5) + 1;
+      int bx[APL], by[APL];
+#pragma unroll
+      for (int k = 0; k < APL; ++k) {
+        const bool v = i0 + k < N;
+        bx[k] = v ? nx[k] : 0;
+        by[k] = v ? ny[k] : 0;
+        if (v) atomicOr(&sbit[(ny[k] + rB) * bstride + (nx[k] >> 5)], 1u << (nx[k] & 31));
+      }
+      g.sync();
+      box_near_counts<APL>(sbit, S, p.t_rep - 1, p.t_att - 1, bx, by, aR, aA);
+      far_border_counts<LPE, APL, false>(p, g, spw, sfar, N, S, i0, XI, YI, aRf, aAf);
     } else {
       const int NW = (N + 1) >> 1;
 #pragma unroll 2

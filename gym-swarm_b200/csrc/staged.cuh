@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(1024) collide_kernel(const StepParams p, const
     int16_t* __restrict__ nx = sc.nx + base;
     int16_t* __restrict__ ny = sc.ny + base;
     uint8_t* __restrict__ eff = sc.eff + base;
-    const uint8_t* __restrict__ slab = p.slab + (size_t)env * (size_t)p.K;
+    const uint8_t* __restrict__ slab = p.slab ? p.slab + (size_t)env * (size_t)p.K : nullptr;
     int cur = 0;
     unsigned err = 0;
     for (;;) {
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(1024) collide_bitmap_kernel(const StepParams p
     int16_t* __restrict__ nx = sc.nx + base;
     int16_t* __restrict__ ny = sc.ny + base;
     uint8_t* __restrict__ eff = sc.eff + base;
-    const uint8_t* __restrict__ slab = p.slab + (size_t)env * (size_t)p.K;
+    const uint8_t* __restrict__ slab = p.slab ? p.slab + (size_t)env * (size_t)p.K : nullptr;
     int cur = 0;
     unsigned err = 0;
     // the thread's (<= 16) candidate positions live in registers for all rounds: re-reading them from global in every

@@ -214,7 +214,10 @@ def test_fused_reward_by_ring_sweep(N, S):
 
 @pytest.mark.parametrize("N,S,att,rep", [(16, 32, 5, 2), (24, 12, 5, 2), (33, 64, 5, 2), (64, 64, 9, 3), (100, 96, 16, 1),
                                          (128, 128, 5, 2), (128, 128, 2, 5), (128, 128, 0, 0), (128, 128, 17, 2),
-                                         (255, 64, 5, 2), (200, 300, 5, 2), (12, 5, 3, 1), (128, 256, 16, 16)])
+                                         (255, 64, 5, 2), (200, 300, 5, 2), (12, 5, 3, 1), (128, 256, 16, 16),
+                                         # 8 agents per lane (N = 129 .. 256): box popcounts + border pass without a pair sweep
+                                         (256, 128, 5, 2), (256, 128, 16, 16), (136, 96, 9, 3), (200, 64, 2, 5), (129, 32, 5, 2),
+                                         (256, 128, 0, 0), (248, 160, 17, 2)])
 @pytest.mark.parametrize("ring", [False, True])
 def test_two_launch_step(N, S, att, rep, ring):
     """The lane-group step as two launches (transition, then reward; the default from 2^22 agents per handle up, forced
