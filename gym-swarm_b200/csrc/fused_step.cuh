@@ -950,8 +950,9 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
         for (int k = 0; k < APL; ++k) { aV[k] = sacc[i0 + k]; accA[k] = sacc[C::NMAX + i0 + k]; accD[k] = sacc[2 * C::NMAX + i0 + k]; }
       }
       if (p.far_border) far_border_counts<LPE, APL>(p, g, spw, sfar, N, S, i0, XI, YI, aRf, aAf);
-    } else if (PHASE == 2 && VFM == 0 && APL == 8 && p.box_near && p.far_border) {
-      // N = 129 .. 256 (8 agents per lane, no ring sweep): in the reward launch all four counts come without a pair sweep --
+    } else if (PHASE != 1 && VFM == 0 && APL == 8 && p.box_near && p.far_border) {
+      // N = 129 .. 256 (8 agents per lane, no ring sweep; reward launch AND single launch -- the collision rounds left the
+      // bitmap clean): all four counts come without a pair sweep --
       // {rep, att} from box popcounts on the rebuilt (padded) occupancy bitmap, the far thresholds from the border pass
       // (72 + ~30 instead of 8 x 128 word evaluations per lane at N = 256)
       const int rB = max(max(p.t_rep, p.t_att) - 1, 0), bstride = (S >> 5) + 1;

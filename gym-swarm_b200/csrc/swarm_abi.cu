@@ -608,7 +608,7 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
   if (c->fused) {
     p.split = c->split ? 1 : 0;
     p.eff_buf = out->eff_action ? out->eff_action : c->eff_scratch;
-    p.box_near = (c->split && c->box_near && !vf) ? 1 : 0;
+    p.box_near = ((c->split || c->apl == 8) && c->box_near && !vf) ? 1 : 0;   // (8 agents per lane: in the single launch too)
     CUDA_TRY(c, fused_step_launch(c->lpe, c->apl, p, s));
     c->launches = c->split ? 2 : 1;
     return SWARM_OK;

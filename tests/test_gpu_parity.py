@@ -116,7 +116,7 @@ def _oracle_lockstep(E, N, S, T, seed, path="auto", att=5, rep=2, eat=-10.0, vf=
 
 @pytest.mark.parametrize("N,S", [(2, 4), (3, 5), (4, 20), (5, 9), (8, 16), (9, 16), (16, 32), (17, 12), (31, 40),
                                  (32, 32), (33, 64), (64, 64), (100, 48), (128, 128), (129, 50), (255, 64),
-                                 (256, 300)])
+                                 (256, 300), (256, 128), (200, 96), (136, 32)])
 def test_oracle_lockstep_fused_shapes(N, S):
     dense = S * S < 4 * N
     _oracle_lockstep(E=9, N=N, S=S, T=25, seed=N * 1000 + S, n_actions=9, K=512 if dense else None,
