@@ -9,7 +9,7 @@ python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${R}_bench_r
 python bench.py --steps 100 --warmup 10 --vf 5 --no-cpu-baseline --no-subconfigs > gpurun_out/${R}_bench_cfg3_vf5.json 2>/dev/null; echo vf5 rc=$?
 python bench.py --steps 200 --warmup 10 --flags 16 --no-cpu-baseline --no-subconfigs --no-e2e > gpurun_out/${R}_bench_cfg3_one_launch.json 2>/dev/null; echo one-launch rc=$?
 python bench.py --steps 200 --warmup 10 --flags 32 --no-cpu-baseline --no-subconfigs --no-e2e > gpurun_out/${R}_bench_cfg3_ring.json 2>/dev/null; echo ring rc=$?
-for c in cfg2 cfg4 cfg5 stream; do python bench.py --config $c --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/${R}_bench_$c.json 2> gpurun_out/${R}_bench_$c.err; echo $c rc=$?; done
+for c in cfg2 cfg4 cfg5 stream n256; do python bench.py --config $c --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/${R}_bench_$c.json 2> gpurun_out/${R}_bench_$c.err; echo $c rc=$?; done
 python tools/kernel_roofline.py > gpurun_out/${R}_kernel_roofline.jsonl 2> gpurun_out/kernel_roofline.err; echo kr rc=$?
 for c in cfg3 cfg4 cfg5; do
   B="python bench.py --config $c --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-subconfigs --graph off"
