@@ -391,12 +391,43 @@ def run_sub(job, name, steps, warmup, strong=True, graph=False, stats_every=0, T
     if graph:
         roll = env.capture_rollout(actions, retarget, slab, [curriculum_weights(t, cfg["curriculum"]) for t in range(T)])
         n_replays = max(1, -(-steps // T))
+        rps = max(1, stats_every // T) if stats_every else 0      # replays per statistics interval
+        if stats_every:
+            n_replays = max(2 * rps, -(-n_replays // rps) * rps)
         steps = n_replays * T
         for _ in range(max(3, -(-warmup // T))):
             roll.replay()
-        ms = job.timed(roll.replay, n_replays)
+        ms_plain = job.timed(roll.replay, n_replays)
+        ms = ms_plain
         rec["timed_loop"] = f"CUDA graph replays of {T} steps"
         rec["gpu_launches"] = int(roll.launches * n_replays)
+        if stats_every:
+            done_replays = [0]
+
+            def replay_with_stats():
+                roll.replay()
+                done_replays[0] += 1
+                if done_replays[0] % rps == 0:
+                    if pending[0] >= 3:                       # the oldest result: long finished, never blocks in practice
+                        env.stats_end(wait=True)
+                        pending[0] -= 1
+                    env.stats_begin(allreduce=world > 1)
+                    pending[0] += 1
+
+            ms = job.timed(replay_with_stats, n_replays)
+            results = []
+            while pending[0] > 0:
+                results.append(env.stats_end(wait=True))
+                pending[0] -= 1
+            rec["timed_loop"] = (f"CUDA graph replays of {T} steps (per-GPU batches of this config are launch bound in eager "
+                                 f"mode from 4 GPUs up); every {stats_every} steps swarm_stats_begin (multi-CTA reduction on the "
+                                 f"step stream, {'NCCL all-reduce of 8 doubles on the device buffer + ' if world > 1 else ''}"
+                                 f"D2H on the library's side stream), results collected 3 intervals later, no host sync")
+            rec["ms_per_step_without_stats"] = ms_plain / steps
+            rec["stats_overhead_frac"] = ms / ms_plain - 1.0
+            rec["stats_reductions_in_timed_loop"] = steps // stats_every
+            rec["episode_stats" + ("_allreduced" if world > 1 else "")] = results[-1] if results else None
+            rec["gpu_launches"] += 2 * (steps // stats_every)
     else:
         if stats_every:
             steps = max(2 * stats_every, -(-steps // stats_every) * stats_every)
@@ -639,7 +670,10 @@ def main():
         configs["cfg2"] = run_sub(job, "cfg2", steps=800, warmup=40, strong=False, graph=True)
         configs["cfg3_strong"] = run_sub(job, "cfg3", steps=100, warmup=10, strong=True)
         configs["cfg4"] = run_sub(job, "cfg4", steps=96, warmup=16, strong=True, graph=True)
-        configs["cfg5"] = run_sub(job, "cfg5", steps=3 * STATS_EVERY, warmup=10, strong=True, stats_every=STATS_EVERY)
+        # (from 4 ranks up the per-GPU batch of cfg5 is launch bound in eager mode: CUDA-graph replays there; the replays also
+        # record rewards / dones per step, which costs ~8 % where the step is GPU bound, so large batches stay eager)
+        configs["cfg5"] = run_sub(job, "cfg5", steps=3 * STATS_EVERY, warmup=10, strong=True, stats_every=STATS_EVERY,
+                                  graph=CONFIGS["cfg5"]["E"] // job.world <= 262144)
         if not args.no_e2e:
             configs["cfg3_e2e_terms"] = run_e2e_terms(job, cfg, h_actions, h_retarget, h_slab, T, numa)
 
