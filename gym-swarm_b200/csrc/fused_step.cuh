@@ -925,7 +925,7 @@ fused_step_kernel(const __grid_constant__ StepParams p) {
       // ALU pipe to the DPX ops.
       const unsigned one = (unsigned)p.one, c256 = (unsigned)p.one << 8;
       int nhit = 0;
-      if (PHASE == 2 && VFM == 0 && p.box_near) {
+      if (PHASE != 1 && VFM == 0 && p.box_near) {
         // reward launch: {rep, att} from box popcounts on the rebuilt (padded) occupancy bitmap; far thresholds below
         const int rB = max(max(p.t_rep, p.t_att) - 1, 0), bstride = (S >> 5) + 1;
         int bx[APL], by[APL];

@@ -31,6 +31,7 @@ struct Ctx {
   bool force_pairwise = false;  // SWARM_PATH_STAGED_PAIRWISE: never use the box-count reward path
   bool split = false;         // lane-group kernels: two launches per step (transition, reward), see fused_step_kernel
   bool box_near = false;      // ... and its reward launch may count {rep, att} by box popcounts
+  bool box_one_launch = false;      // non-vf steps: single launch with box popcounts (N > 32 or 8 agents per lane)
   uint8_t* eff_scratch = nullptr;   // [E,N] effective actions between the two launches (when the caller binds no eff_action)
   int lpe = 0, apl = 0;
   int bitmap_words = 0;
@@ -417,6 +418,7 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
       c->box_near = c->bitmap_words > 0 && (S % 32) == 0 && tp.t_rep <= 16 && tp.t_att <= 16 && tp.far_border && bw <= 2048 &&
                     !(cfg->flags & SWARM_FLAG_NO_BOX_NEAR);
       if (c->box_near) c->bitmap_words = std::max(c->bitmap_words, bw);
+      c->box_one_launch = c->box_near && (cfg->num_agents > 32) && !(cfg->flags & SWARM_FLAG_FUSED_SPLIT);
     }
     // (A box-count variant of the reward on this per-env bitmap was measured for the lane-group kernels in round 1:
     // 0.42-0.45 ms / step at cfg3 against 0.275 for the ring sweep -- the shared-memory gathers of 32 lanes into random
@@ -445,7 +447,9 @@ int swarm_create(const swarm_config* cfg, swarm_handle* out) {
     if (c->split) {
       const cudaError_t ae = cudaMalloc(&c->eff_scratch, (size_t)agents + 16);
       if (ae != cudaSuccess) { delete c; return fail(nullptr, SWARM_E_CUDA, "swarm_create: cudaMalloc (effective actions)"); }
-      if (!c->tiny) c->path_name += " x2 launches";
+      if (!c->tiny) c->path_name += (c->box_one_launch && c->apl != 8) ? "+box (vf: x2 launches)" : " x2 launches";
+    } else if (c->box_one_launch && !c->tiny) {
+      c->path_name += "+box";
     }
     const StepParams p0 = base_params(c);
     const cudaError_t pe = fused_prepare(c->lpe, c->apl, p0);
@@ -606,11 +610,17 @@ int swarm_step(swarm_handle h, const swarm_step_in* in, const swarm_step_out* ou
     return SWARM_OK;
   }
   if (c->fused) {
-    p.split = c->split ? 1 : 0;
+    // {rep, att} by box popcounts where they apply.  From 33 agents up they also pay in the single-launch kernel, and with
+    // them the single launch is at least as fast as two at every batch size (cfg3: 0.200 vs 0.201 ms at 65,536 envs,
+    // 0.033 vs 0.040 at 8,192), so such steps never split; vf_size steps and the ring-sweep shapes keep the split.
+    // (8 agents per lane: the single launch is the slower one at large batches -- 32,768 x 256: 0.363 vs 0.267 ms -- so
+    // that shape splits by size as before and takes the box counts in either mode)
+    const bool box_single = c->box_one_launch && !vf;
+    p.split = (c->split && !(box_single && c->apl != 8)) ? 1 : 0;
     p.eff_buf = out->eff_action ? out->eff_action : c->eff_scratch;
-    p.box_near = ((c->split || c->apl == 8) && c->box_near && !vf) ? 1 : 0;   // (8 agents per lane: in the single launch too)
+    p.box_near = ((p.split || box_single) && c->box_near && !vf) ? 1 : 0;
     CUDA_TRY(c, fused_step_launch(c->lpe, c->apl, p, s));
-    c->launches = c->split ? 2 : 1;
+    c->launches = p.split ? 2 : 1;
     return SWARM_OK;
   }
   // ---- staged path -------------------------------------------------------------------------------

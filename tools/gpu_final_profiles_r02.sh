@@ -7,7 +7,8 @@ R=r02
 python bench.py > gpurun_out/${R}_bench_default.json 2> gpurun_out/${R}_bench_default.err; echo default rc=$?
 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${R}_bench_reference_cfg3.json 2>/dev/null; echo ref rc=$?
 python bench.py --steps 100 --warmup 10 --vf 5 --no-cpu-baseline --no-subconfigs > gpurun_out/${R}_bench_cfg3_vf5.json 2>/dev/null; echo vf5 rc=$?
-python bench.py --steps 200 --warmup 10 --flags 16 --no-cpu-baseline --no-subconfigs --no-e2e > gpurun_out/${R}_bench_cfg3_one_launch.json 2>/dev/null; echo one-launch rc=$?
+python bench.py --steps 200 --warmup 10 --flags 8 --no-cpu-baseline --no-subconfigs --no-e2e > gpurun_out/${R}_bench_cfg3_two_launch.json 2>/dev/null; echo two-launch rc=$?
+python bench.py --steps 200 --warmup 10 --flags 48 --no-cpu-baseline --no-subconfigs --no-e2e > gpurun_out/${R}_bench_cfg3_one_launch_ring.json 2>/dev/null; echo one-launch-ring rc=$?
 python bench.py --steps 200 --warmup 10 --flags 32 --no-cpu-baseline --no-subconfigs --no-e2e > gpurun_out/${R}_bench_cfg3_ring.json 2>/dev/null; echo ring rc=$?
 for c in cfg2 cfg4 cfg5 stream n256; do python bench.py --config $c --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/${R}_bench_$c.json 2> gpurun_out/${R}_bench_$c.err; echo $c rc=$?; done
 python tools/kernel_roofline.py > gpurun_out/${R}_kernel_roofline.jsonl 2> gpurun_out/kernel_roofline.err; echo kr rc=$?
@@ -24,7 +25,7 @@ full() {  # <tag> <kernel regex> <skip> <count> <command...>
   fi
 }
 B3="python bench.py --config cfg3 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-subconfigs --graph off"
-full cfg3_fused fused_step 6 2 $B3
+full cfg3_fused fused_step 6 1 $B3
 [ -s gpurun_out/${R}_cfg3_fused.ncu-rep ] && python tools/ncu_regions.py gpurun_out/${R}_cfg3_fused.ncu-rep > gpurun_out/${R}_cfg3_fused_regions.txt
 full cfg3_vf5 fused_step 6 2 $B3 --vf 5
 full cfg5_tiny "tiny8_packed|tiny_step" 3 1 python bench.py --config cfg5 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-subconfigs --graph off

@@ -59,11 +59,16 @@ def summarise(tag):
 def main():
     traffic = json.load(open(os.path.join(PROF, "ncu_traffic.json")))
     pipe = json.load(open(os.path.join(PROF, "ncu_pipe.json")))
-    for tag, key in (("cfg3_fused", "cfg3:fused<32,4>+bitmap x2 launches"), ("cfg3_vf5", "cfg3:vf5:fused<32,4>+bitmap x2 launches"),
+    for tag, key in (("cfg3_fused", "cfg3:fused<32,4>+bitmap+box (vf: x2 launches)"), ("cfg3_vf5", "cfg3:vf5:fused<32,4>+bitmap+box (vf: x2 launches)"),
                      ("cfg5_tiny", "cfg5:tiny<8> (vf: fused<8,1>)"), ("cfg4_staged", "cfg4:staged+box (vf: staged pairwise)")):
         ks = summarise(tag)
         if not ks:
             continue
+        # a capture may hold several launches of the SAME kernel (several steps of a single-launch path): one per name
+        seen = {}
+        for k in ks:
+            seen.setdefault(k["kernel"], k)
+        ks = list(seen.values())
         rd, wr, us = sum(k["read"] for k in ks), sum(k["write"] for k in ks), sum(k["us"] for k in ks)
         names = " + ".join(k["kernel"].split("(")[0].replace("void ", "") for k in ks)
         traffic[key] = {"traffic_bytes": int(rd + wr),
