@@ -8,7 +8,7 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 CSRC=$ROOT/gym-swarm_b200/csrc
 OBJ=$ROOT/build/obj_$NAME
 mkdir -p $OBJ
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $@"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -diag-suppress=128 $@"
 pids=()
 for u in swarm_abi fused_launch fused_vf_launch tiny_launch; do
   (cd $CSRC && nvcc $FLAGS -c $u.cu -o $OBJ/$u.o) & pids+=($!)
