@@ -409,6 +409,37 @@ def test_errors_and_freeze():
     env2.close()
 
 
+def test_bad_action_ids_in_the_packed_kernel():
+    """Action ids > 8 in the packed 8-agent kernel: error bit, and the step is the one with id 8 (no move) in their place
+    (the scalar kernel's rule, tiny_step.cuh)."""
+    from gym_swarm_b200 import _lib
+    from gym_swarm_b200.envs import BatchedSwarmEnv
+    rng = np.random.default_rng(5)
+    E = 96
+    acts = rng.integers(0, 9, size=(6, E, 8)).astype(np.uint8)
+    bad = acts.copy()
+    mask = rng.random(size=bad.shape) < 0.05
+    mask[:, 0, :] = False                                   # env 0 stays clean
+    bad[mask] = rng.integers(9, 256, size=int(mask.sum())).astype(np.uint8)
+    clean = acts.copy()
+    clean[mask] = 8
+    envs = [BatchedSwarmEnv(E, 8, 16, auto_reset=True, per_agent=False, seed=3) for _ in range(2)]
+    assert envs[0].path_name.startswith("tiny<8>")
+    for e in envs:
+        e.reset()
+    for t in range(6):
+        envs[0].step(bad[t])
+        envs[1].step(clean[t])
+    a, b = envs[0].state_numpy(), envs[1].state_numpy()
+    for k in ("x", "y", "px", "py", "target"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    assert a["err"][0] == 0 and b["err"].max() == 0
+    hit = mask.any(axis=(0, 2))
+    assert np.all((a["err"][hit] & _lib.ERR_BAD_ACTION) != 0) and np.all(a["err"][~hit] == 0)
+    for e in envs:
+        e.close()
+
+
 def test_compat_surface_matches_reference_tests():
     """The reference's own smoke tests (gym_swarm/tests/test_discrete_swarm.py:12-40) against SwarmEnv."""
     from gym_swarm_b200.envs import ContinuousSwarmEnv, SwarmEnv
