@@ -313,6 +313,35 @@ def test_device_tapes_equal_host_materialised_tapes(E, N, S, path):
     env.close()
 
 
+def test_large_n_predator_stream_philox_and_frozen():
+    """predator_block_async_kernel inside swarm_step (N >= 4096, E % 4 == 0): the retarget flags drawn in the kernel
+    (device tapes) and frozen envs (auto_reset off; at 25 % density episodes end within a few steps)."""
+    from gym_swarm_b200 import tapes
+    from gym_swarm_b200.envs import BatchedSwarmEnv
+    from oracle import swarm_oracle as so
+    E, N, S, T, R, seed = 4, 4096, 128, 4, 8, 77
+    env = BatchedSwarmEnv(E, N, S, auto_reset=True, per_agent=False, debug_outputs=False, seed=seed, device_tapes=True,
+                          reset_slots=R, pred_attempts=32)
+    assert env.path_name.startswith("staged"), env.path_name
+    rt = tapes.philox_reset_tapes(env.reset_seed, R, E, N, S, KR=env.KR, KP=env.KP)
+    ora = so.OracleBatch(E, N, S, 5, 2, -10.0, True)
+    ora.set_reset_tapes(rt.place, rt.ptape)
+    env.reset()
+    ora.reset()
+    act_rng = np.random.default_rng(seed)
+    for t in range(T):
+        actions = act_rng.integers(0, 9, size=(E, N), dtype=np.uint8)
+        retarget, slab = tapes.philox_step_tapes(seed, t, E, env.K)
+        env.step(actions, {"attraction": 1.0, "repulsion": 0.5, "alignment": 0.25, "vf_size": None})
+        a = env.state_numpy()
+        b = ora.step(actions, slab, retarget, (1.0, 0.5, 0.25), None, False)
+        for k in ("x", "y", "px", "py", "target"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg=f"step {t} {k}")
+        np.testing.assert_array_equal(env.done.cpu().numpy(), b["done"], err_msg=f"step {t} done")
+    env.close()
+    _oracle_lockstep(E=4, N=4096, S=128, T=8, seed=9, n_actions=8, auto_reset=False, agent_out=False)
+
+
 def test_staged_path_names():
     from gym_swarm_b200.envs import BatchedSwarmEnv
     for kw, name in ((dict(path="auto"), "staged+box"), (dict(path="staged_pairwise"), "staged+bitmap")):
